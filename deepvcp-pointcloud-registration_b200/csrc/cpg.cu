@@ -1,0 +1,189 @@
+// Corresponding-point generation -- cpg.py:27-60.
+//
+//   cost[c', f'] = (src[f'] - T'[c', f'])^2, where T' re-reads the LOGICAL
+//   row-major order of the [32, C] target tensor as [C, 32] (quirk Q4);
+//   volume [32, G, G, G] -> Conv3d 32->16 -> 16->4 -> 4->1 (k=3, pad=1, bias, no
+//   activation) -> softmax over the C voxels -> vcp = sum w_c cand_c / sum w_c.
+//
+// v1: one thread per output voxel and layer; activations travel through an
+// L2-resident workspace laid out [M][channel][voxel] so that neighbouring threads
+// read neighbouring addresses; weights are re-ordered in shared memory to
+// [tap][cin][cout] so one LDS.128 feeds four FMAs.
+#include "common.cuh"
+
+namespace dvcp {
+
+__global__ void __launch_bounds__(256)
+cpg_cost_kernel(const float *__restrict__ src, const float *__restrict__ tgt, int layout, int C,
+                float *__restrict__ vol) {
+    const int64_t m = blockIdx.y;
+    const float *t = tgt + m * 32 * (int64_t)C;
+    const float *s = src + m * 32;
+    float *v = vol + m * 32 * (int64_t)C;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 32 * C; e += gridDim.x * blockDim.x) {
+        // e enumerates (f', c') with c' fastest so that the write is coalesced
+        const int f = e / C, c = e - f * C;
+        const int L = c * 32 + f;   // flat position in the logical [32, C] tensor
+        const float tv = layout == 0 ? __ldg(t + L) : __ldg(t + (int64_t)(L % C) * 32 + (L / C));
+        const float d = __ldg(s + f) - tv;
+        v[e] = d * d;
+    }
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+cpg_conv_kernel(const float *__restrict__ in, const float *__restrict__ w, const float *__restrict__ bias, int G,
+                float *__restrict__ out) {
+    extern __shared__ __align__(16) float sw[];   // [27][CIN][COUT]
+    const int C = G * G * G;
+    for (int i = threadIdx.x; i < 27 * CIN * COUT; i += blockDim.x) {
+        const int co = i % COUT, ci = (i / COUT) % CIN, tap = i / (COUT * CIN);
+        sw[i] = w[(co * CIN + ci) * 27 + tap];
+    }
+    __syncthreads();
+    const int64_t m = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const int iz = c % G, iy = (c / G) % G, ix = c / (G * G);
+    const float *src = in + m * CIN * (int64_t)C;
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = __ldg(bias + o);
+    for (int dx = -1; dx <= 1; ++dx) {
+        const int x = ix + dx;
+        if (x < 0 || x >= G) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = iy + dy;
+            if (y < 0 || y >= G) continue;
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int z = iz + dz;
+                if (z < 0 || z >= G) continue;
+                const int tap = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
+                const float *p = src + (x * G + y) * G + z;
+                const float *wt = sw + tap * CIN * COUT;
+#pragma unroll 4
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float v = __ldg(p + (int64_t)ci * C);
+                    if (COUT % 4 == 0) {
+                        const float4 *w4 = reinterpret_cast<const float4 *>(wt + ci * COUT);
+#pragma unroll
+                        for (int o = 0; o < COUT / 4; ++o) {
+                            const float4 ww = w4[o];
+                            acc[4 * o] = fmaf(ww.x, v, acc[4 * o]);
+                            acc[4 * o + 1] = fmaf(ww.y, v, acc[4 * o + 1]);
+                            acc[4 * o + 2] = fmaf(ww.z, v, acc[4 * o + 2]);
+                            acc[4 * o + 3] = fmaf(ww.w, v, acc[4 * o + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(wt[ci * COUT + o], v, acc[o]);
+                    }
+                }
+            }
+        }
+    }
+    float *dst = out + m * COUT * (int64_t)C + c;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) dst[(int64_t)o * C] = acc[o];
+}
+
+// softmax over the C voxels of one key-point + weighted candidate sum.
+__global__ void __launch_bounds__(256)
+cpg_softmax_vcp_kernel(const float *__restrict__ logits, const float *__restrict__ cand, int C,
+                       float *__restrict__ vcp) {
+    __shared__ float red[4][8];
+    const int64_t m = blockIdx.x;
+    const float *l = logits + m * C;
+    const float *cp = cand + m * C * 3;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float mx = -INFINITY;
+    for (int c = tid; c < C; c += blockDim.x) mx = fmaxf(mx, l[c]);
+#pragma unroll
+    for (int s = 16; s; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    if (lane == 0) red[0][warp] = mx;
+    __syncthreads();
+    mx = red[0][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[0][w]);
+    float z = 0.f;
+    for (int c = tid; c < C; c += blockDim.x) z += expf(l[c] - mx);
+#pragma unroll
+    for (int s = 16; s; s >>= 1) z += __shfl_xor_sync(0xffffffffu, z, s);
+    __syncthreads();
+    if (lane == 0) red[0][warp] = z;
+    __syncthreads();
+    z = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) z += red[0][w];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};   // sum w*x, w*y, w*z, sum w
+    for (int c = tid; c < C; c += blockDim.x) {
+        const float w = expf(l[c] - mx) / z;
+        a[0] = fmaf(w, cp[3 * c], a[0]);
+        a[1] = fmaf(w, cp[3 * c + 1], a[1]);
+        a[2] = fmaf(w, cp[3 * c + 2], a[2]);
+        a[3] += w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int s = 16; s; s >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], s);
+        if (lane == 0) red[k][warp] = a[k];
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            num += red[tid][w];
+            den += red[3][w];
+        }
+        vcp[m * 3 + tid] = num / den;
+    }
+}
+
+}  // namespace dvcp
+
+using namespace dvcp;
+
+extern "C" int64_t dvcp_cpg_workspace_bytes(int64_t M, int G) {
+    if (M <= 0 || G <= 0) return 0;
+    return M * (int64_t)G * G * G * (32 + 16 + 4 + 1) * (int64_t)sizeof(float);
+}
+
+extern "C" int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
+                        int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
+                        int64_t workspace_bytes, dvcp_stream_t stream) {
+    if (!src_dfe || !tgt_dfe || !cand || !vcp || !workspace || M <= 0 || G <= 0) return DVCP_E_ARG;
+    if (!p.w1 || !p.b1 || !p.w2 || !p.b2 || !p.w3 || !p.b3 || (layout != 0 && layout != 1)) return DVCP_E_ARG;
+    if (M > 65535 || G > 64) return DVCP_E_UNSUPPORTED;
+    if (workspace_bytes < dvcp_cpg_workspace_bytes(M, G)) return DVCP_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = G * G * G;
+    float *v0 = (float *)workspace;
+    float *v1 = v0 + M * 32 * (int64_t)C;
+    float *v2 = v1 + M * 16 * (int64_t)C;
+    float *v3 = v2 + M * 4 * (int64_t)C;
+    {
+        dim3 grid((32 * C + 255) / 256, (unsigned)M);
+        cpg_cost_kernel<<<grid, 256, 0, st>>>(src_dfe, tgt_dfe, layout, C, v0);
+        DVCP_CHECK_LAUNCH();
+    }
+    dim3 cgrid((C + 127) / 128, (unsigned)M);
+    {
+        auto k = cpg_conv_kernel<32, 16>;
+        const int smem = 27 * 32 * 16 * sizeof(float);
+        DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<cgrid, 128, smem, st>>>(v0, p.w1, p.b1, G, v1);
+        DVCP_CHECK_LAUNCH();
+    }
+    cpg_conv_kernel<16, 4><<<cgrid, 128, 27 * 16 * 4 * sizeof(float), st>>>(v1, p.w2, p.b2, G, v2);
+    DVCP_CHECK_LAUNCH();
+    cpg_conv_kernel<4, 1><<<cgrid, 128, 27 * 4 * 1 * sizeof(float), st>>>(v2, p.w3, p.b3, G, v3);
+    DVCP_CHECK_LAUNCH();
+    cpg_softmax_vcp_kernel<<<(unsigned)M, 256, 0, st>>>(v3, cand, C, vcp);
+    DVCP_CHECK_LAUNCH();
+    if (logits) DVCP_CUDA(cudaMemcpyAsync(logits, v3, M * (int64_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

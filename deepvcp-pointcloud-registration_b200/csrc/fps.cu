@@ -1,0 +1,334 @@
+// Farthest point sampling -- replaces pointnet2_utils.py:63-84 of the reference.
+//
+// Semantics: running minimum distance initialised to float32(1e10);
+// per round d = ((dx*dx) + (dy*dy)) + (dz*dz) with every operation rounded (no
+// FMA); dist[n] = d where d < dist[n]; next = FIRST index of the maximum.
+//
+// Two kernels:
+//  * fps_bucketed_kernel  (float32, N <= 16384): exact spatially-pruned FPS. The
+//    cloud is Morton-sorted into buckets of 32 points (one warp lane per point),
+//    each bucket keeps its bounding box and the (max dist, lowest index) of its
+//    members. A round only revisits buckets whose box lower bound -- evaluated
+//    with the same rounded arithmetic, hence never above any member's rounded
+//    distance -- is below the bucket's current maximum. Everything lives in
+//    shared memory / registers of ONE CTA per cloud; one __syncthreads per round.
+//  * fps_generic_kernel   (float32/float64, any N <= 57344): plain O(N * npoint).
+#include <cub/block/block_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace dvcp {
+
+// ------------------------------------------------------------------ generic --
+template <typename T>
+struct SqDist;
+template <>
+struct SqDist<float> {
+    __device__ static __forceinline__ float eval(float dx, float dy, float dz) {
+        return sq3_nofma(dx, dy, dz);
+    }
+};
+template <>
+struct SqDist<double> {
+    __device__ static __forceinline__ double eval(double dx, double dy, double dz) {
+        return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+fps_generic_kernel(const T *__restrict__ base, int64_t bs, int64_t ps, int64_t cs, int N, int npoint,
+                   const int64_t *__restrict__ start, int64_t *__restrict__ out64,
+                   int32_t *__restrict__ out32) {
+    extern __shared__ float s_dist[];
+    __shared__ unsigned s_hi[2][32], s_lo[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T *p = base + (int64_t)b * bs;
+    for (int n = tid; n < N; n += blockDim.x) s_dist[n] = 1e10f;
+    unsigned far = (unsigned)start[b];
+    __syncthreads();
+    for (int i = 0; i < npoint; ++i) {
+        if (tid == 0) {
+            if (out64) out64[(int64_t)b * npoint + i] = far;
+            if (out32) out32[(int64_t)b * npoint + i] = (int32_t)far;
+        }
+        const T cx = p[(int64_t)far * ps], cy = p[(int64_t)far * ps + cs], cz = p[(int64_t)far * ps + 2 * cs];
+        unsigned hi = 0u, lo = 0u;
+        for (int n = tid; n < N; n += blockDim.x) {
+            const T x = p[(int64_t)n * ps], y = p[(int64_t)n * ps + cs], z = p[(int64_t)n * ps + 2 * cs];
+            const T d = SqDist<T>::eval(x - cx, y - cy, z - cz);
+            float cur = s_dist[n];
+            if (d < (T)cur) {
+                cur = (float)d;
+                s_dist[n] = cur;
+            }
+            const unsigned bits = __float_as_uint(cur);
+            const unsigned l = 0xffffffffu - (unsigned)n;
+            if (bits > hi || (bits == hi && l > lo)) {
+                hi = bits;
+                lo = l;
+            }
+        }
+        warp_max_pair(hi, lo);
+        if (lane == 0) {
+            s_hi[i & 1][warp] = hi;
+            s_lo[i & 1][warp] = lo;
+        }
+        __syncthreads();
+        hi = s_hi[i & 1][lane];
+        lo = s_lo[i & 1][lane];
+        warp_max_pair(hi, lo);
+        far = 0xffffffffu - lo;
+    }
+}
+
+// ----------------------------------------------------------------- bucketed --
+__device__ __forceinline__ unsigned expand_bits10(unsigned v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// WARPS warps; each warp owns 32 buckets of 32 points: capacity WARPS * 1024.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int64_t cs, int N,
+                    int npoint, const int64_t *__restrict__ start, int64_t *__restrict__ out64,
+                    int32_t *__restrict__ out32) {
+    constexpr int THREADS = WARPS * 32;
+    constexpr int CAP = WARPS * 1024;
+    constexpr int ITEMS = 32;
+    using Sort = cub::BlockRadixSort<unsigned, THREADS, ITEMS, unsigned>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sx = reinterpret_cast<float *>(smem_raw);
+    float *sy = sx + CAP;
+    float *sz = sy + CAP;
+    unsigned short *sidx = reinterpret_cast<unsigned short *>(sz + CAP);
+    __shared__ unsigned s_hi[2][WARPS], s_lo[2][WARPS];
+    __shared__ float s_box[6][WARPS];
+    __shared__ unsigned s_startpos;
+
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float *p = base + (int64_t)b * bs;
+    const unsigned startidx = (unsigned)start[b];
+
+    // ---- cloud bounding box -> Morton keys -> block sort (prologue, once) ----
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int n = tid; n < N; n += THREADS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = __ldg(p + (int64_t)n * ps + c * cs);
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = warp_min_f(mn[c]);
+        mx[c] = warp_max_f(mx[c]);
+        if (lane == 0) {
+            s_box[c][warp] = mn[c];
+            s_box[3 + c][warp] = mx[c];
+        }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float a = INFINITY, z = -INFINITY;
+        for (int w = 0; w < WARPS; ++w) {
+            a = fminf(a, s_box[c][w]);
+            z = fmaxf(z, s_box[3 + c][w]);
+        }
+        mn[c] = a;
+        scale[c] = (z > a) ? 1023.0f / (z - a) : 0.0f;
+    }
+    unsigned keys[ITEMS], vals[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int n = tid * ITEMS + i;
+        if (n < N) {
+            unsigned q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = (__ldg(p + (int64_t)n * ps + c * cs) - mn[c]) * scale[c];
+                q[c] = (unsigned)fminf(fmaxf(v, 0.0f), 1023.0f);
+            }
+            keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+            vals[i] = (unsigned)n;
+        } else {
+            keys[i] = 0xffffffffu;   // sentinels sort last
+            vals[i] = 0xffffu;
+        }
+    }
+    __syncthreads();
+    Sort(*reinterpret_cast<typename Sort::TempStorage *>(smem_raw)).Sort(keys, vals, 0, 30 + 2);
+    __syncthreads();   // temp storage aliased with sx/sy/sz/sidx: done with it
+    // thread `tid` now holds sorted positions tid*32 .. tid*32+31 (= bucket `tid`)
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int pos = tid * ITEMS + i;
+        const unsigned n = vals[i];
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (n != 0xffffu) {
+            x = __ldg(p + (int64_t)n * ps);
+            y = __ldg(p + (int64_t)n * ps + cs);
+            z = __ldg(p + (int64_t)n * ps + 2 * cs);
+            if (n == startidx) s_startpos = (unsigned)pos;
+        }
+        sx[pos] = x;
+        sy[pos] = y;
+        sz[pos] = z;
+        sidx[pos] = (unsigned short)n;
+    }
+    __syncthreads();
+
+    // ---- per-lane state: dist[k] = point `lane` of bucket (warp*32 + k);
+    //      lane k additionally owns bucket k's box and (max dist, tie word). ----
+    const int wbase = warp * 1024;
+    float dist[32];
+    float bminx = 0.f, bminy = 0.f, bminz = 0.f, bmaxx = 0.f, bmaxy = 0.f, bmaxz = 0.f;
+    unsigned bval = 0u, blo = 0u;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int pos = wbase + k * 32 + lane;
+        const bool valid = sidx[pos] != 0xffffu;
+        dist[k] = valid ? 1e10f : 0.0f;
+        const float x = sx[pos], y = sy[pos], z = sz[pos];
+        const float a0 = warp_min_f(valid ? x : INFINITY), a1 = warp_min_f(valid ? y : INFINITY),
+                    a2 = warp_min_f(valid ? z : INFINITY);
+        const float z0 = warp_max_f(valid ? x : -INFINITY), z1 = warp_max_f(valid ? y : -INFINITY),
+                    z2 = warp_max_f(valid ? z : -INFINITY);
+        unsigned hi = __float_as_uint(dist[k]);
+        unsigned lo = ((0xffffu - (unsigned)sidx[pos]) << 16) | (unsigned)pos;
+        warp_max_pair(hi, lo);
+        if (lane == k) {
+            bminx = a0; bminy = a1; bminz = a2;
+            bmaxx = z0; bmaxy = z1; bmaxz = z2;
+            bval = hi; blo = lo;
+        }
+    }
+
+    unsigned pos = s_startpos, idx = startidx;
+    for (int i = 0; i < npoint; ++i) {
+        if (tid == 0) {
+            if (out64) out64[(int64_t)b * npoint + i] = idx;
+            if (out32) out32[(int64_t)b * npoint + i] = (int32_t)idx;
+        }
+        const float cx = sx[pos], cy = sy[pos], cz = sz[pos];
+        // lower bound of the rounded distance to any member of my bucket
+        const float ex = fmaxf(fmaxf(__fsub_rn(bminx, cx), __fsub_rn(cx, bmaxx)), 0.0f);
+        const float ey = fmaxf(fmaxf(__fsub_rn(bminy, cy), __fsub_rn(cy, bmaxy)), 0.0f);
+        const float ez = fmaxf(fmaxf(__fsub_rn(bminz, cz), __fsub_rn(cz, bmaxz)), 0.0f);
+        const float lb = sq3_nofma(ex, ey, ez);
+        const unsigned mask = __ballot_sync(0xffffffffu, lb < __uint_as_float(bval));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (!(mask & (0xffu << (8 * g)))) continue;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int k = g * 8 + kk;
+                if (!(mask & (1u << k))) continue;
+                const int pp = wbase + k * 32 + lane;
+                const float d = sq3_nofma(__fsub_rn(sx[pp], cx), __fsub_rn(sy[pp], cy), __fsub_rn(sz[pp], cz));
+                if (d < dist[k]) dist[k] = d;
+                unsigned hi = __float_as_uint(dist[k]);
+                unsigned lo = ((0xffffu - (unsigned)sidx[pp]) << 16) | (unsigned)pp;
+                warp_max_pair(hi, lo);
+                if (lane == k) {
+                    bval = hi;
+                    blo = lo;
+                }
+            }
+        }
+        unsigned hi = bval, lo = blo;
+        warp_max_pair(hi, lo);
+        if (WARPS > 1) {
+            if (lane == 0) {
+                s_hi[i & 1][warp] = hi;
+                s_lo[i & 1][warp] = lo;
+            }
+            __syncthreads();
+            hi = lane < WARPS ? s_hi[i & 1][lane] : 0u;
+            lo = lane < WARPS ? s_lo[i & 1][lane] : 0u;
+            warp_max_pair(hi, lo);
+        }
+        pos = lo & 0xffffu;
+        idx = 0xffffu - (lo >> 16);
+    }
+}
+
+template <int WARPS>
+static int launch_bucketed(const dvcp_cloud_t &c, int B, int N, int npoint, const int64_t *start,
+                           int64_t *o64, int32_t *o32, cudaStream_t st) {
+    constexpr int CAP = WARPS * 1024;
+    using Sort = cub::BlockRadixSort<unsigned, WARPS * 32, 32, unsigned>;
+    size_t data = (size_t)CAP * (3 * sizeof(float) + sizeof(unsigned short));
+    size_t smem = data > sizeof(typename Sort::TempStorage) ? data : sizeof(typename Sort::TempStorage);
+    auto k = fps_bucketed_kernel<WARPS>;
+    DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B, WARPS * 32, smem, st>>>((const float *)c.base, c.bstride, c.pstride, c.cstride, N, npoint,
+                                   start, o64, o32);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace dvcp
+
+extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, const int64_t *start,
+                        int64_t *out64, int32_t *out32, dvcp_stream_t stream) {
+    using namespace dvcp;
+    if (!xyz.base || !start || (!out64 && !out32) || B <= 0 || N <= 0 || npoint <= 0) return DVCP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 0 && N <= 16384 && N >= 64) {
+        if (N <= 1024) return launch_bucketed<1>(xyz, B, N, npoint, start, out64, out32, st);
+        if (N <= 2048) return launch_bucketed<2>(xyz, B, N, npoint, start, out64, out32, st);
+        if (N <= 4096) return launch_bucketed<4>(xyz, B, N, npoint, start, out64, out32, st);
+        if (N <= 8192) return launch_bucketed<8>(xyz, B, N, npoint, start, out64, out32, st);
+        return launch_bucketed<16>(xyz, B, N, npoint, start, out64, out32, st);
+    }
+    if (N > 57344) return DVCP_E_UNSUPPORTED;
+    size_t smem = (size_t)N * sizeof(float);
+    if (dtype == 0) {
+        auto k = fps_generic_kernel<float>;
+        DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<B, 1024, smem, st>>>((const float *)xyz.base, xyz.bstride, xyz.pstride, xyz.cstride, N, npoint,
+                                 start, out64, out32);
+    } else if (dtype == 1) {
+        auto k = fps_generic_kernel<double>;
+        DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<B, 1024, smem, st>>>((const double *)xyz.base, xyz.bstride, xyz.pstride, xyz.cstride, N, npoint,
+                                 start, out64, out32);
+    } else {
+        return DVCP_E_ARG;
+    }
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+// Test hook: force the plain kernel for float32 clouds (parity of the two paths).
+extern "C" int dvcp_fps_plain(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start,
+                              int64_t *out64, dvcp_stream_t stream) {
+    using namespace dvcp;
+    if (!xyz.base || !start || !out64 || B <= 0 || N <= 0 || npoint <= 0) return DVCP_E_ARG;
+    if (N > 57344) return DVCP_E_UNSUPPORTED;
+    size_t smem = (size_t)N * sizeof(float);
+    auto k = fps_generic_kernel<float>;
+    DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B, 1024, smem, (cudaStream_t)stream>>>((const float *)xyz.base, xyz.bstride, xyz.pstride,
+                                               xyz.cstride, N, npoint, start, out64, nullptr);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,108 @@
+"""DeepVCP -- deepVCP.py:16-110 of the reference: the registration forward.
+
+Same constructor, forward signature, tensor layouts and state_dict keys; the
+hyper-parameters the reference hard-codes become keyword arguments whose
+defaults are the reference's literals. forward() is a fixed sequence of
+sm_100a kernels (no tensor of the reference larger than the KNN result is
+materialised):
+
+    FPS(src), FPS(tgt)                      pointnet2_utils.py:63-84
+    SA layer(src), SA layer(tgt)            :110-138,176-202 fused
+    weighting MLP + top-K                   weighting_layer.py:26-33
+    key-point stage                         deepVCP.py:44-67,86-91,101
+    candidate grid                          voxelize.py:19-83
+    KNN                                     get_cat_feat_tgt.py:45-52
+    gather + normalise + DFE + max          get_cat_feat_tgt.py:53-96, deep_feat_embedding.py:46-60
+    CPG                                     cpg.py:27-60
+
+B > 1 means B independent pairs (the reference only runs B = 1).
+Reference-mode quirks are on by default and individually
+switchable through `quirks`.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from ._lib import QUIRKS_REFERENCE, cloud_cm, require_cuda
+from .cpg import cpg
+from .deep_feat_embedding import feat_embedding_layer
+from .deep_feat_extraction import feat_extraction_layer
+from .weighting_layer import weighting_layer
+
+
+class DeepVCP(nn.Module):
+    def __init__(self, use_normal, npoint=10000, fe_radius=0.1, fe_nsample=256, K_topk=64, nsample=32,
+                 r=1.0, s=0.4, group_radius=1, quirks=QUIRKS_REFERENCE):
+        super().__init__()
+        self.FE1 = feat_extraction_layer(use_normal=use_normal, npoint=npoint, radius=fe_radius,
+                                         nsample=fe_nsample)
+        self.WL = weighting_layer()
+        self.DFE = feat_embedding_layer()
+        self.cpg = cpg()
+        self.K_topk, self.nsample, self.r, self.s = K_topk, nsample, r, s
+        self.group_radius = group_radius
+        self.quirks = quirks
+        self.last = None   # stage tensors of the most recent forward (for tests / inspection)
+
+    def draw_starts(self, B, N):
+        """The three FPS start draws of one forward in the reference's order:
+        FE(src) -> key-point grouping -> FE(tgt) (deepVCP.py:29,54,72)."""
+        return (F_.draw_fps_start(B, N), F_.draw_fps_start(B, self.K_topk), F_.draw_fps_start(B, N))
+
+    def forward(self, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=False, topk_override=None):
+        """src_pts, tgt_pts [B,C_in,N]; R_init [B,3,3] float64; t_init [1,3] (unused by
+        the reference, quirk Q6) -> (src_keypts [B,K,3], tgt_vcp [B,K,3])."""
+        if self.training:
+            raise RuntimeError("DeepVCP (b200) is the inference path: call .eval() first")
+        if src_pts.dtype != torch.float32 or tgt_pts.dtype != torch.float32:
+            raise NotImplementedError("float32 clouds only (the reference's float64 promotion is not accelerated)")
+        dev = self.cpg.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("DeepVCP (b200) needs its parameters on a CUDA device; there is no CPU fallback")
+        B, C_in, N = src_pts.shape
+        if starts is None:
+            starts = self.draw_starts(B, N)
+        # host tensors (pinned or not) are accepted at the boundary and copied once
+        src = src_pts.to(dev, non_blocking=True).contiguous()
+        tgt = tgt_pts.to(dev, non_blocking=True).contiguous()
+        R = R_init.to(dev, non_blocking=True)
+        require_cuda(src, tgt, R)
+        S = self.FE1.sa1.npoint
+        K, ns = self.K_topk, self.nsample
+        sa = self.FE1.sa1
+        mlp = sa.folded()
+        D = C_in - 3
+        with torch.no_grad():
+            # feature extraction, both clouds (FPS order)
+            _, sfps = F_.fps(cloud_cm(src), dev, src.dtype, B, N, S, starts[0], want64=False, want32=True)
+            _, tfps = F_.fps(cloud_cm(tgt), dev, tgt.dtype, B, N, S, starts[2], want64=False, want32=True)
+            sfeat_cloud = cloud_cm(src[:, 3:, :]) if D else None
+            tfeat_cloud = cloud_cm(tgt[:, 3:, :]) if D else None
+            _, sfeat = F_.sa_layer(cloud_cm(src), sfeat_cloud, D, sfps, B, N, S, sa.radius, sa.nsample, mlp, dev,
+                                   want_xyz=False)
+            _, tfeat = F_.sa_layer(cloud_cm(tgt), tfeat_cloud, D, tfps, B, N, S, sa.radius, sa.nsample, mlp, dev,
+                                   want_xyz=False)
+            # key-point selection
+            scores = self.WL.scores(sfeat)
+            topk = F_.topk(scores, K) if topk_override is None else topk_override.to(dev).view(B, K)
+            dfe = self.DFE.params()
+            keypts, picked, cat, src_dfe, centres = F_.keypoint_stage(
+                src, topk, starts[1], sfeat, R, self.group_radius, ns, dfe, self.quirks,
+                want_cat=keep_stages, want_picked=keep_stages)
+            # candidates, KNN, target-side embedding
+            G = F_.grid_size(self.r, self.s)
+            cand = F_.candidates(centres, self.r, self.s, G)                 # [B,K,C,3]
+            C = G * G * G
+            kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
+                                    want32=True)
+            tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
+                                       self.quirks)                            # [B,K*C,32]
+            # corresponding point generation
+            vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.view(B * K, C * 32), 1,
+                                 cand.view(B * K, C, 3), G, self.cpg.params(), want_logits=keep_stages)
+        if keep_stages:
+            self.last = dict(src_fps=sfps, tgt_fps=tfps, src_fe_feat=sfeat, tgt_fe_feat=tfeat, scores=scores,
+                             topk_idx=topk, src_keypts_full=keypts, picked_idx=picked, src_cat=cat,
+                             src_dfe=src_dfe, centres=centres, candidates=cand, knn_dist=kd, knn_idx=ki64,
+                             tgt_dfe=tgt_dfe.view(B, K, C, 32), logits=logits, vcp=vcp.view(B, K, 3))
+        return keypts[:, :, :3], vcp.view(B, K, 3)

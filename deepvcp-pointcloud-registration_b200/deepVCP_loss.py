@@ -1,0 +1,31 @@
+"""Pose solve -- deepVCP_loss.py:13-90 of the reference (loss value itself is
+training-only and out of scope)."""
+import torch
+
+from . import functional as F_
+
+
+def get_rigid_transform(x, y):
+    """x, y [B,3,N] -> R [B,3,3], t [B,3,1] (reference :13-44): Kabsch with
+    R = V U^T and no reflection correction (quirk Q10). Computed in float64 and
+    returned in the input dtype."""
+    R, t = F_.kabsch(x, y)
+    return R.to(x.dtype), t.to(x.dtype)
+
+
+def svd_optimization(x, y_pred, R_true, t_true):
+    """Reference :57-90: solve, drop the 20 % of points with the largest 1-NN
+    distance to the ground-truth transform of x, solve again.
+    Returns R2, t2, x1, y_pred2 like the reference would for its inlier set; the
+    inlier tensors are not materialised here (None)."""
+    R2, t2, _, _ = F_.kabsch_refine(x, y_pred, R_true, t_true)
+    return R2, t2, None, None
+
+
+def pose_from_forward(src_keypts, tgt_vcp, R_true, t_true):
+    """train.py:110 -> deepVCP_loss.py:105-107,121: permute to [B,3,N], double,
+    two-stage solve. Returns R [B,3,3], t [B,3,1] float64."""
+    x = src_keypts.permute(0, 2, 1).double()
+    y = tgt_vcp.permute(0, 2, 1).double()
+    R2, t2, _, _ = F_.kabsch_refine(x, y, R_true, t_true)
+    return R2, t2

@@ -1,0 +1,263 @@
+"""Tensor-level wrappers of the C ABI: allocate outputs with torch, pass raw
+pointers and the current stream, raise on any non-zero return code.
+
+Clouds may be passed either point-major `[B, N, 3]` or channel-major
+`[B, C, N]` views with arbitrary strides; they are read in place.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (Cloud, MlpLayer, NULL_CLOUD, check, cloud_cm, cloud_pm, lib, ptr, require_cuda,
+                   stream_ptr)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError("expected a float32 tensor, got %s" % t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _starts_to_device(start, B, device):
+    start = torch.as_tensor(start, dtype=torch.int64).reshape(-1)
+    if start.numel() != B:
+        raise RuntimeError("need one FPS start index per cloud")
+    return start.to(device, non_blocking=True)
+
+
+def draw_fps_start(B: int, N: int) -> torch.Tensor:
+    """The reference draws the first FPS index on the CPU default generator
+    (pointnet2_utils.py:75); doing the same keeps torch.manual_seed runs aligned."""
+    return torch.randint(0, N, (B,), dtype=torch.long)
+
+
+# --------------------------------------------------------------------------- #
+def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want32=False):
+    start = _starts_to_device(start, B, device)
+    o64 = torch.empty(B, npoint, dtype=torch.int64, device=device) if want64 else None
+    o32 = torch.empty(B, npoint, dtype=torch.int32, device=device) if want32 else None
+    code = lib().dvcp_fps(xyz_cloud, 0 if dtype == torch.float32 else 1, B, N, npoint, ptr(start), ptr(o64),
+                          ptr(o32), stream_ptr(device))
+    check(code, "dvcp_fps")
+    return o64, o32
+
+
+def fps_plain(xyz_pm, npoint, start):
+    require_cuda(xyz_pm)
+    B, N, _ = xyz_pm.shape
+    start = _starts_to_device(start, B, xyz_pm.device)
+    out = torch.empty(B, npoint, dtype=torch.int64, device=xyz_pm.device)
+    check(lib().dvcp_fps_plain(cloud_pm(xyz_pm), B, N, npoint, ptr(start), ptr(out), stream_ptr(xyz_pm.device)),
+          "dvcp_fps_plain")
+    return out
+
+
+def square_distance(src_pm, dst_pm):
+    require_cuda(src_pm, dst_pm)
+    B, S, _ = src_pm.shape
+    N = dst_pm.shape[1]
+    out = torch.empty(B, S, N, dtype=torch.float32, device=src_pm.device)
+    check(lib().dvcp_square_distance(cloud_pm(src_pm), cloud_pm(dst_pm), B, S, N, ptr(out),
+                                     stream_ptr(src_pm.device)), "dvcp_square_distance")
+    return out
+
+
+def radius2_f32(radius) -> float:
+    """float32(radius ** 2): the comparison constant of pointnet2_utils.py:102."""
+    return float(np.float32(float(radius) ** 2))
+
+
+def ball_query(radius, nsample, xyz_pm, new_xyz_pm):
+    require_cuda(xyz_pm, new_xyz_pm)
+    B, N, _ = xyz_pm.shape
+    S = new_xyz_pm.shape[1]
+    out = torch.empty(B, S, nsample, dtype=torch.int64, device=xyz_pm.device)
+    check(lib().dvcp_ball_query(cloud_pm(xyz_pm), cloud_pm(new_xyz_pm), B, N, S, radius2_f32(radius), nsample,
+                                ptr(out), stream_ptr(xyz_pm.device)), "dvcp_ball_query")
+    return out
+
+
+def index_points(points, idx):
+    require_cuda(points, idx)
+    B, N, C = points.shape
+    points = _f32c(points)
+    idx = idx.contiguous().to(torch.int64)
+    M = idx[0].numel()
+    out = torch.empty(*idx.shape, C, dtype=torch.float32, device=points.device)
+    check(lib().dvcp_index_points(ptr(points), ptr(idx), B, N, C, M, ptr(out), stream_ptr(points.device)),
+          "dvcp_index_points")
+    return out
+
+
+class FoldedMlp:
+    """Device copies of the folded shared-MLP parameters (conv1x1 + eval BN)."""
+
+    def __init__(self, convs, bns):
+        self.tensors = []
+        self.layers = (MlpLayer * len(convs))()
+        for i, (conv, bn) in enumerate(zip(convs, bns)):
+            W = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float().contiguous()
+            b = conv.bias.detach().float().contiguous()
+            invstd = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+            alpha = (bn.weight.detach().float() * invstd).contiguous()
+            beta = (bn.bias.detach().float() - bn.running_mean.detach().float() * alpha).contiguous()
+            self.tensors += [W, b, alpha, beta]
+            self.layers[i] = MlpLayer(W.data_ptr(), b.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                                      conv.in_channels, conv.out_channels)
+        self.n = len(convs)
+        self.out_ch = convs[-1].out_channels
+
+
+def sa_layer(xyz_cloud, feats_cloud, D, centroid_idx32, B, N, S, radius, nsample, mlp: FoldedMlp, device,
+             want_xyz=True):
+    out = torch.empty(B, S, mlp.out_ch, dtype=torch.float32, device=device)
+    oxyz = torch.empty(B, S, 3, dtype=torch.float32, device=device) if want_xyz else None
+    code = lib().dvcp_sa_layer(xyz_cloud, feats_cloud if D > 0 else NULL_CLOUD, D, ptr(centroid_idx32), B, N, S,
+                               radius2_f32(radius), nsample, mlp.layers, mlp.n, ptr(out), ptr(oxyz),
+                               stream_ptr(device))
+    check(code, "dvcp_sa_layer")
+    return oxyz, out
+
+
+def weighting_scores(X, W1, b1, W2, b2, W3, b3):
+    require_cuda(X)
+    B, S, _ = X.shape
+    X = _f32c(X)
+    scores = torch.empty(B, S, dtype=torch.float32, device=X.device)
+    check(lib().dvcp_weighting_scores(ptr(X), B, S, ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
+                                      ptr(scores), stream_ptr(X.device)), "dvcp_weighting_scores")
+    return scores
+
+
+def topk(scores, K):
+    require_cuda(scores)
+    B, S = scores.shape
+    scores = _f32c(scores)
+    out = torch.empty(B, K, dtype=torch.int64, device=scores.device)
+    check(lib().dvcp_topk(ptr(scores), B, S, K, ptr(out), stream_ptr(scores.device)), "dvcp_topk")
+    return out
+
+
+def keypoint_stage(src_pts, topk_idx, kp_start, src_feat, R_init, radius, nsample, dfe, quirks,
+                   want_cat=False, want_picked=False):
+    require_cuda(src_pts, topk_idx, src_feat, R_init)
+    B, C_in, N = src_pts.shape
+    Kp = topk_idx.shape[1]
+    S = src_feat.shape[1]
+    dev = src_pts.device
+    src_pts = _f32c(src_pts)
+    src_feat = _f32c(src_feat)
+    R_init = R_init.to(torch.float64).contiguous()
+    kp_start = _starts_to_device(kp_start, B, dev)
+    keypts = torch.empty(B, Kp, C_in, dtype=torch.float32, device=dev)
+    picked = torch.empty(B, Kp, nsample, dtype=torch.int64, device=dev) if want_picked else None
+    cat = torch.empty(B, Kp, nsample, 35, dtype=torch.float32, device=dev) if want_cat else None
+    sdfe = torch.empty(B, Kp, 32, dtype=torch.float32, device=dev)
+    centres = torch.empty(B, Kp, 3, dtype=torch.float64, device=dev)
+    code = lib().dvcp_keypoint_stage(ptr(src_pts), C_in, B, N, ptr(topk_idx.contiguous()), Kp, ptr(kp_start),
+                                     ptr(src_feat), S, ptr(R_init), radius2_f32(radius), nsample, dfe, quirks,
+                                     ptr(keypts), ptr(picked), ptr(cat), ptr(sdfe), ptr(centres), stream_ptr(dev))
+    check(code, "dvcp_keypoint_stage")
+    return keypts, picked, cat, sdfe, centres
+
+
+def grid_size(r, s) -> int:
+    g = lib().dvcp_grid_size(float(r), float(s))
+    if g <= 0:
+        check(g, "dvcp_grid_size")
+    return g
+
+
+def candidates(centres, r, s, G=None):
+    require_cuda(centres)
+    centres = centres.to(torch.float64).contiguous()
+    lead = centres.shape[:-1]
+    M = centres.numel() // 3
+    G = grid_size(r, s) if G is None else G
+    out = torch.empty(*lead, G * G * G, 3, dtype=torch.float32, device=centres.device)
+    check(lib().dvcp_candidates(ptr(centres), M, float(r), float(s), G, ptr(out), stream_ptr(centres.device)),
+          "dvcp_candidates")
+    return out
+
+
+def knn(ref_cloud, device, B, N, query, K, want64=True, want32=False):
+    require_cuda(query)
+    query = _f32c(query)
+    Q = query.shape[1]
+    dist = torch.empty(B, Q, K, dtype=torch.float32, device=device)
+    i64 = torch.empty(B, Q, K, dtype=torch.int64, device=device) if want64 else None
+    i32 = torch.empty(B, Q, K, dtype=torch.int32, device=device) if want32 else None
+    check(lib().dvcp_knn(ref_cloud, ptr(query), B, N, Q, K, ptr(dist), ptr(i64), ptr(i32), stream_ptr(device)),
+          "dvcp_knn")
+    return dist, i64, i32
+
+
+def dfe_tgt_fused(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, dfe, quirks):
+    require_cuda(cand, tgt_feat, knn_dist, knn_idx32)
+    Q = knn_dist.shape[1]
+    out = torch.empty(B, Q, 32, dtype=torch.float32, device=cand.device)
+    check(lib().dvcp_dfe_tgt_fused(ptr(_f32c(cand)), tgt_cloud, ptr(_f32c(tgt_feat)), ptr(knn_dist), ptr(knn_idx32),
+                                   B, N, Q, dfe, quirks, ptr(out), stream_ptr(cand.device)), "dvcp_dfe_tgt_fused")
+    return out
+
+
+def dfe_dense(X, dfe):
+    """X [..., K, 35] float32/float64 -> [..., 32]."""
+    require_cuda(X)
+    if X.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("DFE input must be float32 or float64")
+    X = X.contiguous()
+    K = X.shape[-2]
+    rows = X.numel() // (K * 35)
+    out = torch.empty(*X.shape[:-2], 32, dtype=torch.float32, device=X.device)
+    check(lib().dvcp_dfe_dense(ptr(X), 0 if X.dtype == torch.float32 else 1, rows, K, dfe, ptr(out),
+                               stream_ptr(X.device)), "dvcp_dfe_dense")
+    return out
+
+
+def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False):
+    """src_dfe [M,32]; tgt_dfe [M,32*C] flat (layout 0: logical [32,C]; 1: [C,32]); cand [M,C,3]."""
+    require_cuda(src_dfe, tgt_dfe, cand)
+    M = src_dfe.shape[0]
+    C = G * G * G
+    dev = src_dfe.device
+    nbytes = lib().dvcp_cpg_workspace_bytes(M, G)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    vcp = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    logits = torch.empty(M, C, dtype=torch.float32, device=dev) if want_logits else None
+    check(lib().dvcp_cpg(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params, ptr(vcp),
+                         ptr(logits), ptr(ws), nbytes, stream_ptr(dev)), "dvcp_cpg")
+    return vcp, logits
+
+
+def kabsch(x, y):
+    """x, y [B,3,n] float32/float64 -> R [B,3,3], t [B,3,1] float64."""
+    require_cuda(x, y)
+    if x.dtype != y.dtype or x.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("kabsch: x and y must share a float32/float64 dtype")
+    B, _, n = x.shape
+    R = torch.empty(B, 3, 3, dtype=torch.float64, device=x.device)
+    t = torch.empty(B, 3, 1, dtype=torch.float64, device=x.device)
+    check(lib().dvcp_kabsch(ptr(x.contiguous()), ptr(y.contiguous()), 0 if x.dtype == torch.float32 else 1, B, n,
+                            ptr(R), ptr(t), stream_ptr(x.device)), "dvcp_kabsch")
+    return R, t
+
+
+def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False):
+    require_cuda(x, y_pred, R_true, t_true)
+    B, _, n = x.shape
+    dev = x.device
+    x = x.double().contiguous()
+    y_pred = y_pred.double().contiguous()
+    R_true = R_true.double().contiguous()
+    t_true = t_true.double().reshape(B, 3, -1)[:, :, 0].contiguous()
+    keep = int(n * inlier_ratio)
+    R2 = torch.empty(B, 3, 3, dtype=torch.float64, device=dev)
+    t2 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev)
+    R1 = torch.empty(B, 3, 3, dtype=torch.float64, device=dev) if want_first else None
+    t1 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev) if want_first else None
+    check(lib().dvcp_kabsch_refine(ptr(x), ptr(y_pred), ptr(R_true), ptr(t_true), B, n, keep, ptr(R2), ptr(t2),
+                                   ptr(R1), ptr(t1), stream_ptr(dev)), "dvcp_kabsch_refine")
+    return R2, t2, R1, t1

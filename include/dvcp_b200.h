@@ -1,0 +1,192 @@
+/*
+ * dvcp_b200.h -- C ABI of the B200-native DeepVCP registration hot path.
+ *
+ * This is the drop-in boundary: a plain-C shared library (libdvcp_b200.so,
+ * built from deepvcp-pointcloud-registration_b200/csrc for sm_100a) that a
+ * binding in any host language can load. No torch / ATen / pybind types cross
+ * it. The reference (vccheng2001/DeepVCP-Pointcloud-Registration) is pure
+ * PyTorch; its "FFI for this path" is the Python call surface of the modules
+ * cited next to each entry point below (paths relative to the reference root)
+ * plus the third-party `knn_cuda.KNN` call convention. INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller allocates all outputs and workspaces; kernels never allocate;
+ *   - inputs are never written;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = launched; < 0 = argument error (DVCP_E_*);
+ *     > 0 = a cudaError_t raised by the launch;
+ *   - point clouds are addressed with element strides
+ *     value(b, n, c) = base[b * bstride + n * pstride + c * cstride]
+ *     so that both the reference's channel-major model input [B, C, N]
+ *     (pstride 1, cstride N) and its point-major utility input [B, N, 3]
+ *     (pstride 3, cstride 1) are read in place;
+ *   - B > 1 always means "B independent single-cloud problems" (the reference
+ *     itself only runs B = 1).
+ */
+#ifndef DVCP_B200_H
+#define DVCP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVCP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DVCP_API __attribute__((visibility("default")))
+#else
+#define DVCP_API
+#endif
+
+#define DVCP_E_ARG        (-1) /* null pointer / non-positive size            */
+#define DVCP_E_UNSUPPORTED (-2) /* size outside what the kernels are built for */
+#define DVCP_E_WORKSPACE  (-3) /* workspace too small                          */
+
+typedef void *dvcp_stream_t;
+
+typedef struct {
+    const void *base;  /* float* or double* (see dtype) */
+    int64_t bstride, pstride, cstride; /* in elements */
+} dvcp_cloud_t;
+
+/* Folded parameters of one shared-MLP layer (1x1 conv + eval BatchNorm + ReLU,
+ * pointnet2_utils.py:171-172,196-198): y = relu((W x + b) * alpha + beta) with
+ * alpha = gamma / sqrt(var + eps), beta = bn_bias - mean * alpha. Row-major
+ * W[out][in]. */
+typedef struct {
+    const float *W, *b, *alpha, *beta;
+    int in_ch, out_ch;
+} dvcp_mlp_layer_t;
+
+DVCP_API int dvcp_abi_version(void);
+DVCP_API const char *dvcp_error_string(int code);
+
+/* ---- a1  farthest_point_sample(xyz, npoint)        pointnet2_utils.py:63-84
+ * start[B] is the random first index the caller drew (pointnet2_utils.py:75).
+ * dtype 0: float32 cloud, 1: float64 cloud. out64 [B,npoint] (int64) and/or
+ * out32 [B,npoint] (int32) may be null. */
+DVCP_API int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, const int64_t *start,
+             int64_t *out64, int32_t *out32, dvcp_stream_t stream);
+
+/* Test hook: the plain O(N * npoint) kernel for float32 clouds (the spatially
+ * pruned kernel dvcp_fps normally dispatches to must give identical indices). */
+DVCP_API int dvcp_fps_plain(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
+                   dvcp_stream_t stream);
+
+/* ---- a2  square_distance(src, dst)                  pointnet2_utils.py:19-40
+ * out [B,S,N] float32, expanded form. Utility only: the hot path never
+ * materialises it. */
+DVCP_API int dvcp_square_distance(dvcp_cloud_t src, dvcp_cloud_t dst, int B, int S, int N, float *out,
+                         dvcp_stream_t stream);
+
+/* ---- a3  query_ball_point(radius, nsample, xyz, new_xyz)  pointnet2_utils.py:87-107
+ * radius2 = float32(radius**2). out [B,S,nsample] int64; an empty ball yields
+ * N in every slot (the reference then raises in index_points). */
+DVCP_API int dvcp_ball_query(dvcp_cloud_t xyz, dvcp_cloud_t new_xyz, int B, int N, int S, float radius2,
+                    int nsample, int64_t *out, dvcp_stream_t stream);
+
+/* ---- a4  index_points(points, idx)                  pointnet2_utils.py:43-60
+ * points [B,N,C] contiguous float32, idx [B,M] int64 -> out [B,M,C]. */
+DVCP_API int dvcp_index_points(const float *points, const int64_t *idx, int B, int N, int C, int64_t M,
+                      float *out, dvcp_stream_t stream);
+
+/* ---- a5+a6  PointNetSetAbstraction.forward (group_all=False), eval mode
+ *             pointnet2_utils.py:110-138,176-202
+ * Fused: centroid gather, ball query, grouping [xyz - centre, feats], shared
+ * MLP, max over the ball. centroid_idx [B,S] int32 are the FPS indices.
+ * feats: D extra channels addressed like a cloud (null when D == 0).
+ * out_feat [B,S,out_ch_last] float32, out_xyz [B,S,3] float32 (may be null). */
+DVCP_API int dvcp_sa_layer(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *centroid_idx, int B,
+                  int N, int S, float radius2, int nsample, const dvcp_mlp_layer_t *layers_host,
+                  int n_layers, float *out_feat, float *out_xyz, dvcp_stream_t stream);
+
+/* ---- a8  weighting_layer.forward(X, K)              weighting_layer.py:26-33
+ * X [B,S,32]; W1[16,32] b1 W2[8,16] b2 W3[1,8] b3; scores [B,S] (softplus
+ * output, may be null if only indices are wanted -> then `scores` is still
+ * required as workspace); topk [B,K] int64 ordered (score desc, index asc). */
+DVCP_API int dvcp_weighting_scores(const float *X, int B, int S, const float *W1, const float *b1,
+                          const float *W2, const float *b2, const float *W3, const float *b3,
+                          float *scores, dvcp_stream_t stream);
+DVCP_API int dvcp_topk(const float *scores, int B, int S, int K, int64_t *topk, dvcp_stream_t stream);
+
+/* ---- a9..a11 + a15(src)  key-point stage            deepVCP.py:44-67,86-91,101
+ * src_pts [B,C_in,N] channel-major float32; topk [B,Kp] int64; kp_start [B]
+ * int64 (FPS start among the key-points, deepVCP.py:54 -> pointnet2_utils.py:75);
+ * src_feat [B,S,32] (FPS order); R_init [B,3,3] float64; dfe = {W1[32,35],b1,
+ * W2[32,32],b2,W3[32,32],b3}. quirks: bit 0 = reference key-point layout (Q3).
+ * Outputs (any may be null): keypts [B,Kp,C_in], picked [B,Kp,nsample] int64,
+ * src_cat [B,Kp,nsample,35], src_dfe [B,Kp,32], centres [B,Kp,3] float64. */
+typedef struct {
+    const float *W1, *b1, *W2, *b2, *W3, *b3;
+} dvcp_dfe_params_t;
+DVCP_API int dvcp_keypoint_stage(const float *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
+                        const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
+                        float radius2, int nsample, dvcp_dfe_params_t dfe, int quirks, float *keypts,
+                        int64_t *picked, float *src_cat, float *src_dfe, double *centres,
+                        dvcp_stream_t stream);
+
+/* ---- a12 voxelize(point_clouds, r, s)               voxelize.py:19-83
+ * centres [M,3] float64 -> out [M,G^3,3] float32; G from dvcp_grid_size. */
+DVCP_API int dvcp_grid_size(double r, double s);
+DVCP_API int dvcp_candidates(const double *centres, int64_t M, double r, double s, int G, float *out,
+                    dvcp_stream_t stream);
+
+/* ---- a13 knn_cuda.KNN(k, transpose_mode=True)(ref, query)
+ *          call sites get_cat_feat_tgt.py:45,52; deepVCP_loss.py:70,72
+ * ref addressed as a cloud [B,N,3]; query [B,Q,3] contiguous float32.
+ * dist [B,Q,K] float32 (sqrt), idx64 [B,Q,K] and/or idx32 (either may be null).
+ * Order: (squared distance, index) ascending. 1 <= K <= 32, K <= N. */
+DVCP_API int dvcp_knn(dvcp_cloud_t ref, const float *query, int B, int N, int64_t Q, int K, float *dist,
+             int64_t *idx64, int32_t *idx32, dvcp_stream_t stream);
+
+/* ---- a14+a15 Get_Cat_Feat_Tgt + feat_embedding_layer(src=False), fused
+ *          get_cat_feat_tgt.py:53-96, deep_feat_embedding.py:46-60
+ * cand [B,Q,3]; tgt_xyz cloud [B,N,3]; tgt_feat [B,N,32]; knn_dist [B,Q,32];
+ * knn_idx [B,Q,32] int32 -> out [B,Q,32]. quirks bit 1 = per-feature weight (Q7). */
+DVCP_API int dvcp_dfe_tgt_fused(const float *cand, dvcp_cloud_t tgt_xyz, const float *tgt_feat,
+                       const float *knn_dist, const int32_t *knn_idx, int B, int N, int64_t Q,
+                       dvcp_dfe_params_t dfe, int quirks, float *out, dvcp_stream_t stream);
+
+/* ---- a15 feat_embedding_layer.forward on a materialised input
+ *          deep_feat_embedding.py:23-61
+ * X [rows,K,35] (dtype 0 float32 / 1 float64, cast like X.float()) -> out [rows,32]. */
+DVCP_API int dvcp_dfe_dense(const void *X, int dtype, int64_t rows, int K, dvcp_dfe_params_t dfe, float *out,
+                   dvcp_stream_t stream);
+
+/* ---- a16 cpg.forward                                 cpg.py:27-60
+ * src_dfe [M,32]; tgt_dfe [M,32*C] holding, per key-point, the LOGICAL
+ * row-major order of the reference's [32,C] argument when layout == 0, or the
+ * DFE's own [C,32] order when layout == 1 (the kernel then applies the
+ * permute of deepVCP.py:106 itself); cand [M,C,3]; conv weights as in the
+ * state_dict (cpg.conv{1,2,3}.weight/bias). vcp [M,3]; logits [M,C] may be null.
+ * workspace: dvcp_cpg_workspace_bytes(M, G). */
+typedef struct {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+} dvcp_cpg_params_t;
+DVCP_API int64_t dvcp_cpg_workspace_bytes(int64_t M, int G);
+DVCP_API int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
+             int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
+             int64_t workspace_bytes, dvcp_stream_t stream);
+
+/* ---- a17 get_rigid_transform(x, y)                   deepVCP_loss.py:13-44
+ * x, y [B,3,n] (dtype 0 float32 / 1 float64); R [B,3,3], t [B,3] float64.
+ * R = V U^T without reflection correction (Q10). */
+DVCP_API int dvcp_kabsch(const void *x, const void *y, int dtype, int B, int n, double *R, double *t,
+                dvcp_stream_t stream);
+
+/* ---- a18 svd_optimization(x, y_pred, R_true, t_true)  deepVCP_loss.py:57-90
+ * x, y_pred [B,3,n] float64; R_true [B,3,3], t_true [B,3] float64; keep =
+ * int(0.8 n). Outputs R2 [B,3,3], t2 [B,3] float64; R1/t1 (first solve) may be
+ * null. n <= 1024. */
+DVCP_API int dvcp_kabsch_refine(const double *x, const double *y_pred, const double *R_true,
+                       const double *t_true, int B, int n, int keep, double *R2, double *t2,
+                       double *R1, double *t1, dvcp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVCP_B200_H */

@@ -1,0 +1,485 @@
+"""GPU parity: every CUDA entry point (through the C ABI) against the CPU oracle
+and the fixtures recorded from the reference. Index-producing stages must be
+bit-exact; floating-point stages carry their tolerance in the test."""
+import importlib
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, golden_state_dict, load_golden
+from oracle import stages
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda"
+
+FEAT_RTOL = 1e-3      # north_star: features within 1e-3 relative (to the tensor's max magnitude)
+ROT_TOL_DEG = 1e-3    # north_star: rotation within 1e-3 degrees
+TRANS_TOL = 1e-4      # north_star: translation within 1e-4 m
+
+
+@pytest.fixture(scope="module")
+def dv():
+    return importlib.import_module(PKG)
+
+
+@pytest.fixture(scope="module")
+def F(dv):
+    return dv.functional
+
+
+@pytest.fixture(scope="module")
+def prim():
+    return load_golden("primitives")
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rot_angle_deg(Ra, Rb):
+    Ra, Rb = Ra.double().cpu(), Rb.double().cpu()
+    d = Ra @ Rb.transpose(-1, -2)
+    c = ((d.diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2).clamp(-1, 1)
+    # small-angle safe: use the skew part
+    s = 0.5 * torch.stack([d[..., 2, 1] - d[..., 1, 2], d[..., 0, 2] - d[..., 2, 0],
+                           d[..., 1, 0] - d[..., 0, 1]], -1).norm(dim=-1)
+    return torch.rad2deg(torch.atan2(s, c)).max().item()
+
+
+def lattice_cloud(n, seed, extent=8.0, step=0.125):
+    g = torch.Generator().manual_seed(seed)
+    return torch.round((torch.rand(1, n, 3, generator=g) * 2 - 1) * extent / step) * step
+
+
+# ------------------------------------------------------------------ FPS ------
+@pytest.mark.parametrize("n,npoint", [(64, 64), (300, 300), (1000, 1000), (1024, 1024), (1500, 700),
+                                       (2048, 2048), (5000, 5000), (10000, 10000), (16384, 16384)])
+def test_fps_random_cloud_bit_exact(dv, n, npoint):
+    g = torch.Generator().manual_seed(n)
+    xyz = torch.rand(2, n, 3, generator=g) * 4 - 2
+    start = torch.tensor([n // 3, n - 1])
+    ref = stages.farthest_point_sample(xyz, npoint, start)
+    out = dv.farthest_point_sample(xyz.to(DEV), npoint, start)
+    assert out.dtype == torch.int64
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("n", [512, 4096])
+def test_fps_lattice_ties_bit_exact(dv, n):
+    xyz = lattice_cloud(n, 7)
+    start = torch.tensor([5])
+    ref = stages.farthest_point_sample(xyz, n, start)
+    out = dv.farthest_point_sample(xyz.to(DEV), n, start)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_fps_kitti_shaped_full_size(dv, synthetic):
+    src, _, _, _ = synthetic.make_batch("kitti", [0], 16384)
+    xyz = src.permute(0, 2, 1)                           # strided view, read in place
+    start = torch.tensor([1234])
+    ref = stages.farthest_point_sample(xyz.contiguous(), 16384, start)
+    out = dv.farthest_point_sample(xyz.to(DEV), 16384, start).cpu()
+    assert torch.equal(out, ref)
+    assert torch.equal(out.sort()[0], torch.arange(16384).view(1, -1))   # npoint == N: a permutation
+
+
+def test_fps_plain_and_pruned_kernels_agree(dv, F):
+    g = torch.Generator().manual_seed(3)
+    xyz = (torch.randn(3, 3000, 3, generator=g) * 5).to(DEV)
+    start = torch.tensor([0, 17, 2999])
+    assert torch.equal(F.fps_plain(xyz, 3000, start), dv.farthest_point_sample(xyz, 3000, start))
+
+
+def test_fps_float64_and_padding(dv, prim):
+    xyz = T(prim["xyz"])
+    ref = T(prim["fps_f64"])
+    out = dv.farthest_point_sample(xyz.double().to(DEV), 300, ref[:, 0])
+    assert torch.equal(out.cpu(), ref)
+    ref = T(prim["fps_pad"])
+    out = dv.farthest_point_sample(xyz[:, :10].contiguous().to(DEV), 16, ref[:, 0])
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_fps_matches_reference_fixture(dv, prim):
+    for tag, key in (("f32", "xyz"), ("lat", "xyz_l")):
+        ref = T(prim["fps_" + tag])
+        out = dv.farthest_point_sample(T(prim[key]).to(DEV), 300, ref[:, 0])
+        assert torch.equal(out.cpu(), ref)
+
+
+def test_fps_default_start_follows_cpu_rng(dv):
+    xyz = torch.rand(2, 500, 3).to(DEV)
+    torch.manual_seed(123)
+    expect = torch.randint(0, 500, (2,), dtype=torch.long)
+    torch.manual_seed(123)
+    out = dv.farthest_point_sample(xyz, 8)
+    assert torch.equal(out[:, 0].cpu(), expect)
+
+
+# ------------------------------------------------- square distance / ball ----
+def test_square_distance_bit_exact(dv, prim):
+    out = dv.square_distance(T(prim["q"]).to(DEV), T(prim["xyz"]).to(DEV))
+    assert torch.equal(out.cpu(), T(prim["sqd"]))
+
+
+def test_ball_query_reference_fixture(dv, prim):
+    out = dv.query_ball_point(0.2, 16, T(prim["xyz"]).to(DEV), T(prim["q"]).to(DEV))
+    assert torch.equal(out.cpu(), T(prim["ball_r02_n16"]))
+    xl = T(prim["xyz_l"]).to(DEV)
+    out = dv.query_ball_point(0.25, 8, xl, xl[:, :40].contiguous())
+    assert torch.equal(out.cpu(), T(prim["ball_l_r025_n8"]))
+
+
+@pytest.mark.parametrize("n,s,radius,nsample", [(777, 100, 0.5, 32), (9000, 333, 1.0, 256), (16384, 64, 0.3, 8)])
+def test_ball_query_vs_oracle(dv, n, s, radius, nsample):
+    xyz = lattice_cloud(n, n, extent=6.0, step=0.25)
+    q = xyz[:, torch.randperm(n, generator=torch.Generator().manual_seed(1))[:s]].contiguous()
+    ref = stages.query_ball_point(radius, nsample, xyz, q)
+    out = dv.query_ball_point(radius, nsample, xyz.to(DEV), q.to(DEV))
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_ball_query_empty_ball_yields_n(dv):
+    xyz = torch.zeros(1, 40, 3)
+    q = torch.full((1, 2, 3), 100.0)
+    out = dv.query_ball_point(0.1, 4, xyz.to(DEV), q.to(DEV))
+    assert (out == 40).all()
+    with pytest.raises(IndexError):
+        dv.query_ball_point(0.1, 64, xyz.to(DEV), q.to(DEV))   # N < nsample (reference :106)
+
+
+def test_index_points_and_sample_and_group(dv, prim):
+    out = dv.index_points(T(prim["xyz"]).to(DEV), T(prim["ip_idx"]).to(DEV))
+    assert torch.equal(out.cpu(), T(prim["ip_out"]))
+    xyz = T(prim["xyz"])
+    new_xyz_ref = T(prim["sag_new_xyz"])
+    start = torch.stack([(xyz[b] == new_xyz_ref[b, 0]).all(dim=1).nonzero()[0, 0] for b in range(2)])
+    nx, npts, idx = dv.sample_and_group(32, 0.4, 8, xyz.to(DEV), T(prim["sag_feats"]).to(DEV), returnidx=True,
+                                        start=start)
+    assert torch.equal(idx.cpu(), T(prim["sag_idx"]))
+    assert torch.equal(nx.cpu(), new_xyz_ref)
+    assert torch.equal(npts.cpu(), T(prim["sag_new_points"]))
+
+
+# ------------------------------------------------------ SA layer / WL --------
+@pytest.mark.parametrize("name", ["fwd_modelnet_n1024_g5", "fwd_kitti_n2048_g7"])
+def test_feat_extraction_vs_reference_fixture(dv, name):
+    g = load_golden(name)
+    sd = golden_state_dict(g)
+    use_normal = g["src"].shape[1] == 6
+    N = g["src"].shape[2]
+    fe = dv.feat_extraction_layer(use_normal=use_normal, npoint=N)
+    fe.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("FE1.")})
+    fe = fe.to(DEV).eval()
+    xyz, feats = fe(T(g["src"]).to(DEV), start=torch.tensor([int(g["starts"][0])]))
+    ref = T(g["src_fe_feat"])
+    assert feats.shape == ref.shape
+    assert rel_err(feats, ref) < FEAT_RTOL
+    assert rel_err(feats, ref) < 1e-5          # in practice float32 round-off only
+    src_xyz = T(g["src"])[:, :3].permute(0, 2, 1)
+    assert torch.equal(xyz.cpu(), stages.index_points(src_xyz.contiguous(), T(g["src_fps"]).long()))
+
+
+def test_sa_layer_dense_ball(dv):
+    """Many members per ball (beyond nsample) and a feature tail: oracle comparison."""
+    g = torch.Generator().manual_seed(5)
+    N = 600
+    pts = torch.cat([torch.rand(2, 3, N, generator=g), torch.randn(2, 3, N, generator=g)], dim=1)
+    fe = dv.feat_extraction_layer(use_normal=True, npoint=N, radius=0.3, nsample=16)
+    for bn in fe.sa1.mlp_bns:
+        bn.running_mean.normal_(0, 0.1, generator=g)
+        bn.running_var.uniform_(0.5, 1.5, generator=g)
+    sd = {"FE1." + k: v for k, v in fe.state_dict().items()}
+    start = torch.tensor([3, 77])
+    _, ref, _ = stages.feat_extraction(sd, pts, start, radius=0.3, nsample=16)
+    fe = fe.to(DEV).eval()
+    _, out = fe(pts.to(DEV), start=start)
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_weighting_topk(dv, prim):
+    sd = golden_state_dict(prim, "wl_sd/")
+    wl = dv.weighting_layer()
+    wl.load_state_dict({k[3:]: v for k, v in sd.items()})
+    wl = wl.to(DEV)
+    x = T(prim["wl_x"]).to(DEV)
+    scores = wl.scores(x)
+    ref_scores = stages.weighting_scores(sd, T(prim["wl_x"]))
+    assert rel_err(scores, ref_scores) < 1e-6
+    assert torch.equal(wl(x).cpu(), T(prim["wl_out"]))
+
+
+def test_topk_ties_lowest_index_first(F):
+    s = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0, 0.5, 2.0, 7.0] + [0.0] * 100]).to(DEV)
+    assert F.topk(s, 6).cpu().tolist() == [[7, 1, 2, 4, 3, 6]]
+
+
+# ------------------------------------------------------ candidates / KNN -----
+@pytest.mark.parametrize("G", [5, 6, 7, 11, 15])
+def test_candidates_bit_exact(dv, prim, G):
+    r = float(prim["vox_r%d" % G])
+    out = dv.voxelize(T(prim["vox_centres"]).to(DEV), r, 0.4)
+    assert torch.equal(out.cpu(), T(prim["vox_G%d" % G]))
+
+
+@pytest.mark.parametrize("n,q,k", [(100, 37, 1), (1000, 500, 5), (5000, 1000, 32), (16384, 2000, 32), (8193, 65, 32)])
+def test_knn_vs_oracle_with_ties(dv, n, q, k):
+    ref_pts = lattice_cloud(n, n + 1, extent=10.0, step=0.5)          # exact distance ties
+    g = torch.Generator().manual_seed(2)
+    qry = torch.round((torch.rand(1, q, 3, generator=g) * 2 - 1) * 40) / 4
+    d_ref, i_ref = stages.knn(ref_pts, qry, k)
+    d, i = dv.KNN(k, transpose_mode=True)(ref_pts.to(DEV), qry.to(DEV))
+    assert torch.equal(i.cpu(), i_ref)
+    assert torch.equal(d.cpu(), d_ref)
+    d2, i2 = dv.KNN(k, transpose_mode=False)(ref_pts.transpose(1, 2).to(DEV), qry.transpose(1, 2).to(DEV))
+    assert torch.equal(i2.cpu(), i_ref.transpose(1, 2))
+
+
+def test_knn_kitti_full_size_sampled_and_sorted(dv, F, synthetic):
+    _, tgt, _, _ = synthetic.make_batch("kitti", [2], 16384)
+    g = torch.Generator().manual_seed(4)
+    centres = (torch.rand(1, 64, 3, generator=g, dtype=torch.float64) * 2 - 1) * 30
+    cand = F.candidates(centres.to(DEV), 2.0, 0.4).view(1, -1, 3)      # 85184 queries
+    tg = tgt.to(DEV)
+    from importlib import import_module
+    lib = import_module(PKG + "._lib")
+    d, i, _ = F.knn(lib.cloud_cm(tg), tg.device, 1, 16384, cand, 32)
+    d, i = d.cpu(), i.cpu()
+    assert (d[..., 1:] >= d[..., :-1]).all()
+    assert int(i.min()) >= 0 and int(i.max()) < 16384
+    pick = torch.randperm(cand.shape[1], generator=g)[:1500]
+    d_ref, i_ref = stages.knn(tgt[:, :3].permute(0, 2, 1).contiguous(), cand[:, pick].cpu(), 32)
+    assert torch.equal(i[:, pick], i_ref)
+    assert torch.equal(d[:, pick], d_ref)
+
+
+# ------------------------------------------------------------- DFE / CPG -----
+def test_dfe_dense_vs_reference_fixture(dv, prim):
+    sd = golden_state_dict(prim, "dfe_sd/")
+    dfe = dv.feat_embedding_layer()
+    dfe.load_state_dict({k[4:]: v for k, v in sd.items()})
+    dfe = dfe.to(DEV)
+    out = dfe(T(prim["dfe_xs"]).to(DEV), src=True)
+    assert out.shape == prim["dfe_src_out"].shape
+    assert rel_err(out, T(prim["dfe_src_out"])) < 1e-5
+    out = dfe(T(prim["dfe_xt"]).to(DEV), src=False)
+    assert out.shape == prim["dfe_tgt_out"].shape
+    assert rel_err(out, T(prim["dfe_tgt_out"])) < 1e-5
+
+
+def test_cat_feat_tgt_module_and_fused_dfe(dv, F):
+    g = load_golden("fwd_modelnet_n1024_g5")
+    sd = golden_state_dict(g)
+    cand = T(g["candidates"])
+    tgt = T(g["tgt"])
+    txyz = tgt[:, :3].permute(0, 2, 1).contiguous()
+    tfeat = T(g["tgt_fe_feat"])
+    s = int(g["stride"])
+    # standalone module returns the reference's float64 tensor
+    cat = dv.Get_Cat_Feat_Tgt()(cand.to(DEV), None, txyz.to(DEV), tfeat.to(DEV))
+    assert cat.dtype == torch.float64
+    ref = T(g["tgt_cat_s"])
+    assert torch.allclose(cat[:, ::8, ::s].cpu(), ref, rtol=0, atol=1e-6)
+    # fused gather + DFE against the reference's DFE output
+    lib = importlib.import_module(PKG + "._lib")
+    dfe = dv.feat_embedding_layer()
+    dfe.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("DFE.")})
+    dfe = dfe.to(DEV)
+    B, M, C, _ = cand.shape
+    tg = tgt.to(DEV)
+    cq = cand.view(B, M * C, 3).to(DEV)
+    kd, _, ki = F.knn(lib.cloud_cm(tg), tg.device, B, 1024, cq, 32, want64=False, want32=True)
+    out = F.dfe_tgt_fused(cq, lib.cloud_cm(tg), tfeat.to(DEV), kd, ki, B, 1024, dfe.params(), lib.QUIRKS_REFERENCE)
+    out = out.view(B, M, C, 32)[:, :, ::s]
+    assert rel_err(out, T(g["tgt_dfe_s"])) < 1e-5
+
+
+def test_cpg_standalone_vs_reference_fixture(dv, prim):
+    sd = golden_state_dict(prim, "cpg_sd/")
+    net = dv.cpg()
+    net.load_state_dict({k[4:]: v for k, v in sd.items()})
+    net = net.to(DEV)
+    a, b, c = T(prim["cpg_a"]).to(DEV), T(prim["cpg_b"]).to(DEV), T(prim["cpg_c"]).to(DEV)
+    out = net(a, b, c, 1, 0.4)                                   # contiguous [B,N,32,C]: layout 0
+    assert torch.allclose(out.cpu(), T(prim["cpg_out"]), rtol=0, atol=5e-6)
+    bt = b.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)   # the view deepVCP.py:106 produces: layout 1
+    out = net(a, bt, c, 1, 0.4)
+    assert torch.allclose(out.cpu(), T(prim["cpg_out"]), rtol=0, atol=5e-6)
+
+
+# --------------------------------------------------------------- Kabsch ------
+def test_kabsch_vs_reference_fixture(dv, prim):
+    x, y = T(prim["kab_x"]), T(prim["kab_y"])
+    R, t = dv.get_rigid_transform(x.to(DEV), y.to(DEV))
+    assert R.dtype == torch.float64
+    assert torch.allclose(R.cpu(), T(prim["kab_R"]), atol=1e-12)
+    assert torch.allclose(t.cpu(), T(prim["kab_t"]), atol=1e-12)
+    R32, t32 = dv.get_rigid_transform(x.float().to(DEV), y.float().to(DEV))
+    assert R32.dtype == torch.float32
+    assert rot_angle_deg(R32, T(prim["kab_R"])) < 1e-3
+
+
+def test_kabsch_reflection_not_corrected(dv):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3, 50, generator=g, dtype=torch.float64)
+    y = x.clone()
+    y[:, 2] *= -1                                                   # mirrored target
+    R, _ = dv.get_rigid_transform(x.to(DEV), y.to(DEV))
+    Rr, _ = stages.get_rigid_transform(x, y)
+    assert torch.allclose(R.cpu(), Rr, atol=1e-10)
+    assert torch.det(R[0].cpu()) < 0                                # quirk Q10
+
+
+def test_svd_optimization_vs_reference_fixture(dv, prim):
+    R2, t2, _, _ = dv.svd_optimization(T(prim["kab_x"]).to(DEV), T(prim["kab_y"]).float().to(DEV),
+                                       T(prim["svdopt_Rt"]).to(DEV), T(prim["svdopt_tt"]).to(DEV))
+    assert torch.allclose(R2.cpu(), T(prim["svdopt_R2"]), atol=1e-10)
+    assert torch.allclose(t2.cpu(), T(prim["svdopt_t2"]), atol=1e-10)
+
+
+def test_kabsch_sweep_batch(dv, F):
+    g = torch.Generator().manual_seed(99)
+    B = 4096
+    x = torch.randn(B, 3, 64, generator=g)
+    Rg = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    Rg = Rg * torch.sign(torch.det(Rg)).view(B, 1, 1)
+    y = Rg @ x + torch.randn(B, 3, 1, generator=g) + 0.01 * torch.randn(B, 3, 64, generator=g)
+    R, t = F.kabsch(x.to(DEV), y.to(DEV))
+    Rr, tr = stages.get_rigid_transform(x.double(), y.double())
+    assert rot_angle_deg(R, Rr) < ROT_TOL_DEG
+    assert (t.cpu() - tr).abs().max() < TRANS_TOL
+
+
+# -------------------------------------------------------- whole forward ------
+def build_model(dv, g, N):
+    use_normal = g["src"].shape[1] == 6
+    model = dv.DeepVCP(use_normal=use_normal, npoint=N, r=float(g["r"]), s=float(g["s"]))
+    model.load_state_dict(golden_state_dict(g))
+    return model.to(DEV).eval()
+
+
+def topk_equivalent(scores, a, b):
+    if not torch.equal(scores[a], scores[b]):
+        return False
+    return True
+
+
+@pytest.mark.parametrize("name", ["fwd_modelnet_n1024_g5", "fwd_modelnet_n512_g6", "fwd_kitti_n2048_g7"])
+def test_forward_vs_reference_fixture(dv, name):
+    g = load_golden(name)
+    N = int(g["n_points"])
+    model = build_model(dv, g, N)
+    st = g["starts"]
+    starts = tuple(torch.tensor([int(v)]) for v in st)
+    src, tgt, R = T(g["src"]), T(g["tgt"]), T(g["R"])
+    ref_topk = T(g["topk_idx"]).long().view(1, -1)
+    # pass 1: free-running, checks the index-producing stages and the key-point choice
+    model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True)
+    L = model.last
+    assert torch.equal(L["src_fps"].cpu(), T(g["src_fps"]))
+    assert torch.equal(L["tgt_fps"].cpu(), T(g["tgt_fps"]))
+    assert rel_err(L["src_fe_feat"], T(g["src_fe_feat"])) < 1e-5
+    sc = L["scores"][0].cpu()
+    mine = L["topk_idx"][0].cpu()
+    # the reference's choice and ours may differ only inside groups of (near-)equal scores
+    assert torch.allclose(sc[mine], sc[ref_topk[0]], rtol=1e-6, atol=0)
+    # pass 2: teacher-forced key-point choice (torch.topk tie order is unspecified)
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True,
+                    topk_override=ref_topk)
+    L = model.last
+    assert torch.equal(L["src_keypts_full"].cpu(), T(g["src_keypts_full"]))
+    assert torch.equal(L["picked_idx"].cpu().to(torch.int16), T(g["picked_idx"]))
+    assert torch.allclose(L["src_cat"].cpu(), T(g["src_cat"]), atol=1e-6)
+    assert torch.allclose(L["centres"].cpu(), T(g["centres"]), rtol=0, atol=1e-12)
+    assert rel_err(L["src_dfe"], T(g["src_dfe"]).squeeze(2)) < 1e-5
+    s = int(g["stride"])
+    assert rel_err(L["tgt_dfe"][:, :, ::s], T(g["tgt_dfe_s"])) < FEAT_RTOL
+    assert rel_err(L["tgt_dfe"][:, :, ::s], T(g["tgt_dfe_s"])) < 1e-5
+    assert torch.equal(kp.cpu(), T(g["src_keypts"]))
+    assert (vcp.cpu() - T(g["vcp"])).abs().max() < 2e-5
+    # candidates: float64 centres may differ in the last bit -> compare with 1 ulp slack
+    assert torch.allclose(L["candidates"].cpu(), T(g["candidates"]), rtol=0, atol=4e-6)
+    # pose (train.py:110): two-stage Kabsch against the reference's own result
+    R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), T(g["t"]).view(1, 3, 1).to(DEV))
+    assert rot_angle_deg(R2, T(g["R2"])) < ROT_TOL_DEG
+    assert (t2.cpu() - T(g["t2"])).abs().max() < TRANS_TOL
+
+
+def test_forward_knn_indices_vs_oracle(dv):
+    """KNN indices inside the forward are bit-exact against the oracle on the same candidates."""
+    g = load_golden("fwd_kitti_n2048_g7")
+    model = build_model(dv, g, 2048)
+    starts = tuple(torch.tensor([int(v)]) for v in g["starts"])
+    ref_topk = T(g["topk_idx"]).long().view(1, -1)
+    model(T(g["src"]).to(DEV), T(g["tgt"]).to(DEV), T(g["R"]).to(DEV), torch.zeros(1, 3), starts=starts,
+          keep_stages=True, topk_override=ref_topk)
+    L = model.last
+    cand = L["candidates"].cpu()
+    txyz = T(g["tgt"])[:, :3].permute(0, 2, 1).contiguous()
+    d_ref, i_ref = stages.knn(txyz, cand.view(1, -1, 3), 32)
+    assert torch.equal(L["knn_idx"].cpu(), i_ref)
+    assert torch.equal(L["knn_dist"].cpu(), d_ref)
+
+
+def test_batched_forward_equals_independent_forwards(dv, synthetic):
+    N = 1024
+    src, tgt, R, t = synthetic.make_batch("modelnet", [10, 11, 12], N)
+    torch.manual_seed(0)
+    model = dv.DeepVCP(use_normal=True, npoint=N, r=0.8, s=0.4).to(DEV).eval()
+    starts = (torch.tensor([1, 2, 3]), torch.tensor([4, 5, 6]), torch.tensor([7, 8, 9]))
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts)
+    for b in range(3):
+        st = tuple(s[b:b + 1] for s in starts)
+        kb, vb = model(src[b:b + 1].to(DEV), tgt[b:b + 1].to(DEV), R[b:b + 1].to(DEV), torch.zeros(1, 3), starts=st)
+        assert torch.equal(kb[0], kp[b])
+        assert torch.equal(vb[0], vcp[b])
+
+
+def test_forward_seeded_rng_matches_explicit_starts(dv, synthetic):
+    N = 1024
+    src, tgt, R, _ = synthetic.make_batch("modelnet", [20], N)
+    torch.manual_seed(0)
+    model = dv.DeepVCP(use_normal=True, npoint=N, r=0.8, s=0.4).to(DEV).eval()
+    torch.manual_seed(42)
+    a = torch.randint(0, N, (1,)), torch.randint(0, 64, (1,)), torch.randint(0, N, (1,))
+    torch.manual_seed(42)
+    kp1, v1 = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3))
+    kp2, v2 = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=a)
+    assert torch.equal(kp1, kp2) and torch.equal(v1, v2)
+
+
+def test_cpu_tensors_to_ops_raise(dv):
+    with pytest.raises(RuntimeError):
+        dv.query_ball_point(0.2, 4, torch.rand(1, 10, 3), torch.rand(1, 2, 3))
+    with pytest.raises(RuntimeError):
+        dv.DeepVCP(use_normal=True).eval()(torch.rand(1, 6, 64), torch.rand(1, 6, 64),
+                                           torch.eye(3, dtype=torch.float64)[None], torch.zeros(1, 3))
+
+
+def test_kitti_shaped_forward_full_size_properties(dv, synthetic):
+    """BASELINE config K8 shape, B=2: index-stage properties + oracle on the cheap stages."""
+    N = 16384
+    src, tgt, R, t = synthetic.make_batch("kitti", [0, 1], N)
+    torch.manual_seed(1)
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=2.0, s=0.4).to(DEV).eval()
+    starts = (torch.tensor([11, 12]), torch.tensor([13, 14]), torch.tensor([15, 16]))
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True)
+    L = model.last
+    assert kp.shape == (2, 64, 3) and vcp.shape == (2, 64, 3)
+    assert torch.isfinite(vcp).all()
+    for key in ("src_fps", "tgt_fps"):
+        assert torch.equal(L[key].cpu().long().sort(dim=1)[0], torch.arange(N).expand(2, N))
+    d = L["knn_dist"].cpu()
+    assert (d[..., 1:] >= d[..., :-1]).all()
+    # vcp is a convex combination of the candidates of its key-point
+    cand = L["candidates"].cpu()
+    assert (vcp.cpu() >= cand.min(dim=2)[0] - 1e-4).all() and (vcp.cpu() <= cand.max(dim=2)[0] + 1e-4).all()
+    # FPS of the full-size cloud against the oracle (pair 0, src)
+    ref = stages.farthest_point_sample(src[:1, :3].permute(0, 2, 1).contiguous(), N, starts[0][:1])
+    assert torch.equal(L["src_fps"][:1].cpu().long(), ref)
+    R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(2, 3, 1).to(DEV))
+    assert torch.isfinite(R2).all() and torch.isfinite(t2).all()

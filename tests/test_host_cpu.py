@@ -1,0 +1,135 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the
+header declares, host logic (state_dict layout, argument validation, sharding),
+and that the product never falls back to the CPU."""
+import ctypes
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import PKG, ROOT, golden_state_dict, load_golden
+
+
+@pytest.fixture(scope="module")
+def dv():
+    return importlib.import_module(PKG)
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "dvcp_b200.h")).read()
+    return sorted(set(re.findall(r"DVCP_API[^;(]*?\b(dvcp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(dv):
+    path = dv.build()
+    L = ctypes.CDLL(path)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "missing export " + s
+    lib = importlib.import_module(PKG + "._lib")
+    assert sorted(lib.SIGNATURES) == syms          # the binding covers the whole header
+    assert dv.lib().dvcp_abi_version() == 1
+    assert b"invalid argument" in dv.lib().dvcp_error_string(-1)
+
+
+def test_library_has_sm100a_code_only(dv):
+    out = subprocess.run(["cuobjdump", "--list-elf", dv.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}
+
+
+def test_argument_errors_without_a_gpu(dv):
+    L = dv.lib()
+    lib = importlib.import_module(PKG + "._lib")
+    null = lib.NULL_CLOUD
+    assert L.dvcp_fps(null, 0, 1, 10, 10, None, None, None, None) == -1
+    assert L.dvcp_grid_size(2.0, 0.4) == 11 and L.dvcp_grid_size(1.0, 0.4) == 6 and L.dvcp_grid_size(0.8, 0.4) == 5
+    assert L.dvcp_grid_size(4.0, 0.4) == 21
+    assert L.dvcp_grid_size(-1.0, 0.4) == -1
+    assert L.dvcp_cpg_workspace_bytes(64, 11) == 64 * 1331 * 53 * 4
+
+
+def test_state_dict_layout_matches_reference(dv):
+    g = load_golden("fwd_modelnet_n1024_g5")
+    sd = golden_state_dict(g)
+    model = dv.DeepVCP(use_normal=True)
+    mine = model.state_dict()
+    assert list(mine.keys()) == list(sd.keys())
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape), k
+    model.load_state_dict(sd)
+    assert sum(p.numel() for p in model.parameters()) == 34690
+    assert sum(p.numel() for p in dv.DeepVCP(use_normal=False).parameters()) == 34642
+
+
+def test_no_cpu_fallback(dv):
+    model = dv.DeepVCP(use_normal=True, npoint=64).eval()
+    x = torch.rand(1, 6, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(x, x, torch.eye(3, dtype=torch.float64)[None], torch.zeros(1, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dv.farthest_point_sample(torch.rand(1, 10, 3), 4)
+    with pytest.raises(RuntimeError, match="eval"):
+        dv.DeepVCP(use_normal=True)(x, x, torch.eye(3, dtype=torch.float64)[None], torch.zeros(1, 3))
+
+
+def test_product_does_not_import_oracle():
+    pkg_dir = os.path.join(ROOT, PKG)
+    for root, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle", text, re.M), f
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_shard_ranges_cover_all_pairs(dv):
+    sh = dv.sharding
+    for n in (1, 7, 8, 256, 257):
+        for world in (1, 2, 4, 8):
+            blocks = [sh.shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+GLOO_WORKER = r"""
+import importlib, os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+dv = importlib.import_module({pkg!r})
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+n = 7
+g = torch.Generator().manual_seed(0)
+poses = torch.randn(n, 12, generator=g, dtype=torch.float64)     # what world=1 would produce
+lo, hi = dv.sharding.shard_range(n, rank, world)
+out = dv.sharding.all_gather_poses(poses[lo:hi].clone(), n)
+assert torch.equal(out, poses), (rank, out, poses)                # bit-identical, pair-id order
+R, t = dv.sharding.unpack_poses(out)
+assert torch.equal(dv.sharding.pack_poses(R, t), poses)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_all_gather_poses_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT, pkg=PKG))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
+        assert "ok" in out
