@@ -1,0 +1,323 @@
+"""bench.py -- KITTI-shaped registration throughput (pairs/s) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step = one pass of the hot path (DeepVCP forward + two-stage pose solve) over
+one batch of synthetic KITTI-shaped pairs (BASELINE.json config 3: B = 8 pairs
+per GPU, 16384 points, 64 key-points, 11^3 candidates, K = 32). Weak scaling:
+every rank processes its own 8 pairs per step; the only collective is the
+all-gather of poses (sharding.py). Prints ONE JSON line on rank 0.
+
+  value     pairs/s, inputs resident in HBM, device time (CUDA events), max over ranks
+  e2e       pairs/s through the public API with pinned HOST buffers: H2D copies,
+            forward, pose solve and the D2H read of the poses inside the timed region
+  roofline  the dominant kernel's algorithmic bytes / its event-timed duration
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port (oracle/) timed on this box's host cores on a
+            bounded sample (one pair) -- a reported baseline, not the target
+
+--impl reference times that same CPU port as the reference arm (the reference is
+pure Python + an absent third-party CUDA extension and /root/reference does not
+travel to the GPU box; oracle/ is its pinned restatement).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "deepvcp-pointcloud-registration_b200"
+
+WORKLOAD = dict(kind="kitti", pairs_per_gpu=8, n_points=16384, keypoints=64, grid=11, k=32, r=2.0, s=0.4)
+WORKLOAD_NAME = ("K8: KITTI-shaped voxelized scan pairs, B=8 per GPU, N=16384, 64 keypoints, "
+                 "11^3 candidate grid, K=32 (BASELINE.json configs[2])")
+METRIC = "KITTI-shaped registration pairs/sec (DeepVCP forward + pose solve)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(B, N, S, Q, K, C_in):
+    """Per-launch algorithmic bytes of every stage (SURVEY 8d figures x units per launch)."""
+    kp = WORKLOAD["keypoints"]
+    return {
+        "fps": 2 * B * (12 * N + 4 * S),                                   # 2B clouds: xyz in, int32 order out
+        "sa_layer": 2 * B * (4 * C_in * N + 4 * S + 128 * S),              # cloud + centroid ids in, [S,32] out
+        "weighting_topk": B * (128 * S + 4 * S + 8 * kp),
+        "keypoint_candidates": B * (24 * kp + 12 * Q),
+        "knn": B * (12 * N + 12 * Q + Q * K * (4 + 4)),                    # int32 indices (fused path)
+        "dfe": B * (12 * N + 128 * N + 12 * Q + Q * K * 8 + 128 * Q),
+        "cpg": B * (128 * kp + 128 * Q + 12 * Q + 12 * kp),
+    }
+
+
+def make_inputs(dv, rank, B):
+    w = WORKLOAD
+    ids = [rank * B + i for i in range(B)]
+    return dv.synthetic.make_batch(w["kind"], ids, w["n_points"])
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    dv = importlib.import_module(PKG)
+    F_ = dv.functional
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOAD
+    B, N = w["pairs_per_gpu"], w["n_points"]
+    G = w["grid"]
+    Q = w["keypoints"] * G ** 3
+    src, tgt, R, t = make_inputs(dv, rank, B)
+    torch.manual_seed(0)
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=w["r"], s=w["s"]).to(dev).eval()
+    g = torch.Generator().manual_seed(1000 + rank)
+    starts = (torch.randint(0, N, (B,), generator=g), torch.randint(0, 64, (B,), generator=g),
+              torch.randint(0, N, (B,), generator=g))
+    # host side: pinned buffers (the e2e leg copies from these every step)
+    h_src, h_tgt, h_R, h_t = src.pin_memory(), tgt.pin_memory(), R.pin_memory(), t.view(B, 3, 1).pin_memory()
+    h_pose = torch.empty(B, 12, dtype=torch.float64).pin_memory()
+    d_src, d_tgt, d_R, d_t = (x.to(dev) for x in (h_src, h_tgt, h_R, h_t))
+    t_init = torch.zeros(1, 3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step_device():
+        kp, vcp = model(d_src, d_tgt, d_R, t_init, starts=starts)
+        R2, t2 = dv.pose_from_forward(kp, vcp, d_R, d_t)
+        return dv.sharding.pack_poses(R2, t2)
+
+    def step_e2e():
+        s_, t_, R_, tt_ = (x.to(dev, non_blocking=True) for x in (h_src, h_tgt, h_R, h_t))
+        kp, vcp = model(s_, t_, R_, t_init, starts=starts)
+        R2, t2 = dv.pose_from_forward(kp, vcp, R_, tt_)
+        h_pose.copy_(dv.sharding.pack_poses(R2, t2), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return h_pose
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        poses = step_device()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: K steps, device time, per-stage events, clocks sampled ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.profile = True
+    stage_ms = {}
+    launches0 = F_.LAUNCHES
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    per_step_events = []
+    for a, b in ev:
+        flush.fill_(1)                                                     # L2 flush between timed iterations
+        a.record()
+        poses = step_device()
+        b.record()
+        per_step_events.append(model._events)
+    barrier()
+    launches = F_.LAUNCHES - launches0
+    model.profile = False
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    for evs in per_step_events:
+        for (_, e0), (name, e1) in zip(evs, evs[1:]):
+            stage_ms[name] = stage_ms.get(name, 0.0) + e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e leg: host buffers in, poses out, wall clock around synchronised steps ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # multi-GPU: the one collective of the path, then max over ranks
+    all_poses = dv.sharding.all_gather_poses(poses, B * world)
+    assert all_poses.shape == (B * world, 12)
+    tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tm[0]), float(tm[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ms_step = ms_total / args.steps
+        pairs = B * world
+        ab = algorithmic_bytes(B, N, N, Q, w["k"], 3)
+        kernels = {}
+        for name, tot in stage_ms.items():
+            avg = tot / args.steps
+            gbs = ab[name] / (avg * 1e-3) / 1e9 if name in ab and avg > 0 else None
+            kernels[name] = {"ms": round(avg, 4), "share": round(avg / ms_step, 4),
+                             "algorithmic_mb": round(ab.get(name, 0) / 1e6, 3),
+                             "achieved_gbs": None if gbs is None else round(gbs, 2),
+                             "frac_hbm": None if gbs is None else round(gbs / peak, 5)}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"])
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "note": "FPS is latency-bound (sequential rounds), see DESIGN.md" if dom == "fps" else ""}
+        h2d = sum(x.numel() * x.element_size() for x in (h_src, h_tgt, h_R, h_t))
+        out = {
+            "metric": METRIC, "value": round(pairs / (ms_step * 1e-3), 3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "b200",
+            "config": {"workload": WORKLOAD_NAME, "pairs_per_gpu": B, "n_points": N, "keypoints": 64,
+                       "grid": "11^3", "k": 32, "timing": "CUDA events per step, L2 flushed (256 MiB write) "
+                       "between timed steps", "parallelism": "pairs sharded by rank, all-gather of poses only"},
+            "roofline": roofline, "kernels": kernels,
+            "e2e": {"value": round(pairs / (e2e_ms * 1e-3 / args.steps), 3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_pose.numel() * 8},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_port_baseline(steps=3, warmup=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_once(state):
+    import torch
+    from oracle import stages
+    sd, src, tgt, R, t, starts = state
+    w = WORKLOAD
+    o = stages.deepvcp_forward(sd, src, tgt, R, w["r"], w["s"], starts)
+    stages.pose_from_forward(o["src_keypts"], o["vcp"], R, t.view(1, 3, 1))
+
+
+def cpu_port_state():
+    import torch
+    dv_syn = importlib.import_module(PKG + ".synthetic")
+    dv = importlib.import_module(PKG)
+    w = WORKLOAD
+    src, tgt, R, t = dv_syn.make_batch(w["kind"], [0], w["n_points"])
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in dv.DeepVCP(use_normal=False).state_dict().items()}
+    N = w["n_points"]
+    starts = (torch.tensor([1]), torch.tensor([2]), torch.tensor([3]))
+    return sd, src, tgt, R, t, starts
+
+
+def cpu_port_baseline(steps, warmup):
+    """The oracle port of the reference's CPU path on ONE pair of the workload."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = cpu_port_state()
+    for _ in range(warmup):
+        cpu_port_once(state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_once(state)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(1.0 / dt, 5), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 pair of the K8 workload per step (forward + pose solve), %d step(s), "
+                      "C oracle with OpenMP + torch CPU ops on all host threads" % steps,
+            "s_per_pair": round(dt, 3)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU algorithm (pinned oracle port) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = 1 if args.warmup > 0 else 0
+    base = cpu_port_baseline(steps=steps, warmup=warm)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "pairs/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+        "ms_per_step": round(1e3 / base["value"], 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME, "sample": base["sample"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,11 +43,18 @@ class DeepVCP(nn.Module):
         self.group_radius = group_radius
         self.quirks = quirks
         self.last = None   # stage tensors of the most recent forward (for tests / inspection)
+        self.profile = False   # record a CUDA event after every stage (bench.py reads them)
+        self._events = None
 
     def draw_starts(self, B, N):
         """The three FPS start draws of one forward in the reference's order:
         FE(src) -> key-point grouping -> FE(tgt) (deepVCP.py:29,54,72)."""
         return (F_.draw_fps_start(B, N), F_.draw_fps_start(B, self.K_topk), F_.draw_fps_start(B, N))
+
+    def stage_times_ms(self):
+        """Per-stage device time of the last profiled forward (after a synchronize)."""
+        ev = self._events or []
+        return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(ev, ev[1:])}
 
     def forward(self, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=False, topk_override=None):
         """src_pts, tgt_pts [B,C_in,N]; R_init [B,3,3] float64; t_init [1,3] (unused by
@@ -72,19 +79,32 @@ class DeepVCP(nn.Module):
         sa = self.FE1.sa1
         mlp = sa.folded()
         D = C_in - 3
+        ev = self._events = [] if self.profile else None
+
+        def mark(name):
+            if ev is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream(dev))
+                ev.append((name, e))
+
         with torch.no_grad():
-            # feature extraction, both clouds (FPS order)
-            _, sfps = F_.fps(cloud_cm(src), dev, src.dtype, B, N, S, starts[0], want64=False, want32=True)
-            _, tfps = F_.fps(cloud_cm(tgt), dev, tgt.dtype, B, N, S, starts[2], want64=False, want32=True)
-            sfeat_cloud = cloud_cm(src[:, 3:, :]) if D else None
-            tfeat_cloud = cloud_cm(tgt[:, 3:, :]) if D else None
-            _, sfeat = F_.sa_layer(cloud_cm(src), sfeat_cloud, D, sfps, B, N, S, sa.radius, sa.nsample, mlp, dev,
-                                   want_xyz=False)
-            _, tfeat = F_.sa_layer(cloud_cm(tgt), tfeat_cloud, D, tfps, B, N, S, sa.radius, sa.nsample, mlp, dev,
-                                   want_xyz=False)
+            mark("begin")
+            # feature extraction: source and target clouds go through each kernel in ONE
+            # launch (2B independent clouds); features come out in FPS order
+            both = torch.cat([src, tgt], dim=0)
+            st2 = torch.cat([torch.as_tensor(starts[0]).reshape(-1), torch.as_tensor(starts[2]).reshape(-1)])
+            _, fps2 = F_.fps(cloud_cm(both), dev, both.dtype, 2 * B, N, S, st2, want64=False, want32=True)
+            mark("fps")
+            feat_cloud = cloud_cm(both[:, 3:, :]) if D else None
+            _, feat2 = F_.sa_layer(cloud_cm(both), feat_cloud, D, fps2, 2 * B, N, S, sa.radius, sa.nsample, mlp,
+                                   dev, want_xyz=False)
+            mark("sa_layer")
+            sfps, tfps = fps2[:B], fps2[B:]
+            sfeat, tfeat = feat2[:B], feat2[B:]
             # key-point selection
             scores = self.WL.scores(sfeat)
             topk = F_.topk(scores, K) if topk_override is None else topk_override.to(dev).view(B, K)
+            mark("weighting_topk")
             dfe = self.DFE.params()
             keypts, picked, cat, src_dfe, centres = F_.keypoint_stage(
                 src, topk, starts[1], sfeat, R, self.group_radius, ns, dfe, self.quirks,
@@ -92,14 +112,18 @@ class DeepVCP(nn.Module):
             # candidates, KNN, target-side embedding
             G = F_.grid_size(self.r, self.s)
             cand = F_.candidates(centres, self.r, self.s, G)                 # [B,K,C,3]
+            mark("keypoint_candidates")
             C = G * G * G
             kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
                                     want32=True)
+            mark("knn")
             tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
                                        self.quirks)                            # [B,K*C,32]
+            mark("dfe")
             # corresponding point generation
             vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.view(B * K, C * 32), 1,
                                  cand.view(B * K, C, 3), G, self.cpg.params(), want_logits=keep_stages)
+            mark("cpg")
         if keep_stages:
             self.last = dict(src_fps=sfps, tgt_fps=tfps, src_fe_feat=sfeat, tgt_fe_feat=tfeat, scores=scores,
                              topk_idx=topk, src_keypts_full=keypts, picked_idx=picked, src_cat=cat,

@@ -14,6 +14,16 @@ from ._lib import (Cloud, MlpLayer, NULL_CLOUD, check, cloud_cm, cloud_pm, lib, 
                    stream_ptr)
 
 
+# number of kernels of libdvcp_b200.so launched through this module (bench.py's
+# `gpu_launches`); every wrapper adds what its entry point launches.
+LAUNCHES = 0
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _f32c(t):
     if t.dtype != torch.float32:
         raise RuntimeError("expected a float32 tensor, got %s" % t.dtype)
@@ -41,6 +51,7 @@ def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want3
     code = lib().dvcp_fps(xyz_cloud, 0 if dtype == torch.float32 else 1, B, N, npoint, ptr(start), ptr(o64),
                           ptr(o32), stream_ptr(device))
     check(code, "dvcp_fps")
+    _count(1)
     return o64, o32
 
 
@@ -51,6 +62,7 @@ def fps_plain(xyz_pm, npoint, start):
     out = torch.empty(B, npoint, dtype=torch.int64, device=xyz_pm.device)
     check(lib().dvcp_fps_plain(cloud_pm(xyz_pm), B, N, npoint, ptr(start), ptr(out), stream_ptr(xyz_pm.device)),
           "dvcp_fps_plain")
+    _count(1)
     return out
 
 
@@ -61,6 +73,7 @@ def square_distance(src_pm, dst_pm):
     out = torch.empty(B, S, N, dtype=torch.float32, device=src_pm.device)
     check(lib().dvcp_square_distance(cloud_pm(src_pm), cloud_pm(dst_pm), B, S, N, ptr(out),
                                      stream_ptr(src_pm.device)), "dvcp_square_distance")
+    _count(1)
     return out
 
 
@@ -76,6 +89,7 @@ def ball_query(radius, nsample, xyz_pm, new_xyz_pm):
     out = torch.empty(B, S, nsample, dtype=torch.int64, device=xyz_pm.device)
     check(lib().dvcp_ball_query(cloud_pm(xyz_pm), cloud_pm(new_xyz_pm), B, N, S, radius2_f32(radius), nsample,
                                 ptr(out), stream_ptr(xyz_pm.device)), "dvcp_ball_query")
+    _count(1)
     return out
 
 
@@ -88,6 +102,7 @@ def index_points(points, idx):
     out = torch.empty(*idx.shape, C, dtype=torch.float32, device=points.device)
     check(lib().dvcp_index_points(ptr(points), ptr(idx), B, N, C, M, ptr(out), stream_ptr(points.device)),
           "dvcp_index_points")
+    _count(1)
     return out
 
 
@@ -118,6 +133,7 @@ def sa_layer(xyz_cloud, feats_cloud, D, centroid_idx32, B, N, S, radius, nsample
                                radius2_f32(radius), nsample, mlp.layers, mlp.n, ptr(out), ptr(oxyz),
                                stream_ptr(device))
     check(code, "dvcp_sa_layer")
+    _count(1)
     return oxyz, out
 
 
@@ -128,6 +144,7 @@ def weighting_scores(X, W1, b1, W2, b2, W3, b3):
     scores = torch.empty(B, S, dtype=torch.float32, device=X.device)
     check(lib().dvcp_weighting_scores(ptr(X), B, S, ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(W3), ptr(b3),
                                       ptr(scores), stream_ptr(X.device)), "dvcp_weighting_scores")
+    _count(1)
     return scores
 
 
@@ -137,6 +154,7 @@ def topk(scores, K):
     scores = _f32c(scores)
     out = torch.empty(B, K, dtype=torch.int64, device=scores.device)
     check(lib().dvcp_topk(ptr(scores), B, S, K, ptr(out), stream_ptr(scores.device)), "dvcp_topk")
+    _count(1)
     return out
 
 
@@ -160,6 +178,7 @@ def keypoint_stage(src_pts, topk_idx, kp_start, src_feat, R_init, radius, nsampl
                                      ptr(src_feat), S, ptr(R_init), radius2_f32(radius), nsample, dfe, quirks,
                                      ptr(keypts), ptr(picked), ptr(cat), ptr(sdfe), ptr(centres), stream_ptr(dev))
     check(code, "dvcp_keypoint_stage")
+    _count(1)
     return keypts, picked, cat, sdfe, centres
 
 
@@ -179,6 +198,7 @@ def candidates(centres, r, s, G=None):
     out = torch.empty(*lead, G * G * G, 3, dtype=torch.float32, device=centres.device)
     check(lib().dvcp_candidates(ptr(centres), M, float(r), float(s), G, ptr(out), stream_ptr(centres.device)),
           "dvcp_candidates")
+    _count(1)
     return out
 
 
@@ -191,6 +211,7 @@ def knn(ref_cloud, device, B, N, query, K, want64=True, want32=False):
     i32 = torch.empty(B, Q, K, dtype=torch.int32, device=device) if want32 else None
     check(lib().dvcp_knn(ref_cloud, ptr(query), B, N, Q, K, ptr(dist), ptr(i64), ptr(i32), stream_ptr(device)),
           "dvcp_knn")
+    _count(1)
     return dist, i64, i32
 
 
@@ -200,6 +221,7 @@ def dfe_tgt_fused(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, dfe, qui
     out = torch.empty(B, Q, 32, dtype=torch.float32, device=cand.device)
     check(lib().dvcp_dfe_tgt_fused(ptr(_f32c(cand)), tgt_cloud, ptr(_f32c(tgt_feat)), ptr(knn_dist), ptr(knn_idx32),
                                    B, N, Q, dfe, quirks, ptr(out), stream_ptr(cand.device)), "dvcp_dfe_tgt_fused")
+    _count(1)
     return out
 
 
@@ -214,6 +236,7 @@ def dfe_dense(X, dfe):
     out = torch.empty(*X.shape[:-2], 32, dtype=torch.float32, device=X.device)
     check(lib().dvcp_dfe_dense(ptr(X), 0 if X.dtype == torch.float32 else 1, rows, K, dfe, ptr(out),
                                stream_ptr(X.device)), "dvcp_dfe_dense")
+    _count(1)
     return out
 
 
@@ -229,6 +252,7 @@ def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False):
     logits = torch.empty(M, C, dtype=torch.float32, device=dev) if want_logits else None
     check(lib().dvcp_cpg(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params, ptr(vcp),
                          ptr(logits), ptr(ws), nbytes, stream_ptr(dev)), "dvcp_cpg")
+    _count(5)
     return vcp, logits
 
 
@@ -242,6 +266,7 @@ def kabsch(x, y):
     t = torch.empty(B, 3, 1, dtype=torch.float64, device=x.device)
     check(lib().dvcp_kabsch(ptr(x.contiguous()), ptr(y.contiguous()), 0 if x.dtype == torch.float32 else 1, B, n,
                             ptr(R), ptr(t), stream_ptr(x.device)), "dvcp_kabsch")
+    _count(1)
     return R, t
 
 
@@ -260,4 +285,5 @@ def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False)
     t1 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev) if want_first else None
     check(lib().dvcp_kabsch_refine(ptr(x), ptr(y_pred), ptr(R_true), ptr(t_true), B, n, keep, ptr(R2), ptr(t2),
                                    ptr(R1), ptr(t1), stream_ptr(dev)), "dvcp_kabsch_refine")
+    _count(1)
     return R2, t2, R1, t1
