@@ -23,6 +23,10 @@ class Cloud(ctypes.Structure):
     _fields_ = [("base", c_vp), ("bstride", c_i64), ("pstride", c_i64), ("cstride", c_i64)]
 
 
+class CloudIndex(ctypes.Structure):
+    _fields_ = [("sorted_xyz", c_vp), ("sorted_idx", c_vp), ("bucket_box", c_vp), ("cap", c_i32)]
+
+
 class MlpLayer(ctypes.Structure):
     _fields_ = [("W", c_vp), ("b", c_vp), ("alpha", c_vp), ("beta", c_vp), ("in_ch", c_i32), ("out_ch", c_i32)]
 
@@ -39,13 +43,15 @@ class CpgParams(ctypes.Structure):
 SIGNATURES = {
     "dvcp_abi_version": (c_i32, []),
     "dvcp_error_string": (ctypes.c_char_p, [c_i32]),
-    "dvcp_fps": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dvcp_fps": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_vp]),
+    "dvcp_index_capacity": (c_i32, [c_i32]),
+    "dvcp_build_index": (c_i32, [Cloud, c_i32, c_i32, CloudIndex, c_vp]),
     "dvcp_fps_plain": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_square_distance": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_ball_query": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp]),
     "dvcp_index_points": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "dvcp_sa_layer": (c_i32, [Cloud, Cloud, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32,
-                              ctypes.POINTER(MlpLayer), c_i32, c_vp, c_vp, c_vp]),
+                              ctypes.POINTER(MlpLayer), c_i32, CloudIndex, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_weighting_scores": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_topk": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_keypoint_stage": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_f32,
@@ -53,6 +59,8 @@ SIGNATURES = {
     "dvcp_grid_size": (c_i32, [c_f64, c_f64]),
     "dvcp_candidates": (c_i32, [c_vp, c_i64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "dvcp_knn": (c_i32, [Cloud, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dvcp_knn_indexed": (c_i32, [CloudIndex, c_vp, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
+                                 c_vp]),
     "dvcp_dfe_tgt_fused": (c_i32, [c_vp, Cloud, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, DfeParams, c_i32, c_vp,
                                    c_vp]),
     "dvcp_dfe_dense": (c_i32, [c_vp, c_i32, c_i64, c_i32, DfeParams, c_vp, c_vp]),
@@ -121,6 +129,7 @@ def cloud_cm(t: torch.Tensor) -> Cloud:
 
 
 NULL_CLOUD = Cloud(None, 0, 0, 0)
+NULL_INDEX = CloudIndex(None, None, None, 0)
 
 
 def dfe_params(w1, b1, w2, b2, w3, b3) -> DfeParams:

@@ -97,10 +97,11 @@ ball_query_kernel(Cloud xyz, Cloud qry, int N, int S, float r2, int nsample, int
 }
 
 // ------------------------------------------------- fused set abstraction -----
-// One warp per centroid: ball query (as above) + for every member the shared MLP
+// One warp per centroid: ball query + for every member the shared MLP
 // [3+D] -> C1 -> C2 -> C3 (conv1x1 + folded eval-BN + ReLU) + running max.
-// Padding slots of the reference repeat member 0, so they do not change the max.
-// Lane l owns output channel l (C3 <= 32... C3 up to 64 uses two per lane).
+// Padding slots of the reference repeat member 0, so they do not change the max;
+// only the SET of the first `nsample` members (ascending index) matters.
+// Lane l owns output channels l and l+32.
 struct SaParams {
     const float *W[3], *b[3], *alpha[3], *beta[3];
     int cin[3], cout[3];
@@ -111,121 +112,479 @@ constexpr int SA_WARPS = 16;
 constexpr int SA_MAXC = 64;       // widest layer supported
 constexpr int SA_MAXIN = 3 + 64;  // widest input supported
 
+struct SaWeights {
+    const float *swt;
+    int woff[3], boff[3];
+};
+
+__device__ __forceinline__ int sa_weight_floats(const SaParams &P, SaWeights &w) {
+    int off = 0;
+    for (int l = 0; l < P.n_layers; ++l) {
+        w.woff[l] = off;
+        off += P.cin[l] * P.cout[l];
+        w.boff[l] = off;
+        off += 3 * P.cout[l];
+    }
+    return off;
+}
+
+__device__ __forceinline__ void sa_stage_weights(const SaParams &P, float *swt, SaWeights &w) {
+    sa_weight_floats(P, w);
+    w.swt = swt;
+    for (int l = 0; l < P.n_layers; ++l) {
+        for (int i = threadIdx.x; i < P.cin[l] * P.cout[l]; i += blockDim.x) swt[w.woff[l] + i] = P.W[l][i];
+        for (int i = threadIdx.x; i < P.cout[l]; i += blockDim.x) {
+            swt[w.boff[l] + i] = P.b[l][i];
+            swt[w.boff[l] + P.cout[l] + i] = P.alpha[l][i];
+            swt[w.boff[l] + 2 * P.cout[l] + i] = P.beta[l][i];
+        }
+    }
+}
+
+// Shared MLP of ONE member, evaluated by the whole warp (lane = output channel).
+// rel = member - centre; extra channels read from `feats` at original index pn.
+__device__ __forceinline__ void sa_member_mlp(const SaParams &P, const SaWeights &w, const Cloud &feats, int D,
+                                              int b, int pn, float rx, float ry, float rz, float &best0,
+                                              float &best1) {
+    const int lane = lane_id();
+    float cur0 = 0.f, cur1 = 0.f;
+    int cin = 3 + D;
+    for (int l = 0; l < P.n_layers; ++l) {
+        const int co = P.cout[l];
+        const float *W = w.swt + w.woff[l];
+        const float *bb = w.swt + w.boff[l];
+        const int o0 = lane, o1 = lane + 32;
+        float acc0 = 0.f, acc1 = 0.f;
+        if (l == 0) {
+            for (int k = 0; k < cin; ++k) {
+                const float v = k == 0 ? rx : (k == 1 ? ry : (k == 2 ? rz : feats.at(b, pn, k - 3)));
+                if (o0 < co) acc0 = fmaf(W[o0 * cin + k], v, acc0);
+                if (o1 < co) acc1 = fmaf(W[o1 * cin + k], v, acc1);
+            }
+        } else {
+            for (int k = 0; k < cin; ++k) {
+                const float v = (k < 32) ? __shfl_sync(0xffffffffu, cur0, k) : __shfl_sync(0xffffffffu, cur1, k - 32);
+                if (o0 < co) acc0 = fmaf(W[o0 * cin + k], v, acc0);
+                if (o1 < co) acc1 = fmaf(W[o1 * cin + k], v, acc1);
+            }
+        }
+        cur0 = o0 < co ? fmaxf(fmaf(acc0 + bb[o0], bb[co + o0], bb[2 * co + o0]), 0.f) : 0.f;
+        cur1 = o1 < co ? fmaxf(fmaf(acc1 + bb[o1], bb[co + o1], bb[2 * co + o1]), 0.f) : 0.f;
+        cin = co;
+    }
+    best0 = fmaxf(best0, cur0);
+    best1 = fmaxf(best1, cur1);
+}
+
+// Brute-force variant: walks the whole cloud (any N). When `need` is given, only
+// centroids flagged there are processed (overflow pass of the pruned kernel).
 __global__ void __launch_bounds__(SA_WARPS * 32)
-sa_layer_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict__ cidx, int N, int S, float r2,
-                int nsample, SaParams P, float *__restrict__ out_feat, float *__restrict__ out_xyz) {
+sa_layer_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict__ cidx, int B, int N, int S, float r2,
+                int nsample, SaParams P, const unsigned char *__restrict__ need, float *__restrict__ out_feat,
+                float *__restrict__ out_xyz) {
     extern __shared__ float smem[];
     float *sx = smem, *sy = sx + BQ_TILE, *sz = sy + BQ_TILE, *sp = sz + BQ_TILE;
-    float *swt = sp + BQ_TILE;   // weights: per layer W[cout][cin], b, alpha, beta
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // stage weights
-    int woff[3], boff[3];
-    {
-        int off = 0;
-        for (int l = 0; l < P.n_layers; ++l) {
-            woff[l] = off;
-            off += P.cin[l] * P.cout[l];
-            boff[l] = off;
-            off += 3 * P.cout[l];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SaWeights w;
+    sa_stage_weights(P, sp + BQ_TILE, w);
+    const int groups = (S + SA_WARPS - 1) / SA_WARPS;
+    const int clast = P.cout[P.n_layers - 1];
+    // work item = (cloud b, group of SA_WARPS centroids); a small persistent grid walks
+    // them when this is the (normally empty) overflow pass
+    for (int item = blockIdx.x; item < B * groups; item += gridDim.x) {
+        const int b = item / groups;
+        const int s = (item - b * groups) * SA_WARPS + warp;
+        bool active = s < S;
+        if (need) {
+            active = active && need[(int64_t)b * S + s] != 0;
+            if (!__syncthreads_or(active)) continue;
         }
-        for (int l = 0; l < P.n_layers; ++l) {
-            for (int i = threadIdx.x; i < P.cin[l] * P.cout[l]; i += blockDim.x) swt[woff[l] + i] = P.W[l][i];
-            for (int i = threadIdx.x; i < P.cout[l]; i += blockDim.x) {
-                swt[boff[l] + i] = P.b[l][i];
-                swt[boff[l] + P.cout[l] + i] = P.alpha[l][i];
-                swt[boff[l] + 2 * P.cout[l] + i] = P.beta[l][i];
+        const int c = active ? cidx[(int64_t)b * S + s] : 0;
+        const float qx = xyz.at(b, c, 0), qy = xyz.at(b, c, 1), qz = xyz.at(b, c, 2);
+        const float qq = norm2_nofma(qx, qy, qz);
+        if (active && out_xyz && lane < 3)
+            out_xyz[((int64_t)b * S + s) * 3 + lane] = lane == 0 ? qx : (lane == 1 ? qy : qz);
+        float best0 = -INFINITY, best1 = -INFINITY;
+        int cnt = active ? 0 : nsample;
+        for (int base = 0; base < N; base += BQ_TILE) {
+            const int count = min(BQ_TILE, N - base);
+            __syncthreads();
+            stage_tile(xyz, b, base, count, sx, sy, sz, sp);
+            __syncthreads();
+            if (cnt >= nsample) continue;
+            for (int i = 0; i < count && cnt < nsample; i += 32) {
+                const int n = i + lane;
+                const bool ok = n < count;
+                const float px = ok ? sx[n] : 0.f, py = ok ? sy[n] : 0.f, pz = ok ? sz[n] : 0.f,
+                            pp = ok ? sp[n] : 0.f;
+                const float d2 = sqdist_expanded(qx, qy, qz, qq, px, py, pz, pp);
+                const bool in = ok && !(d2 > r2);
+                unsigned m = __ballot_sync(0xffffffffu, in);
+                if (!m) continue;
+                int take = min(__popc(m), nsample - cnt);   // members of this step, ascending index
+                cnt += __popc(m);
+                while (take-- > 0) {
+                    const int src_lane = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float mx = __shfl_sync(0xffffffffu, px, src_lane);
+                    const float my = __shfl_sync(0xffffffffu, py, src_lane);
+                    const float mz = __shfl_sync(0xffffffffu, pz, src_lane);
+                    sa_member_mlp(P, w, feats, D, b, base + i + src_lane, mx - qx, my - qy, mz - qz, best0, best1);
+                }
             }
         }
+        if (active) {
+            if (lane < clast) out_feat[((int64_t)b * S + s) * clast + lane] = best0;
+            if (lane + 32 < clast) out_feat[((int64_t)b * S + s) * clast + lane + 32] = best1;
+        }
+        __syncthreads();
     }
-    const int s = blockIdx.x * SA_WARPS + warp;
-    const bool active = s < S;
-    const int c = active ? cidx[(int64_t)b * S + s] : 0;
+}
+
+// Pruned variant: uses the spatial index (Morton buckets + boxes). A bucket can
+// hold a member only if its box is within sqrt(r^2 + E) of the centre, where E
+// bounds the rounding error of the expanded-form distance: |d2_fl - d2| <=
+// 12 * 2^-24 * (|q| + |p|)^2 (three roundings in the dot product and each squared
+// norm, two in the final sums). Flagged buckets are tested point by point with
+// the exact arithmetic, members are collected, and -- only if there are more than
+// nsample -- the nsample smallest indices are kept, as the reference's sort does.
+constexpr int SAP_WARPS = 8;
+constexpr int SAP_LIST = 512;
+
+__global__ void __launch_bounds__(SAP_WARPS * 32)
+sa_layer_pruned_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict__ cidx, int N, int S, float r2,
+                       int nsample, SaParams P, dvcp_cloud_index_t index, unsigned char *__restrict__ need,
+                       float *__restrict__ out_feat, float *__restrict__ out_xyz) {
+    extern __shared__ float smem[];
+    int *l_id = reinterpret_cast<int *>(smem);                 // [SAP_WARPS][SAP_LIST]
+    float *l_x = smem + SAP_WARPS * SAP_LIST;                  // x, y, z planes follow
+    float *l_y = l_x + SAP_WARPS * SAP_LIST;
+    float *l_z = l_y + SAP_WARPS * SAP_LIST;
+    float *swt = l_z + SAP_WARPS * SAP_LIST;
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SaWeights w;
+    sa_stage_weights(P, swt, w);
+    __syncthreads();
+    const int s = blockIdx.x * SAP_WARPS + warp;
+    if (s >= S) return;
+    int *mid = l_id + warp * SAP_LIST;
+    float *mx_ = l_x + warp * SAP_LIST, *my_ = l_y + warp * SAP_LIST, *mz_ = l_z + warp * SAP_LIST;
+    const int c = cidx[(int64_t)b * S + s];
     const float qx = xyz.at(b, c, 0), qy = xyz.at(b, c, 1), qz = xyz.at(b, c, 2);
     const float qq = norm2_nofma(qx, qy, qz);
-    if (active && out_xyz && lane < 3) out_xyz[((int64_t)b * S + s) * 3 + lane] = lane == 0 ? qx : (lane == 1 ? qy : qz);
-    const int clast = P.cout[P.n_layers - 1];
-    float best0 = -INFINITY, best1 = -INFINITY;   // channels lane, lane+32
-    int cnt = active ? 0 : nsample;
-
-    for (int base = 0; base < N; base += BQ_TILE) {
-        const int count = min(BQ_TILE, N - base);
-        __syncthreads();
-        stage_tile(xyz, b, base, count, sx, sy, sz, sp);
-        __syncthreads();
-        if (cnt >= nsample) continue;
-        for (int i = 0; i < count && cnt < nsample; i += 32) {
-            const int n = i + lane;
-            const bool ok = n < count;
-            const float px = ok ? sx[n] : 0.f, py = ok ? sy[n] : 0.f, pz = ok ? sz[n] : 0.f,
-                        pp = ok ? sp[n] : 0.f;
-            const float d2 = sqdist_expanded(qx, qy, qz, qq, px, py, pz, pp);
-            const bool in = ok && !(d2 > r2);
-            unsigned m = __ballot_sync(0xffffffffu, in);
-            if (!m) continue;
-            // members of this step, ascending; keep only the first nsample overall
-            int take = min(__popc(m), nsample - cnt);
-            cnt += __popc(m);
-            while (take-- > 0) {
-                const int src_lane = __ffs(m) - 1;
-                m &= m - 1;
-                const int pn = base + i + src_lane;
-                // input row: [p - centre (3), feats (D)], every lane holds the full row
-                float a_in[SA_MAXIN];
-                const float mx = __shfl_sync(0xffffffffu, px, src_lane);
-                const float my = __shfl_sync(0xffffffffu, py, src_lane);
-                const float mz = __shfl_sync(0xffffffffu, pz, src_lane);
-                a_in[0] = mx - qx;
-                a_in[1] = my - qy;
-                a_in[2] = mz - qz;
-                for (int d = 0; d < D; ++d) a_in[3 + d] = feats.at(b, pn, d);
-                // generic layers through shared scratch would be slow; layer widths are
-                // small, so every lane computes up to two output channels per layer and
-                // the row is re-broadcast with shuffles.
-                float cur0 = 0.f, cur1 = 0.f;
-                int cin = 3 + D;
-                for (int l = 0; l < P.n_layers; ++l) {
-                    const int co = P.cout[l];
-                    const float *W = swt + woff[l];
-                    const float *bb = swt + boff[l];
-                    float y0 = 0.f, y1 = 0.f;
-                    const int o0 = lane, o1 = lane + 32;
-                    if (l == 0) {
-                        if (o0 < co) {
-                            float acc = 0.f;
-                            for (int k = 0; k < cin; ++k) acc = fmaf(W[o0 * cin + k], a_in[k], acc);
-                            y0 = acc;
-                        }
-                        if (o1 < co) {
-                            float acc = 0.f;
-                            for (int k = 0; k < cin; ++k) acc = fmaf(W[o1 * cin + k], a_in[k], acc);
-                            y1 = acc;
-                        }
-                    } else {
-                        float acc0 = 0.f, acc1 = 0.f;
-                        for (int k = 0; k < cin; ++k) {
-                            const float v = (k < 32) ? __shfl_sync(0xffffffffu, cur0, k)
-                                                     : __shfl_sync(0xffffffffu, cur1, k - 32);
-                            if (o0 < co) acc0 = fmaf(W[o0 * cin + k], v, acc0);
-                            if (o1 < co) acc1 = fmaf(W[o1 * cin + k], v, acc1);
-                        }
-                        y0 = acc0;
-                        y1 = acc1;
-                    }
-                    if (o0 < co) y0 = fmaxf(fmaf(y0 + bb[o0], bb[co + o0], bb[2 * co + o0]), 0.f);
-                    if (o1 < co) y1 = fmaxf(fmaf(y1 + bb[o1], bb[co + o1], bb[2 * co + o1]), 0.f);
-                    cur0 = y0;
-                    cur1 = y1;
-                    cin = co;
-                }
-                best0 = fmaxf(best0, cur0);
-                best1 = fmaxf(best1, cur1);
-            }
+    if (out_xyz && lane < 3) out_xyz[((int64_t)b * S + s) * 3 + lane] = lane == 0 ? qx : (lane == 1 ? qy : qz);
+    const float qn = sqrtf(qq) * 1.0001f;
+    const int cap = index.cap, NB = cap / 32, T = NB / 32;
+    const float *box = index.bucket_box + (int64_t)b * NB * 8;
+    const float *sxp = index.sorted_xyz + (int64_t)b * 3 * cap;
+    const int32_t *sip = index.sorted_idx + (int64_t)b * cap;
+    // can a box (min n*, max x*) hold a member?  lb <= r2 + E, E = rounding bound of the expanded form
+    auto box_may_hold = [&](float nx, float ny, float nz, float xx, float xy, float xz) -> bool {
+        const float ex = fmaxf(fmaxf(nx - qx, qx - xx), 0.f);
+        const float ey = fmaxf(fmaxf(ny - qy, qy - xy), 0.f);
+        const float ez = fmaxf(fmaxf(nz - qz, qz - xz), 0.f);
+        const float lb = ex * ex + ey * ey + ez * ez;
+        const float ax = fmaxf(fabsf(nx), fabsf(xx)), ay = fmaxf(fabsf(ny), fabsf(xy)), az = fmaxf(fabsf(nz), fabsf(xz));
+        const float pn = sqrtf(ax * ax + ay * ay + az * az) * 1.0001f;
+        const float E = 8e-7f * (qn + pn) * (qn + pn);
+        return lb * 0.9999f <= r2 + E;
+    };
+    // level 1: lane l tests the union box of its T Morton-consecutive buckets
+    float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8) + 1);
+        if (b1.z > 0.f) {
+            snx = fminf(snx, b0.x); sny = fminf(sny, b0.y); snz = fminf(snz, b0.z);
+            sxx = fmaxf(sxx, b0.w); sxy = fmaxf(sxy, b1.x); sxz = fmaxf(sxz, b1.y);
         }
     }
-    if (active) {
-        if (lane < clast) out_feat[((int64_t)b * S + s) * clast + lane] = best0;
-        if (lane + 32 < clast) out_feat[((int64_t)b * S + s) * clast + lane + 32] = best1;
+    int cnt = 0;
+    unsigned sm = __ballot_sync(0xffffffffu, snx <= sxx && box_may_hold(snx, sny, snz, sxx, sxy, sxz));
+    while (sm) {
+        const int sl = __ffs(sm) - 1;
+        sm &= sm - 1;
+        bool flag = false;
+        if (lane < T) {   // level 2: the buckets of that group, one per lane
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+            flag = b1.z > 0.f && box_may_hold(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+        }
+        unsigned fm = __ballot_sync(0xffffffffu, flag);
+        while (fm) {
+            const int j2 = sl * T + __ffs(fm) - 1;
+            fm &= fm - 1;
+            const int pos = j2 * 32 + lane;
+            const float px = __ldg(sxp + pos), py = __ldg(sxp + cap + pos), pz = __ldg(sxp + 2 * cap + pos);
+            const int id = __ldg(sip + pos);
+            const float d2 = sqdist_expanded(qx, qy, qz, qq, px, py, pz, norm2_nofma(px, py, pz));
+            const bool in = id >= 0 && !(d2 > r2);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+            if (in && slot < SAP_LIST) {
+                mid[slot] = id;
+                mx_[slot] = px;
+                my_[slot] = py;
+                mz_[slot] = pz;
+            }
+            cnt += __popc(m);
+        }
     }
+    if (need && lane == 0) need[(int64_t)b * S + s] = cnt > SAP_LIST;
+    if (cnt > SAP_LIST) return;   // rare: the brute-force pass redoes this centroid
+    __syncwarp();
+    const int clast = P.cout[P.n_layers - 1];
+    float best0 = -INFINITY, best1 = -INFINITY;
+    for (int i = 0; i < cnt; ++i) {
+        const int id = mid[i];
+        if (cnt > nsample) {   // keep only the nsample smallest indices
+            int smaller = 0;
+            for (int k = lane; k < cnt; k += 32) smaller += mid[k] < id;
+            smaller = __reduce_add_sync(0xffffffffu, smaller);
+            if (smaller >= nsample) continue;
+        }
+        sa_member_mlp(P, w, feats, D, b, id, mx_[i] - qx, my_[i] - qy, mz_[i] - qz, best0, best1);
+    }
+    if (lane < clast) out_feat[((int64_t)b * S + s) * clast + lane] = best0;
+    if (lane + 32 < clast) out_feat[((int64_t)b * S + s) * clast + lane + 32] = best1;
+}
+
+// Fast variant for the DeepVCP feature layer (three layers C1=16, C2=16, C3=32,
+// input 3 + D with D in {0, 3}). A warp works on SAF_CPW centroids at a time:
+// phase 1 finds the members of each (as above) and appends (id, member - centre,
+// centroid slot) to a warp-local list; phase 2 evaluates the shared MLP with ONE
+// MEMBER PER LANE (weights broadcast from shared memory as float4), transposes
+// the 32 outputs through shared memory and folds them into the per-centroid
+// maxima. Compared with the lane-per-channel form this removes the shuffles and
+// keeps all 32 lanes busy although a ball holds only a handful of points.
+constexpr int SAF_WARPS = 8;
+constexpr int SAF_CPW = 8;      // centroids per warp pass
+constexpr int SAF_LIST = 256;   // list entries per warp
+
+template <int CIN>
+struct SafSmem {
+    // weights, rows padded to float4
+    static constexpr int LD1 = (CIN + 3) / 4 * 4;
+    float w1[16 * LD1], w2[16 * 16], w3[32 * 16];
+    float bn1[3 * 16], bn2[3 * 16], bn3[3 * 32];   // bias, alpha, beta
+    int id[SAF_WARPS][SAF_LIST];
+    float rx[SAF_WARPS][SAF_LIST], ry[SAF_WARPS][SAF_LIST], rz[SAF_WARPS][SAF_LIST];
+    unsigned char slot[SAF_WARPS][SAF_LIST];
+    float tile[SAF_WARPS][32][33];
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(SAF_WARPS * 32)
+sa_layer_fast_kernel(Cloud xyz, Cloud feats, const int32_t *__restrict__ cidx, int N, int S, float r2, int nsample,
+                     SaParams P, dvcp_cloud_index_t index, unsigned char *__restrict__ need,
+                     float *__restrict__ out_feat, float *__restrict__ out_xyz) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SafSmem<CIN> &sm = *reinterpret_cast<SafSmem<CIN> *>(smem_raw);
+    constexpr int LD1 = SafSmem<CIN>::LD1;
+    constexpr int D = CIN - 3;
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 16 * LD1; i += blockDim.x) {
+        const int o = i / LD1, k = i - o * LD1;
+        sm.w1[i] = k < CIN ? P.W[0][o * CIN + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.w2[i] = P.W[1][i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sm.w3[i] = P.W[2][i];
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        sm.bn1[i] = P.b[0][i]; sm.bn1[16 + i] = P.alpha[0][i]; sm.bn1[32 + i] = P.beta[0][i];
+        sm.bn2[i] = P.b[1][i]; sm.bn2[16 + i] = P.alpha[1][i]; sm.bn2[32 + i] = P.beta[1][i];
+    }
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+        sm.bn3[i] = P.b[2][i]; sm.bn3[32 + i] = P.alpha[2][i]; sm.bn3[64 + i] = P.beta[2][i];
+    }
+    __syncthreads();
+    int *mid = sm.id[warp];
+    float *mrx = sm.rx[warp], *mry = sm.ry[warp], *mrz = sm.rz[warp];
+    unsigned char *mslot = sm.slot[warp];
+    const int cap = index.cap, NB = cap / 32, T = NB / 32;
+    const float *box = index.bucket_box + (int64_t)b * NB * 8;
+    const float *sxp = index.sorted_xyz + (int64_t)b * 3 * cap;
+    const int32_t *sip = index.sorted_idx + (int64_t)b * cap;
+    // union box of this lane's T Morton-consecutive buckets
+    float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8) + 1);
+        if (b1.z > 0.f) {
+            snx = fminf(snx, b0.x); sny = fminf(sny, b0.y); snz = fminf(snz, b0.z);
+            sxx = fmaxf(sxx, b0.w); sxy = fmaxf(sxy, b1.x); sxz = fmaxf(sxz, b1.y);
+        }
+    }
+    const int groups = (S + SAF_CPW - 1) / SAF_CPW;
+    for (int g = blockIdx.x * SAF_WARPS + warp; g < groups; g += gridDim.x * SAF_WARPS) {
+        const int s0 = g * SAF_CPW;
+        int total = 0;
+        unsigned overflow = 0;   // bit c: centroid c must be redone by the brute-force pass
+        // ---------------- phase 1: members of each centroid ----------------
+        for (int c = 0; c < SAF_CPW && s0 + c < S; ++c) {
+            const int s = s0 + c;
+            const int ci = cidx[(int64_t)b * S + s];
+            const float qx = xyz.at(b, ci, 0), qy = xyz.at(b, ci, 1), qz = xyz.at(b, ci, 2);
+            const float qq = norm2_nofma(qx, qy, qz);
+            if (out_xyz && lane < 3) out_xyz[((int64_t)b * S + s) * 3 + lane] = lane == 0 ? qx : (lane == 1 ? qy : qz);
+            const float qn = sqrtf(qq) * 1.0001f;
+            auto box_may_hold = [&](float nx, float ny, float nz, float xx, float xy, float xz) -> bool {
+                const float ex = fmaxf(fmaxf(nx - qx, qx - xx), 0.f);
+                const float ey = fmaxf(fmaxf(ny - qy, qy - xy), 0.f);
+                const float ez = fmaxf(fmaxf(nz - qz, qz - xz), 0.f);
+                const float lb = ex * ex + ey * ey + ez * ez;
+                const float ax = fmaxf(fabsf(nx), fabsf(xx)), ay = fmaxf(fabsf(ny), fabsf(xy)),
+                            az = fmaxf(fabsf(nz), fabsf(xz));
+                const float pn = sqrtf(ax * ax + ay * ay + az * az) * 1.0001f;
+                const float E = 8e-7f * (qn + pn) * (qn + pn);
+                return lb * 0.9999f <= r2 + E;
+            };
+            const int start = total;
+            int cnt = 0;
+            unsigned smk = __ballot_sync(0xffffffffu, snx <= sxx && box_may_hold(snx, sny, snz, sxx, sxy, sxz));
+            while (smk) {
+                const int sl = __ffs(smk) - 1;
+                smk &= smk - 1;
+                bool flag = false;
+                if (lane < T) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+                    flag = b1.z > 0.f && box_may_hold(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                }
+                unsigned fm = __ballot_sync(0xffffffffu, flag);
+                while (fm) {
+                    const int pos = (sl * T + __ffs(fm) - 1) * 32 + lane;
+                    fm &= fm - 1;
+                    const float px = __ldg(sxp + pos), py = __ldg(sxp + cap + pos), pz = __ldg(sxp + 2 * cap + pos);
+                    const int id = __ldg(sip + pos);
+                    const float d2 = sqdist_expanded(qx, qy, qz, qq, px, py, pz, norm2_nofma(px, py, pz));
+                    const bool in = id >= 0 && !(d2 > r2);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    const int e = start + cnt + __popc(m & ((1u << lane) - 1u));
+                    if (in && e < SAF_LIST) {
+                        mid[e] = id;
+                        mrx[e] = px - qx;
+                        mry[e] = py - qy;
+                        mrz[e] = pz - qz;
+                        mslot[e] = (unsigned char)c;
+                    }
+                    cnt += __popc(m);
+                }
+            }
+            __syncwarp();
+            if (start + cnt > SAF_LIST) {
+                overflow |= 1u << c;   // does not fit: leave it to the brute-force pass
+                continue;
+            }
+            if (cnt == 0) out_feat[((int64_t)b * S + s) * 32 + lane] = -INFINITY;   // empty ball (as the other kernels)
+            if (cnt > nsample) {
+                // keep the nsample smallest indices (what the reference's sort keeps), compacting in place
+                int kept = 0;
+                // mark the dropped entries, then compact in a second sweep
+                for (int i = lane; i < cnt; i += 32) {
+                    const int id = mid[start + i];
+                    int smaller = 0;
+                    for (int k = 0; k < cnt; ++k) smaller += mid[start + k] < id;
+                    if (smaller >= nsample) mslot[start + i] = 0xff;   // dropped
+                }
+                __syncwarp();
+                kept = 0;
+                for (int i0 = 0; i0 < cnt; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool keep = i < cnt && mslot[start + i] != 0xff;
+                    int id = 0;
+                    float ax = 0.f, ay = 0.f, az = 0.f;
+                    if (i < cnt) { id = mid[start + i]; ax = mrx[start + i]; ay = mry[start + i]; az = mrz[start + i]; }
+                    const unsigned km = __ballot_sync(0xffffffffu, keep);
+                    __syncwarp();
+                    if (keep) {
+                        const int e = start + kept + __popc(km & ((1u << lane) - 1u));
+                        mid[e] = id; mrx[e] = ax; mry[e] = ay; mrz[e] = az; mslot[e] = (unsigned char)c;
+                    }
+                    kept += __popc(km);
+                    __syncwarp();
+                }
+                cnt = kept;
+            }
+            total = start + cnt;
+        }
+        __syncwarp();
+        if (need) {
+            for (int c = lane; c < SAF_CPW && s0 + c < S; c += 32) need[(int64_t)b * S + s0 + c] = (overflow >> c) & 1u;
+        }
+        // ---------------- phase 2: shared MLP, one member per lane ----------------
+        float best = 0.f;   // ReLU outputs are >= 0 and a ball always holds its own centre
+        int cur = -1;
+        auto flush = [&]() {
+            if (cur >= 0 && !((overflow >> cur) & 1u)) out_feat[((int64_t)b * S + s0 + cur) * 32 + lane] = best;
+        };
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            const bool ok = e < total;
+            float x[LD1];
+            x[0] = ok ? mrx[e] : 0.f;
+            x[1] = ok ? mry[e] : 0.f;
+            x[2] = ok ? mrz[e] : 0.f;
+#pragma unroll
+            for (int k = 3; k < LD1; ++k) x[k] = (k < CIN && ok) ? feats.at(b, mid[e], k - 3) : 0.f;
+            float h1[16], h2[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < LD1 / 4; ++k4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[o * LD1 + 4 * k4]);
+                    acc = fmaf(w.x, x[4 * k4], acc);
+                    acc = fmaf(w.y, x[4 * k4 + 1], acc);
+                    acc = fmaf(w.z, x[4 * k4 + 2], acc);
+                    acc = fmaf(w.w, x[4 * k4 + 3], acc);
+                }
+                h1[o] = fmaxf(fmaf(acc + sm.bn1[o], sm.bn1[16 + o], sm.bn1[32 + o]), 0.f);
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&sm.w2[o * 16 + 4 * k4]);
+                    acc = fmaf(w.x, h1[4 * k4], acc);
+                    acc = fmaf(w.y, h1[4 * k4 + 1], acc);
+                    acc = fmaf(w.z, h1[4 * k4 + 2], acc);
+                    acc = fmaf(w.w, h1[4 * k4 + 3], acc);
+                }
+                h2[o] = fmaxf(fmaf(acc + sm.bn2[o], sm.bn2[16 + o], sm.bn2[32 + o]), 0.f);
+            }
+            float(*tile)[33] = sm.tile[warp];
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&sm.w3[o * 16 + 4 * k4]);
+                    acc = fmaf(w.x, h2[4 * k4], acc);
+                    acc = fmaf(w.y, h2[4 * k4 + 1], acc);
+                    acc = fmaf(w.z, h2[4 * k4 + 2], acc);
+                    acc = fmaf(w.w, h2[4 * k4 + 3], acc);
+                }
+                tile[lane][o] = fmaxf(fmaf(acc + sm.bn3[o], sm.bn3[32 + o], sm.bn3[64 + o]), 0.f);
+            }
+            __syncwarp();
+            const int n = min(32, total - e0);
+            for (int i = 0; i < n; ++i) {   // lane = channel; entries are grouped by centroid
+                const int sl = mslot[e0 + i];
+                if (sl != cur) {
+                    flush();
+                    cur = sl;
+                    best = 0.f;
+                }
+                best = fmaxf(best, tile[i][lane]);
+            }
+            __syncwarp();
+        }
+        flush();
+        __syncwarp();
+    }
+    (void)D;
+    (void)N;
 }
 
 // ------------------------------------------------------ square_distance -----
@@ -367,11 +726,12 @@ extern "C" int dvcp_ball_query(dvcp_cloud_t xyz, dvcp_cloud_t new_xyz, int B, in
 
 extern "C" int dvcp_sa_layer(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *centroid_idx, int B,
                              int N, int S, float radius2, int nsample, const dvcp_mlp_layer_t *layers,
-                             int n_layers, float *out_feat, float *out_xyz, dvcp_stream_t stream) {
+                             int n_layers, dvcp_cloud_index_t index, unsigned char *overflow_ws, float *out_feat,
+                             float *out_xyz, dvcp_stream_t stream) {
     if (!xyz.base || !centroid_idx || !layers || !out_feat || B <= 0 || N <= 0 || S <= 0 || nsample <= 0)
         return DVCP_E_ARG;
     if (D < 0 || (D > 0 && !feats.base)) return DVCP_E_ARG;
-    if (n_layers < 1 || n_layers > 3 || 3 + D > SA_MAXIN) return DVCP_E_UNSUPPORTED;
+    if (n_layers < 1 || n_layers > 3 || 3 + D > SA_MAXIN || B > 65535) return DVCP_E_UNSUPPORTED;
     SaParams P;
     P.n_layers = n_layers;
     int cin = 3 + D;
@@ -386,11 +746,44 @@ extern "C" int dvcp_sa_layer(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const 
     }
     for (int l = n_layers; l < 3; ++l) { P.W[l] = P.b[l] = P.alpha[l] = P.beta[l] = nullptr; P.cin[l] = P.cout[l] = 0; }
     Cloud f = D > 0 ? as_cloud(feats) : Cloud{nullptr, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (4 * BQ_TILE + wfloats) * sizeof(float);
     DVCP_CUDA(cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((S + SA_WARPS - 1) / SA_WARPS, B);
-    sa_layer_kernel<<<grid, SA_WARPS * 32, smem, (cudaStream_t)stream>>>(as_cloud(xyz), f, D, centroid_idx, N, S,
-                                                                        radius2, nsample, P, out_feat, out_xyz);
+    const int items = B * ((S + SA_WARPS - 1) / SA_WARPS);
+    const bool pruned = index.sorted_xyz != nullptr;
+    const int grid = pruned ? (items < 2 * DVCP_NUM_SMS ? items : 2 * DVCP_NUM_SMS) : items;
+    if (pruned) {
+        if (!index.sorted_idx || !index.bucket_box || index.cap < N || !overflow_ws) return DVCP_E_ARG;
+        const bool fast = n_layers == 3 && P.cout[0] == 16 && P.cout[1] == 16 && P.cout[2] == 32 && (D == 0 || D == 3);
+        if (fast) {
+            const int groups = (S + SAF_CPW - 1) / SAF_CPW;
+            int gx = (groups + SAF_WARPS - 1) / SAF_WARPS;
+            dim3 fgrid(gx, B);
+            if (D == 0) {
+                auto k = sa_layer_fast_kernel<3>;
+                const int fs = (int)sizeof(SafSmem<3>);
+                DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+                k<<<fgrid, SAF_WARPS * 32, fs, st>>>(as_cloud(xyz), f, centroid_idx, N, S, radius2, nsample, P, index,
+                                                     overflow_ws, out_feat, out_xyz);
+            } else {
+                auto k = sa_layer_fast_kernel<6>;
+                const int fs = (int)sizeof(SafSmem<6>);
+                DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+                k<<<fgrid, SAF_WARPS * 32, fs, st>>>(as_cloud(xyz), f, centroid_idx, N, S, radius2, nsample, P, index,
+                                                     overflow_ws, out_feat, out_xyz);
+            }
+            DVCP_CHECK_LAUNCH();
+        } else {
+        const size_t psmem = (4 * (size_t)SAP_WARPS * SAP_LIST + wfloats) * sizeof(float);
+        DVCP_CUDA(cudaFuncSetAttribute(sa_layer_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        dim3 pgrid((S + SAP_WARPS - 1) / SAP_WARPS, B);
+        sa_layer_pruned_kernel<<<pgrid, SAP_WARPS * 32, psmem, st>>>(as_cloud(xyz), f, D, centroid_idx, N, S, radius2,
+                                                                    nsample, P, index, overflow_ws, out_feat, out_xyz);
+        DVCP_CHECK_LAUNCH();
+        }
+    }
+    sa_layer_kernel<<<grid, SA_WARPS * 32, smem, st>>>(as_cloud(xyz), f, D, centroid_idx, B, N, S, radius2, nsample, P,
+                                                      pruned ? overflow_ws : nullptr, out_feat, out_xyz);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

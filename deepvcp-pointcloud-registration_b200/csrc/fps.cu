@@ -13,6 +13,8 @@
 //    distance -- is below the bucket's current maximum. Everything lives in
 //    shared memory / registers of ONE CTA per cloud; one __syncthreads per round.
 //  * fps_generic_kernel   (float32/float64, any N <= 57344): plain O(N * npoint).
+#include <cstdlib>
+
 #include <cub/block/block_radix_sort.cuh>
 
 #include "common.cuh"
@@ -101,15 +103,18 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
-// WARPS warps; each warp owns 32 buckets of 32 points: capacity WARPS * 1024.
-template <int WARPS>
+// WARPS warps; each warp owns BPW buckets of 32 points: capacity WARPS * BPW * 32.
+// Bucket j (32 consecutive points of the Morton order) belongs to warp j % WARPS,
+// slot j / WARPS: spatial neighbours are spread over the warps, so the few
+// buckets a round revisits are processed in parallel instead of by one warp.
+template <int WARPS, int BPW>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int64_t cs, int N,
                     int npoint, const int64_t *__restrict__ start, int64_t *__restrict__ out64,
-                    int32_t *__restrict__ out32) {
+                    int32_t *__restrict__ out32, dvcp_cloud_index_t index) {
     constexpr int THREADS = WARPS * 32;
-    constexpr int CAP = WARPS * 1024;
-    constexpr int ITEMS = 32;
+    constexpr int CAP = WARPS * BPW * 32;
+    constexpr int ITEMS = BPW;
     using Sort = cub::BlockRadixSort<unsigned, THREADS, ITEMS, unsigned>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sx = reinterpret_cast<float *>(smem_raw);
@@ -122,7 +127,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
 
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float *p = base + (int64_t)b * bs;
-    const unsigned startidx = (unsigned)start[b];
+    const unsigned startidx = start ? (unsigned)start[b] : 0u;
 
     // ---- cloud bounding box -> Morton keys -> block sort (prologue, once) ----
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -144,7 +149,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         }
     }
     __syncthreads();
-    float scale[3];
+    float ext = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float a = INFINITY, z = -INFINITY;
@@ -153,8 +158,10 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
             z = fmaxf(z, s_box[3 + c][w]);
         }
         mn[c] = a;
-        scale[c] = (z > a) ? 1023.0f / (z - a) : 0.0f;
+        ext = fmaxf(ext, z - a);
     }
+    // one scale for all axes: Morton cells are cubes, buckets stay compact
+    const float scale = ext > 0.f ? 1023.0f / ext : 0.0f;
     unsigned keys[ITEMS], vals[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -163,7 +170,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
             unsigned q[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float v = (__ldg(p + (int64_t)n * ps + c * cs) - mn[c]) * scale[c];
+                float v = (__ldg(p + (int64_t)n * ps + c * cs) - mn[c]) * scale;
                 q[c] = (unsigned)fminf(fmaxf(v, 0.0f), 1023.0f);
             }
             keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
@@ -174,9 +181,9 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         }
     }
     __syncthreads();
-    Sort(*reinterpret_cast<typename Sort::TempStorage *>(smem_raw)).Sort(keys, vals, 0, 30 + 2);
+    Sort(*reinterpret_cast<typename Sort::TempStorage *>(smem_raw)).Sort(keys, vals, 0, 32);
     __syncthreads();   // temp storage aliased with sx/sy/sz/sidx: done with it
-    // thread `tid` now holds sorted positions tid*32 .. tid*32+31 (= bucket `tid`)
+    // thread `tid` now holds sorted positions tid*ITEMS .. tid*ITEMS+ITEMS-1
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int pos = tid * ITEMS + i;
@@ -194,16 +201,26 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         sidx[pos] = (unsigned short)n;
     }
     __syncthreads();
+    // optional: publish the Morton-ordered cloud as a spatial index (ball query / KNN reuse it)
+    if (index.sorted_xyz) {
+        float *ox = index.sorted_xyz + (int64_t)b * 3 * CAP;
+        int32_t *oi = index.sorted_idx + (int64_t)b * CAP;
+        for (int i = tid; i < CAP; i += THREADS) {
+            ox[i] = sx[i];
+            ox[CAP + i] = sy[i];
+            ox[2 * CAP + i] = sz[i];
+            oi[i] = sidx[i] == 0xffffu ? -1 : (int32_t)sidx[i];
+        }
+    }
 
-    // ---- per-lane state: dist[k] = point `lane` of bucket (warp*32 + k);
-    //      lane k additionally owns bucket k's box and (max dist, tie word). ----
-    const int wbase = warp * 1024;
-    float dist[32];
+    // ---- per-lane state: dist[k] = point `lane` of bucket (k*WARPS + warp);
+    //      lane k additionally owns that bucket's box and (max dist, tie word). ----
+    float dist[BPW];
     float bminx = 0.f, bminy = 0.f, bminz = 0.f, bmaxx = 0.f, bmaxy = 0.f, bmaxz = 0.f;
     unsigned bval = 0u, blo = 0u;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const int pos = wbase + k * 32 + lane;
+    for (int k = 0; k < BPW; ++k) {
+        const int pos = (k * WARPS + warp) * 32 + lane;
         const bool valid = sidx[pos] != 0xffffu;
         dist[k] = valid ? 1e10f : 0.0f;
         const float x = sx[pos], y = sy[pos], z = sz[pos];
@@ -219,6 +236,14 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
             bmaxx = z0; bmaxy = z1; bmaxz = z2;
             bval = hi; blo = lo;
         }
+        if (index.bucket_box) {
+            const int cntv = __popc(__ballot_sync(0xffffffffu, valid));
+            if (lane == 0) {
+                float4 *bb = reinterpret_cast<float4 *>(index.bucket_box + ((int64_t)b * (CAP / 32) + k * WARPS + warp) * 8);
+                bb[0] = make_float4(a0, a1, a2, z0);
+                bb[1] = make_float4(z1, z2, (float)cntv, 0.f);
+            }
+        }
     }
 
     unsigned pos = s_startpos, idx = startidx;
@@ -233,27 +258,30 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         const float ey = fmaxf(fmaxf(__fsub_rn(bminy, cy), __fsub_rn(cy, bmaxy)), 0.0f);
         const float ez = fmaxf(fmaxf(__fsub_rn(bminz, cz), __fsub_rn(cz, bmaxz)), 0.0f);
         const float lb = sq3_nofma(ex, ey, ez);
-        const unsigned mask = __ballot_sync(0xffffffffu, lb < __uint_as_float(bval));
+        const unsigned mask = __ballot_sync(0xffffffffu, lane < BPW && lb < __uint_as_float(bval));
+        if (mask) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (!(mask & (0xffu << (8 * g)))) continue;
+            for (int g = 0; g < (BPW + 7) / 8; ++g) {
+                if (!(mask & (0xffu << (8 * g)))) continue;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                const int k = g * 8 + kk;
-                if (!(mask & (1u << k))) continue;
-                const int pp = wbase + k * 32 + lane;
-                const float d = sq3_nofma(__fsub_rn(sx[pp], cx), __fsub_rn(sy[pp], cy), __fsub_rn(sz[pp], cz));
-                if (d < dist[k]) dist[k] = d;
-                unsigned hi = __float_as_uint(dist[k]);
-                unsigned lo = ((0xffffu - (unsigned)sidx[pp]) << 16) | (unsigned)pp;
-                warp_max_pair(hi, lo);
-                if (lane == k) {
-                    bval = hi;
-                    blo = lo;
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int k = g * 8 + kk;
+                    if (k >= BPW) break;
+                    if (!(mask & (1u << k))) continue;
+                    const int pp = (k * WARPS + warp) * 32 + lane;
+                    const float d = sq3_nofma(__fsub_rn(sx[pp], cx), __fsub_rn(sy[pp], cy), __fsub_rn(sz[pp], cz));
+                    if (d < dist[k]) dist[k] = d;
+                    unsigned hi = __float_as_uint(dist[k]);
+                    unsigned lo = ((0xffffu - (unsigned)sidx[pp]) << 16) | (unsigned)pp;
+                    warp_max_pair(hi, lo);
+                    if (lane == k) {
+                        bval = hi;
+                        blo = lo;
+                    }
                 }
             }
         }
-        unsigned hi = bval, lo = blo;
+        unsigned hi = lane < BPW ? bval : 0u, lo = lane < BPW ? blo : 0u;
         warp_max_pair(hi, lo);
         if (WARPS > 1) {
             if (lane == 0) {
@@ -270,35 +298,56 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
     }
 }
 
-template <int WARPS>
+template <int WARPS, int BPW>
 static int launch_bucketed(const dvcp_cloud_t &c, int B, int N, int npoint, const int64_t *start,
-                           int64_t *o64, int32_t *o32, cudaStream_t st) {
-    constexpr int CAP = WARPS * 1024;
-    using Sort = cub::BlockRadixSort<unsigned, WARPS * 32, 32, unsigned>;
+                           int64_t *o64, int32_t *o32, dvcp_cloud_index_t index, cudaStream_t st) {
+    constexpr int CAP = WARPS * BPW * 32;
+    if (index.sorted_xyz && (index.cap != CAP || !index.sorted_idx || !index.bucket_box)) return DVCP_E_ARG;
+    using Sort = cub::BlockRadixSort<unsigned, WARPS * 32, BPW, unsigned>;
     size_t data = (size_t)CAP * (3 * sizeof(float) + sizeof(unsigned short));
     size_t smem = data > sizeof(typename Sort::TempStorage) ? data : sizeof(typename Sort::TempStorage);
-    auto k = fps_bucketed_kernel<WARPS>;
+    auto k = fps_bucketed_kernel<WARPS, BPW>;
     DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<B, WARPS * 32, smem, st>>>((const float *)c.base, c.bstride, c.pstride, c.cstride, N, npoint,
-                                   start, o64, o32);
+                                   start, o64, o32, index);
     DVCP_CHECK_LAUNCH();
     return 0;
 }
 
+static int dispatch_bucketed(const dvcp_cloud_t &xyz, int B, int N, int npoint, const int64_t *start,
+                             int64_t *out64, int32_t *out32, dvcp_cloud_index_t index, cudaStream_t st) {
+    if (N <= 1024) return launch_bucketed<4, 8>(xyz, B, N, npoint, start, out64, out32, index, st);
+    if (N <= 2048) return launch_bucketed<8, 8>(xyz, B, N, npoint, start, out64, out32, index, st);
+    if (N <= 4096) return launch_bucketed<16, 8>(xyz, B, N, npoint, start, out64, out32, index, st);
+    if (N <= 8192) return launch_bucketed<16, 16>(xyz, B, N, npoint, start, out64, out32, index, st);
+    return launch_bucketed<16, 32>(xyz, B, N, npoint, start, out64, out32, index, st);
+}
+
 }  // namespace dvcp
 
+extern "C" int dvcp_index_capacity(int N) {
+    if (N < 64 || N > 16384) return 0;
+    if (N <= 1024) return 1024;
+    if (N <= 2048) return 2048;
+    if (N <= 4096) return 4096;
+    if (N <= 8192) return 8192;
+    return 16384;
+}
+
+extern "C" int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index_t index, dvcp_stream_t stream) {
+    using namespace dvcp;
+    if (!xyz.base || !index.sorted_xyz || !index.sorted_idx || !index.bucket_box || B <= 0) return DVCP_E_ARG;
+    if (dvcp_index_capacity(N) == 0) return DVCP_E_UNSUPPORTED;
+    return dispatch_bucketed(xyz, B, N, 0, nullptr, nullptr, nullptr, index, (cudaStream_t)stream);
+}
+
 extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, const int64_t *start,
-                        int64_t *out64, int32_t *out32, dvcp_stream_t stream) {
+                        int64_t *out64, int32_t *out32, dvcp_cloud_index_t index, dvcp_stream_t stream) {
     using namespace dvcp;
     if (!xyz.base || !start || (!out64 && !out32) || B <= 0 || N <= 0 || npoint <= 0) return DVCP_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == 0 && N <= 16384 && N >= 64) {
-        if (N <= 1024) return launch_bucketed<1>(xyz, B, N, npoint, start, out64, out32, st);
-        if (N <= 2048) return launch_bucketed<2>(xyz, B, N, npoint, start, out64, out32, st);
-        if (N <= 4096) return launch_bucketed<4>(xyz, B, N, npoint, start, out64, out32, st);
-        if (N <= 8192) return launch_bucketed<8>(xyz, B, N, npoint, start, out64, out32, st);
-        return launch_bucketed<16>(xyz, B, N, npoint, start, out64, out32, st);
-    }
+    if (dtype == 0 && N <= 16384 && N >= 64) return dispatch_bucketed(xyz, B, N, npoint, start, out64, out32, index, st);
+    if (index.sorted_xyz) return DVCP_E_UNSUPPORTED;
     if (N > 57344) return DVCP_E_UNSUPPORTED;
     size_t smem = (size_t)N * sizeof(float);
     if (dtype == 0) {

@@ -109,6 +109,271 @@ knn_kernel(Cloud ref, const float *__restrict__ query, int N, int64_t Q, int K, 
     }
 }
 
+// ------------------------------------------------------ indexed KNN ---------
+// Same contract, but the reference cloud comes with its spatial index (Morton
+// buckets of 32 points + boxes). Per query:
+//   * lb[j] = fma-chain squared distance from the query to bucket j's box,
+//     evaluated on the clamped offsets with the SAME rounded arithmetic as the
+//     point distances; by monotonicity of rounding no member of the bucket can
+//     have a smaller rounded distance. A bucket is visited only if lb[j] <= the
+//     current K-th best (ties included, so index tie-breaking is preserved).
+//   * a warp walks a CHAIN of consecutive queries (one z-line of the candidate
+//     lattice); the K-th distance of the previous query plus the step between the
+//     two queries bounds the K-th distance of the next one (triangle inequality,
+//     inflated for rounding), which prunes from the first bucket on.
+//   * the K best are one 64-bit key per lane, sorted across the lanes; a visited
+//     bucket (one point per lane) is merged by serial insertion when few points
+//     qualify, else by a bitonic sort + merge.
+constexpr int KNI_WARPS = 8;
+
+__device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+__device__ __forceinline__ unsigned long long bitonic_sort32(unsigned long long key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            key = (lower == up) ? u64min(key, other) : u64max(key, other);
+        }
+    }
+    return key;
+}
+
+// list: ascending across lanes (lanes >= K hold INF). keys: one candidate per lane (INF = none).
+// Only the streaming fallback of the indexed kernel uses this.
+__device__ __forceinline__ void knn_merge(unsigned long long &list, unsigned long long &worst,
+                                          unsigned long long key, unsigned m, int K, int lane) {
+    const unsigned long long INF = 0xffffffffffffffffull;
+    if (__popc(m) <= 8) {
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long c = __shfl_sync(0xffffffffu, key, src);
+            if (c < worst) {
+                const int pos = __popc(__ballot_sync(0xffffffffu, list < c));
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, list, 1);
+                if (lane < K) list = lane > pos ? up : (lane == pos ? c : list);
+                worst = __shfl_sync(0xffffffffu, list, K - 1);
+            }
+        }
+    } else {
+        unsigned long long s = bitonic_sort32((m >> lane) & 1u ? key : INF, lane);
+        const unsigned long long r = __shfl_sync(0xffffffffu, s, 31 - lane);
+        list = u64min(list, r);   // the 32 smallest of the union, bitonic
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, list, j);
+            list = (lane & j) == 0 ? u64min(list, other) : u64max(list, other);
+        }
+        if (lane >= K) list = INF;
+        worst = __shfl_sync(0xffffffffu, list, K - 1);
+    }
+}
+
+// Box of a "super-bucket": lane l owns the T Morton-consecutive buckets l*T .. l*T+T-1.
+struct Box6 {
+    float nx, ny, nz, xx, xy, xz;   // min, max
+};
+__device__ __forceinline__ Box6 load_super_box(const float *box, int T, int lane) {
+    Box6 s{INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int t = 0; t < T; ++t) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8) + 1);
+        if (b1.z > 0.f) {
+            s.nx = fminf(s.nx, b0.x); s.ny = fminf(s.ny, b0.y); s.nz = fminf(s.nz, b0.z);
+            s.xx = fmaxf(s.xx, b0.w); s.xy = fmaxf(s.xy, b1.x); s.xz = fmaxf(s.xz, b1.y);
+        }
+    }
+    return s;
+}
+// fma-chain squared distance from q to a box: a lower bound of every member's rounded distance
+__device__ __forceinline__ float box_lb(float qx, float qy, float qz, float nx, float ny, float nz, float xx,
+                                        float xy, float xz) {
+    const float ex = fmaxf(fmaxf(nx - qx, qx - xx), 0.f);
+    const float ey = fmaxf(fmaxf(ny - qy, qy - xy), 0.f);
+    const float ez = fmaxf(fmaxf(nz - qz, qz - xz), 0.f);
+    return sqdist_direct(ex, ey, ez);   // empty box (min=+inf) -> +inf
+}
+
+constexpr int KNI_BUF = 128;   // qualifying points collected per query before the sort
+
+template <int T>   // T = buckets / 32
+__global__ void __launch_bounds__(KNI_WARPS * 32)
+knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, int64_t Q, int K, int chain,
+                   int zline, float *__restrict__ dist, int64_t *__restrict__ idx64, int32_t *__restrict__ idx32) {
+    __shared__ unsigned long long s_buf[KNI_WARPS][KNI_BUF];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long INF = 0xffffffffffffffffull;
+    const int cap = index.cap;
+    const float *box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
+    const float *sxp = index.sorted_xyz + (int64_t)b * 3 * cap;
+    const int32_t *sip = index.sorted_idx + (int64_t)b * cap;
+    unsigned long long *buf = s_buf[warp];
+    const Box6 sb = load_super_box(box, T, lane);
+    const int64_t nchains = (Q + chain - 1) / chain;
+
+    // key of point at sorted slot `pos` for query (qx,qy,qz): bits(d2) << 32 | id << 16 | pos
+    auto point_key = [&](int pos, float qx, float qy, float qz, float &d2) -> unsigned long long {
+        const float px = __ldg(sxp + pos), py = __ldg(sxp + cap + pos), pz = __ldg(sxp + 2 * cap + pos);
+        const int id = __ldg(sip + pos);
+        d2 = sqdist_direct(px - qx, py - qy, pz - qz);
+        return id >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned)id << 16) | (unsigned)pos) : INF;
+    };
+
+    for (int64_t ch = (int64_t)blockIdx.x * KNI_WARPS + warp; ch < nchains; ch += (int64_t)gridDim.x * KNI_WARPS) {
+        const int64_t q0 = ch * chain, q1 = min(q0 + chain, Q);
+        unsigned long long list = INF;   // result of the previous query of the chain (lane j: j-th neighbour)
+        for (int64_t qi = q0; qi < q1; ++qi) {
+            // boustrophedon over the z-lines of the chain: consecutive queries stay adjacent
+            int64_t q = qi;
+            {
+                const int i = (int)(qi - q0), line = i / zline, k = i - line * zline;
+                if ((line & 1) && q0 + (int64_t)(line + 1) * zline <= q1) q = q0 + (int64_t)line * zline + (zline - 1 - k);
+            }
+            const float *qp = query + ((int64_t)b * Q + q) * 3;
+            const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+            const float lbs = box_lb(qx, qy, qz, sb.nx, sb.ny, sb.nz, sb.xx, sb.xy, sb.xz);
+            // ---- bound thr on the K-th squared distance: K known points, evaluated exactly ----
+            float thr;
+            {
+                unsigned long long k0;
+                float d2 = 0.f;
+                if (__any_sync(0xffffffffu, list != INF)) {
+                    // previous neighbours re-evaluated for this query
+                    k0 = (lane < K && list != INF) ? point_key((int)(list & 0xffffu), qx, qy, qz, d2) : 0ull;
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)(k0 >> 32));
+                    thr = __uint_as_float(mx);
+                } else {
+                    thr = INFINITY;   // first query of a chain: best-first streaming search below
+                }
+            }
+            unsigned long long res = INF;
+            if (!(thr < INFINITY)) {
+                // ---- best-first over the bucket groups, streaming merge; exact for any start ----
+                unsigned long long worst = INF;
+                float rem = lbs;   // this lane's group lower bound; +inf once processed
+                while (true) {
+                    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(rem));
+                    const float now = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
+                    if (mb == 0x7f800000u || !(__uint_as_float(mb) <= now)) break;
+                    const int sl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(rem) == mb)) - 1;
+                    if (lane == sl) rem = INFINITY;
+                    float l = INFINITY;
+                    if (lane < T) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+                        if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                    }
+                    // the group's buckets in increasing order of their own bound
+                    while (true) {
+                        const unsigned lm = __reduce_min_sync(0xffffffffu, __float_as_uint(l));
+                        const float now2 = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
+                        if (lm == 0x7f800000u || !(__uint_as_float(lm) <= now2)) break;
+                        const int bl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(l) == lm)) - 1;
+                        if (lane == bl) l = INFINITY;
+                        float d2;
+                        const unsigned long long key = point_key((sl * T + bl) * 32 + lane, qx, qy, qz, d2);
+                        const unsigned m = __ballot_sync(0xffffffffu, key < worst);
+                        if (m) knn_merge(res, worst, key, m, K, lane);
+                    }
+                }
+            } else {
+            // ---- collect every point with d2 <= thr from the buckets whose box allows it ----
+            int cnt = 0;
+            unsigned sm = __ballot_sync(0xffffffffu, lbs <= thr);
+            while (sm) {
+                const int sl = __ffs(sm) - 1;
+                sm &= sm - 1;
+                float l = INFINITY;
+                if (lane < T) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+                    if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                }
+                unsigned bm = __ballot_sync(0xffffffffu, l <= thr);
+                while (bm) {
+                    const int j = sl * T + __ffs(bm) - 1;
+                    bm &= bm - 1;
+                    float d2;
+                    const unsigned long long key = point_key(j * 32 + lane, qx, qy, qz, d2);
+                    const bool qual = key != INF && d2 <= thr;
+                    const unsigned m = __ballot_sync(0xffffffffu, qual);
+                    const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (qual && slot < KNI_BUF) buf[slot] = key;
+                    cnt += __popc(m);
+                }
+            }
+            __syncwarp();
+            // ---- the K smallest keys, ascending across the lanes ----
+            if (cnt <= KNI_BUF) {
+                for (int g = 0; g < cnt; g += 32) {
+                    unsigned long long k = g + lane < cnt ? buf[g + lane] : INF;
+                    k = bitonic_sort32(k, lane);
+                    if (g == 0) {
+                        res = k;
+                    } else {
+                        const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
+                        res = u64min(res, r);
+#pragma unroll
+                        for (int j = 16; j > 0; j >>= 1) {
+                            const unsigned long long other = __shfl_xor_sync(0xffffffffu, res, j);
+                            res = (lane & j) == 0 ? u64min(res, other) : u64max(res, other);
+                        }
+                    }
+                }
+            } else {
+                // too many qualifying points for the buffer (loose bound): streaming merge over the same buckets
+                unsigned long long worst = INF;
+                unsigned sm2 = __ballot_sync(0xffffffffu, lbs <= thr);
+                while (sm2) {
+                    const int sl = __ffs(sm2) - 1;
+                    sm2 &= sm2 - 1;
+                    for (int t = 0; t < T; ++t) {
+                        const int j = sl * T + t;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
+                        if (!(b1.z > 0.f)) continue;
+                        const float l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                        const float now = worst == INF ? thr : fminf(thr, __uint_as_float((unsigned)(worst >> 32)));
+                        if (!(l <= now)) continue;
+                        float d2;
+                        const unsigned long long key = point_key(j * 32 + lane, qx, qy, qz, d2);
+                        const unsigned m = __ballot_sync(0xffffffffu, key < worst && d2 <= thr);
+                        if (m) knn_merge(res, worst, key, m, K, lane);
+                    }
+                }
+            }
+            }
+            __syncwarp();
+            if (lane >= K) res = INF;
+            if (lane < K) {
+                const int64_t o = ((int64_t)b * Q + q) * K + lane;
+                dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(res >> 32)));
+                const unsigned id = ((unsigned)(res & 0xffffffffu)) >> 16;
+                if (idx64) idx64[o] = id;
+                if (idx32) idx32[o] = (int32_t)id;
+            }
+            list = res;
+        }
+    }
+}
+
+template <int T>
+static int launch_knn_indexed(dvcp_cloud_index_t index, const float *query, int B, int64_t Q, int K, int chain,
+                              int zline, float *dist, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
+    const int64_t nchains = (Q + chain - 1) / chain;
+    int64_t gx = (nchains + KNI_WARPS - 1) / KNI_WARPS;
+    const int64_t cap = (int64_t)DVCP_NUM_SMS * 64 / (B < 64 ? B : 64) + 1;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, B);
+    knn_indexed_kernel<T><<<grid, KNI_WARPS * 32, 0, st>>>(index, query, Q, K, chain, zline, dist, idx64, idx32);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
 }  // namespace dvcp
 
 using namespace dvcp;
@@ -129,6 +394,25 @@ extern "C" int dvcp_candidates(const double *centres, int64_t M, double r, doubl
     candidates_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(centres, M, r, s, G, out);
     DVCP_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int dvcp_knn_indexed(dvcp_cloud_index_t index, const float *query, int B, int N, int64_t Q, int K,
+                                int chain, int zline, float *dist, int64_t *idx64, int32_t *idx32,
+                                dvcp_stream_t stream) {
+    if (!index.sorted_xyz || !index.sorted_idx || !index.bucket_box || !query || !dist || (!idx64 && !idx32) ||
+        B <= 0 || N <= 0 || Q <= 0 || chain < 1)
+        return DVCP_E_ARG;
+    if (zline < 1 || zline > chain) zline = chain;
+    if (K < 1 || K > 32 || K > N || B > 65535 || index.cap < N) return DVCP_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (index.cap / 1024) {
+        case 1: return launch_knn_indexed<1>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 2: return launch_knn_indexed<2>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 4: return launch_knn_indexed<4>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 8: return launch_knn_indexed<8>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 16: return launch_knn_indexed<16>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+    }
+    return DVCP_E_UNSUPPORTED;
 }
 
 extern "C" int dvcp_knn(dvcp_cloud_t ref, const float *query, int B, int N, int64_t Q, int K, float *dist,

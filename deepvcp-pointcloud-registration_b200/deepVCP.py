@@ -93,11 +93,13 @@ class DeepVCP(nn.Module):
             # launch (2B independent clouds); features come out in FPS order
             both = torch.cat([src, tgt], dim=0)
             st2 = torch.cat([torch.as_tensor(starts[0]).reshape(-1), torch.as_tensor(starts[2]).reshape(-1)])
-            _, fps2 = F_.fps(cloud_cm(both), dev, both.dtype, 2 * B, N, S, st2, want64=False, want32=True)
+            index = F_.SpatialIndex(2 * B, N, dev) if F_.SpatialIndex.indexable(N) else None
+            _, fps2 = F_.fps(cloud_cm(both), dev, both.dtype, 2 * B, N, S, st2, want64=False, want32=True,
+                             index=index)
             mark("fps")
             feat_cloud = cloud_cm(both[:, 3:, :]) if D else None
             _, feat2 = F_.sa_layer(cloud_cm(both), feat_cloud, D, fps2, 2 * B, N, S, sa.radius, sa.nsample, mlp,
-                                   dev, want_xyz=False)
+                                   dev, want_xyz=False, index=index)
             mark("sa_layer")
             sfps, tfps = fps2[:B], fps2[B:]
             sfeat, tfeat = feat2[:B], feat2[B:]
@@ -114,8 +116,12 @@ class DeepVCP(nn.Module):
             cand = F_.candidates(centres, self.r, self.s, G)                 # [B,K,C,3]
             mark("keypoint_candidates")
             C = G * G * G
-            kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
-                                    want32=True)
+            if index is not None:   # target clouds are batch items B..2B-1 of the index
+                kd, ki64, ki32 = F_.knn_indexed(index, B, dev, B, N, cand.view(B, K * C, 3), ns, chain=G,
+                                                want64=keep_stages, want32=True)
+            else:
+                kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
+                                        want32=True)
             mark("knn")
             tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
                                        self.quirks)                            # [B,K*C,32]

@@ -10,13 +10,17 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (Cloud, MlpLayer, NULL_CLOUD, check, cloud_cm, cloud_pm, lib, ptr, require_cuda,
-                   stream_ptr)
+from ._lib import (Cloud, CloudIndex, MlpLayer, NULL_CLOUD, NULL_INDEX, check, cloud_cm, cloud_pm, lib, ptr,
+                   require_cuda, stream_ptr)
 
 
 # number of kernels of libdvcp_b200.so launched through this module (bench.py's
 # `gpu_launches`); every wrapper adds what its entry point launches.
 LAUNCHES = 0
+
+# Spatially pruned kernels (exact; results identical to the brute-force kernels).
+# Tests flip this to compare the two families.
+USE_INDEX = True
 
 
 def _count(n):
@@ -44,15 +48,44 @@ def draw_fps_start(B: int, N: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- #
-def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want32=False):
+class SpatialIndex:
+    """Device buffers of a cloud's spatial index (dvcp_cloud_index_t)."""
+
+    def __init__(self, B, N, device):
+        self.cap = lib().dvcp_index_capacity(N)
+        if self.cap == 0:
+            raise RuntimeError("clouds of %d points cannot be indexed (64..16384)" % N)
+        self.sorted_xyz = torch.empty(B, 3, self.cap, dtype=torch.float32, device=device)
+        self.sorted_idx = torch.empty(B, self.cap, dtype=torch.int32, device=device)
+        self.bucket_box = torch.empty(B, self.cap // 32, 8, dtype=torch.float32, device=device)
+        self.B = B
+
+    def c(self, lo=0):
+        """ctypes view starting at batch item `lo`."""
+        return CloudIndex(self.sorted_xyz[lo:].data_ptr(), self.sorted_idx[lo:].data_ptr(),
+                          self.bucket_box[lo:].data_ptr(), self.cap)
+
+    @staticmethod
+    def indexable(N, dtype=torch.float32):
+        return USE_INDEX and dtype == torch.float32 and lib().dvcp_index_capacity(N) > 0
+
+
+def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want32=False, index=None):
     start = _starts_to_device(start, B, device)
     o64 = torch.empty(B, npoint, dtype=torch.int64, device=device) if want64 else None
     o32 = torch.empty(B, npoint, dtype=torch.int32, device=device) if want32 else None
     code = lib().dvcp_fps(xyz_cloud, 0 if dtype == torch.float32 else 1, B, N, npoint, ptr(start), ptr(o64),
-                          ptr(o32), stream_ptr(device))
+                          ptr(o32), index.c() if index is not None else NULL_INDEX, stream_ptr(device))
     check(code, "dvcp_fps")
     _count(1)
     return o64, o32
+
+
+def build_index(xyz_cloud: Cloud, device, B, N):
+    index = SpatialIndex(B, N, device)
+    check(lib().dvcp_build_index(xyz_cloud, B, N, index.c(), stream_ptr(device)), "dvcp_build_index")
+    _count(1)
+    return index
 
 
 def fps_plain(xyz_pm, npoint, start):
@@ -126,14 +159,16 @@ class FoldedMlp:
 
 
 def sa_layer(xyz_cloud, feats_cloud, D, centroid_idx32, B, N, S, radius, nsample, mlp: FoldedMlp, device,
-             want_xyz=True):
+             want_xyz=True, index=None):
     out = torch.empty(B, S, mlp.out_ch, dtype=torch.float32, device=device)
     oxyz = torch.empty(B, S, 3, dtype=torch.float32, device=device) if want_xyz else None
+    ws = torch.empty(B * S, dtype=torch.uint8, device=device) if index is not None else None
     code = lib().dvcp_sa_layer(xyz_cloud, feats_cloud if D > 0 else NULL_CLOUD, D, ptr(centroid_idx32), B, N, S,
-                               radius2_f32(radius), nsample, mlp.layers, mlp.n, ptr(out), ptr(oxyz),
+                               radius2_f32(radius), nsample, mlp.layers, mlp.n,
+                               index.c() if index is not None else NULL_INDEX, ptr(ws), ptr(out), ptr(oxyz),
                                stream_ptr(device))
     check(code, "dvcp_sa_layer")
-    _count(1)
+    _count(2 if index is not None else 1)
     return oxyz, out
 
 
@@ -211,6 +246,20 @@ def knn(ref_cloud, device, B, N, query, K, want64=True, want32=False):
     i32 = torch.empty(B, Q, K, dtype=torch.int32, device=device) if want32 else None
     check(lib().dvcp_knn(ref_cloud, ptr(query), B, N, Q, K, ptr(dist), ptr(i64), ptr(i32), stream_ptr(device)),
           "dvcp_knn")
+    _count(1)
+    return dist, i64, i32
+
+
+def knn_indexed(index, lo, device, B, N, query, K, chain=1, zline=0, want64=True, want32=False):
+    """index: SpatialIndex whose batch items lo..lo+B-1 are the reference clouds."""
+    require_cuda(query)
+    query = _f32c(query)
+    Q = query.shape[1]
+    dist = torch.empty(B, Q, K, dtype=torch.float32, device=device)
+    i64 = torch.empty(B, Q, K, dtype=torch.int64, device=device) if want64 else None
+    i32 = torch.empty(B, Q, K, dtype=torch.int32, device=device) if want32 else None
+    check(lib().dvcp_knn_indexed(index.c(lo), ptr(query), B, N, Q, K, chain, zline or chain, ptr(dist), ptr(i64),
+                                 ptr(i32), stream_ptr(device)), "dvcp_knn_indexed")
     _count(1)
     return dist, i64, i32
 

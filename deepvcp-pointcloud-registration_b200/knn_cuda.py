@@ -25,7 +25,11 @@ class KNN:
             else:
                 B, _, N = ref.shape
                 rc, q = cloud_cm(ref), query.transpose(1, 2).contiguous()
-            dist, idx, _ = F_.knn(rc, ref.device, B, N, q, self.k)
+            if F_.SpatialIndex.indexable(N) and q.shape[1] >= 256:
+                index = F_.build_index(rc, ref.device, B, N)
+                dist, idx, _ = F_.knn_indexed(index, 0, ref.device, B, N, q, self.k)
+            else:
+                dist, idx, _ = F_.knn(rc, ref.device, B, N, q, self.k)
             if not self.transpose_mode:
                 dist, idx = dist.transpose(1, 2).contiguous(), idx.transpose(1, 2).contiguous()
         return dist, idx

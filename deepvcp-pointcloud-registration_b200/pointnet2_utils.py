@@ -110,11 +110,12 @@ class PointNetSetAbstraction(nn.Module):
         dev = xyz.device
         if start is None:
             start = F_.draw_fps_start(B, N)
-        _, fps32 = F_.fps(cloud_cm(xyz), dev, xyz.dtype, B, N, S, start, want64=return_fps, want32=True)
+        index = F_.SpatialIndex(B, N, dev) if F_.SpatialIndex.indexable(N) else None
+        _, fps32 = F_.fps(cloud_cm(xyz), dev, xyz.dtype, B, N, S, start, want64=return_fps, want32=True, index=index)
         D = 0 if points is None else points.shape[1]
         if points is not None and points.dtype != torch.float32:
             points = points.float()
         new_xyz, feats = F_.sa_layer(cloud_cm(xyz), cloud_cm(points) if D else None, D, fps32, B, N, S,
-                                     self.radius, self.nsample, self.folded(), dev)
+                                     self.radius, self.nsample, self.folded(), dev, index=index)
         out = (new_xyz.permute(0, 2, 1), feats.permute(0, 2, 1))
         return out + (fps32,) if return_fps else out

@@ -62,15 +62,32 @@ typedef struct {
     int in_ch, out_ch;
 } dvcp_mlp_layer_t;
 
+/* Spatial index of a cloud (64 <= N <= 16384): the points in Morton order, cut
+ * into buckets of 32 consecutive points with their bounding boxes. Built by
+ * dvcp_build_index, or as a by-product of dvcp_fps (which sorts the cloud
+ * anyway); consumed by the pruned ball-query / SA / KNN kernels. Pruning never
+ * changes results: members are always decided by the exact arithmetic. */
+typedef struct {
+    float *sorted_xyz;   /* [B, 3, cap]  x[], y[], z[] in Morton order; unused slots 0   */
+    int32_t *sorted_idx; /* [B, cap]     original index of each slot; -1 = unused slot   */
+    float *bucket_box;   /* [B, cap/32, 8] minx,miny,minz,maxx,maxy,maxz,count,0          */
+    int cap;             /* dvcp_index_capacity(N)                                        */
+} dvcp_cloud_index_t;
+
 DVCP_API int dvcp_abi_version(void);
 DVCP_API const char *dvcp_error_string(int code);
 
 /* ---- a1  farthest_point_sample(xyz, npoint)        pointnet2_utils.py:63-84
  * start[B] is the random first index the caller drew (pointnet2_utils.py:75).
  * dtype 0: float32 cloud, 1: float64 cloud. out64 [B,npoint] (int64) and/or
- * out32 [B,npoint] (int32) may be null. */
+ * out32 [B,npoint] (int32) may be null. index_out (all-null = not wanted) also
+ * publishes the spatial index of the cloud (float32, 64 <= N <= 16384 only). */
 DVCP_API int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, const int64_t *start,
-             int64_t *out64, int32_t *out32, dvcp_stream_t stream);
+             int64_t *out64, int32_t *out32, dvcp_cloud_index_t index_out, dvcp_stream_t stream);
+
+/* Capacity (slots) of the spatial index of an N-point cloud; 0 = N not indexable. */
+DVCP_API int dvcp_index_capacity(int N);
+DVCP_API int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index_t index_out, dvcp_stream_t stream);
 
 /* Test hook: the plain O(N * npoint) kernel for float32 clouds (the spatially
  * pruned kernel dvcp_fps normally dispatches to must give identical indices). */
@@ -99,10 +116,13 @@ DVCP_API int dvcp_index_points(const float *points, const int64_t *idx, int B, i
  * Fused: centroid gather, ball query, grouping [xyz - centre, feats], shared
  * MLP, max over the ball. centroid_idx [B,S] int32 are the FPS indices.
  * feats: D extra channels addressed like a cloud (null when D == 0).
- * out_feat [B,S,out_ch_last] float32, out_xyz [B,S,3] float32 (may be null). */
+ * out_feat [B,S,out_ch_last] float32, out_xyz [B,S,3] float32 (may be null).
+ * index (all-null = none): spatial index of xyz; when given, only buckets that
+ * can hold a member are visited and overflow_ws ([B*S] bytes) is required. */
 DVCP_API int dvcp_sa_layer(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *centroid_idx, int B,
                   int N, int S, float radius2, int nsample, const dvcp_mlp_layer_t *layers_host,
-                  int n_layers, float *out_feat, float *out_xyz, dvcp_stream_t stream);
+                  int n_layers, dvcp_cloud_index_t index, unsigned char *overflow_ws, float *out_feat,
+                  float *out_xyz, dvcp_stream_t stream);
 
 /* ---- a8  weighting_layer.forward(X, K)              weighting_layer.py:26-33
  * X [B,S,32]; W1[16,32] b1 W2[8,16] b2 W3[1,8] b3; scores [B,S] (softplus
@@ -142,6 +162,16 @@ DVCP_API int dvcp_candidates(const double *centres, int64_t M, double r, double 
  * Order: (squared distance, index) ascending. 1 <= K <= 32, K <= N. */
 DVCP_API int dvcp_knn(dvcp_cloud_t ref, const float *query, int B, int N, int64_t Q, int K, float *dist,
              int64_t *idx64, int32_t *idx32, dvcp_stream_t stream);
+
+/* Same contract and results as dvcp_knn, with the reference cloud given through
+ * its spatial index (exact pruning, see csrc/knn.cu). `chain` consecutive queries
+ * are processed by one warp, each seeded by the result of the previous one, so
+ * they should be spatially close; within a chain every other run of `zline`
+ * queries is walked backwards (candidate lattice: chain = G*G, zline = G walks an
+ * x-slab in boustrophedon order). Any chain >= 1, 1 <= zline <= chain is correct. */
+DVCP_API int dvcp_knn_indexed(dvcp_cloud_index_t ref_index, const float *query, int B, int N, int64_t Q, int K,
+                     int chain, int zline, float *dist, int64_t *idx64, int32_t *idx32,
+                     dvcp_stream_t stream);
 
 /* ---- a14+a15 Get_Cat_Feat_Tgt + feat_embedding_layer(src=False), fused
  *          get_cat_feat_tgt.py:53-96, deep_feat_embedding.py:46-60

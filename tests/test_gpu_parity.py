@@ -201,6 +201,36 @@ def test_sa_layer_dense_ball(dv):
     assert rel_err(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("kind,n", [("kitti", 16384), ("kitti", 5000), ("modelnet", 1024)])
+def test_sa_pruned_kernel_equals_bruteforce_kernel(dv, F, synthetic, kind, n):
+    src, _, _, _ = synthetic.make_batch(kind, [3, 4], n)
+    fe = dv.feat_extraction_layer(use_normal=kind == "modelnet", npoint=n).to(DEV).eval()
+    start = torch.tensor([1, 2])
+    try:
+        F.USE_INDEX = True
+        _, a = fe(src.to(DEV), start=start)
+        F.USE_INDEX = False
+        _, b = fe(src.to(DEV), start=start)
+    finally:
+        F.USE_INDEX = True
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("radius,nsample", [(0.5, 16), (0.12, 64)])
+def test_sa_pruned_crowded_balls(dv, radius, nsample):
+    """More members than nsample (smallest indices kept) and more than the kernel's
+    member list (brute-force overflow pass): both against the oracle."""
+    g = torch.Generator().manual_seed(8)
+    N = 3000
+    pts = torch.cat([torch.rand(1, 3, N, generator=g) * 0.6, torch.randn(1, 3, N, generator=g)], dim=1)
+    fe = dv.feat_extraction_layer(use_normal=True, npoint=N, radius=radius, nsample=nsample)
+    sd = {"FE1." + k: v for k, v in fe.state_dict().items()}
+    start = torch.tensor([9])
+    _, ref, _ = stages.feat_extraction(sd, pts, start, radius=radius, nsample=nsample)
+    _, out = fe.to(DEV).eval()(pts.to(DEV), start=start)
+    assert rel_err(out, ref) < 1e-5
+
+
 def test_weighting_topk(dv, prim):
     sd = golden_state_dict(prim, "wl_sd/")
     wl = dv.weighting_layer()
@@ -239,6 +269,45 @@ def test_knn_vs_oracle_with_ties(dv, n, q, k):
     assert torch.equal(i2.cpu(), i_ref.transpose(1, 2))
 
 
+@pytest.mark.parametrize("n,q,k,chain", [(100, 37, 1, 1), (1000, 500, 5, 7), (5000, 1000, 32, 11), (16384, 3000, 32, 11),
+                                          (8193, 65, 32, 3), (70, 300, 32, 11)])
+def test_knn_indexed_vs_oracle_with_ties(F, n, q, k, chain):
+    """Spatially pruned KNN == brute-force KNN == oracle, bit for bit (lattice clouds: exact ties)."""
+    lib = importlib.import_module(PKG + "._lib")
+    ref_pts = lattice_cloud(n, n + 1, extent=10.0, step=0.5)
+    g = torch.Generator().manual_seed(2)
+    qry = torch.round((torch.rand(1, q, 3, generator=g) * 2 - 1) * 60) / 4      # some queries far outside the cloud
+    d_ref, i_ref = stages.knn(ref_pts, qry, k)
+    rp = ref_pts.to(DEV)
+    index = F.build_index(lib.cloud_pm(rp), rp.device, 1, n)
+    d, i, i32 = F.knn_indexed(index, 0, rp.device, 1, n, qry.to(DEV), k, chain=chain, want32=True)
+    assert torch.equal(i.cpu(), i_ref)
+    d3, i3, _ = F.knn_indexed(index, 0, rp.device, 1, n, qry.to(DEV), k, chain=chain * 4, zline=chain)
+    assert torch.equal(i3.cpu(), i_ref) and torch.equal(d3.cpu(), d_ref)
+    assert torch.equal(i32.cpu().long(), i_ref)
+    assert torch.equal(d.cpu(), d_ref)
+
+
+def test_spatial_index_is_a_permutation_with_tight_boxes(F):
+    lib = importlib.import_module(PKG + "._lib")
+    n = 5000
+    pts = lattice_cloud(n, 3).to(DEV)
+    index = F.build_index(lib.cloud_pm(pts), pts.device, 1, n)
+    sid = index.sorted_idx[0].cpu()
+    valid = sid >= 0
+    assert int(valid.sum()) == n and torch.equal(sid[valid].sort()[0], torch.arange(n, dtype=torch.int32))
+    sxyz = index.sorted_xyz[0].cpu()                      # [3, cap]
+    assert torch.equal(sxyz[:, valid].T, pts[0].cpu()[sid[valid].long()])
+    box = index.bucket_box[0].cpu()
+    for j in (0, 7, index.cap // 32 - 1):
+        sl = slice(j * 32, j * 32 + 32)
+        v = valid[sl]
+        assert int(box[j, 6]) == int(v.sum())
+        if v.any():
+            p = sxyz[:, sl][:, v]
+            assert torch.equal(box[j, :3], p.min(dim=1)[0]) and torch.equal(box[j, 3:6], p.max(dim=1)[0])
+
+
 def test_knn_kitti_full_size_sampled_and_sorted(dv, F, synthetic):
     _, tgt, _, _ = synthetic.make_batch("kitti", [2], 16384)
     g = torch.Generator().manual_seed(4)
@@ -248,6 +317,9 @@ def test_knn_kitti_full_size_sampled_and_sorted(dv, F, synthetic):
     from importlib import import_module
     lib = import_module(PKG + "._lib")
     d, i, _ = F.knn(lib.cloud_cm(tg), tg.device, 1, 16384, cand, 32)
+    index = F.build_index(lib.cloud_cm(tg), tg.device, 1, 16384)
+    d2, i2, _ = F.knn_indexed(index, 0, tg.device, 1, 16384, cand, 32, chain=121, zline=11)
+    assert torch.equal(i, i2) and torch.equal(d, d2)      # all 85184 queries: pruned == brute force
     d, i = d.cpu(), i.cpu()
     assert (d[..., 1:] >= d[..., :-1]).all()
     assert int(i.min()) >= 0 and int(i.max()) < 16384

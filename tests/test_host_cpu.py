@@ -49,7 +49,8 @@ def test_argument_errors_without_a_gpu(dv):
     L = dv.lib()
     lib = importlib.import_module(PKG + "._lib")
     null = lib.NULL_CLOUD
-    assert L.dvcp_fps(null, 0, 1, 10, 10, None, None, None, None) == -1
+    assert L.dvcp_fps(null, 0, 1, 10, 10, None, None, None, lib.NULL_INDEX, None) == -1
+    assert [L.dvcp_index_capacity(n) for n in (10, 64, 1024, 1025, 16384, 16385)] == [0, 1024, 1024, 2048, 16384, 0]
     assert L.dvcp_grid_size(2.0, 0.4) == 11 and L.dvcp_grid_size(1.0, 0.4) == 6 and L.dvcp_grid_size(0.8, 0.4) == 5
     assert L.dvcp_grid_size(4.0, 0.4) == 21
     assert L.dvcp_grid_size(-1.0, 0.4) == -1
