@@ -1,0 +1,281 @@
+// Target-side gather + deep-feature embedding + max-pool on the 5th-generation
+// tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Reference: get_cat_feat_tgt.py:53-96 + deep_feat_embedding.py:46-60. The three
+// Linear layers have no activation between them (deep_feat_embedding.py:48-50), so
+// they are one affine map 35 -> 32; the host collapses them in float64
+// (Wc = W3 W2 W1, bc = W3 (W2 b1 + b2) + b3) and this kernel evaluates
+//     Y[128 x 32] = A[128 x 40] * Bm[40 x 32]
+// per tile of 4 candidates x 32 neighbours, K = 32 weighted features + 3 local
+// coordinates + 1 (bias) + 4 zero columns, as a TF32 tensor-core GEMM with the
+// 3xTF32 split (A = Ah + Al, B = Bh + Bl; Ah*Bh + Al*Bh + Ah*Bl, FP32 accumulate
+// in TMEM), which keeps FP32-level accuracy (error ~2^-21 relative).
+//
+// Roles in a CTA (5 warps), persistent over tiles:
+//   warps 0-3  build their candidate's 32 rows of A (gather the neighbours' feature
+//              rows, scale by the float64 distance weights, split hi/lo) straight
+//              into shared memory in the UMMA K-major core-matrix layout, then
+//              drain the PREVIOUS tile's accumulator: tcgen05.ld of their 32 TMEM
+//              lanes (= their candidate's 32 neighbours), butterfly max over the
+//              lanes (the max-pool over K), one coalesced 128-byte store;
+//   warp 4     allocates TMEM, waits for A, issues the 15 tcgen05.mma of a tile from
+//              one lane and commits to the mbarriers.
+// A is gathered (index-driven) and cannot be described by a TMA tensor map; the
+// operands reach the tensor core through shared-memory matrix descriptors.
+#include "common.cuh"
+
+namespace dvcp {
+
+constexpr int TC_K = 40;                       // padded reduction length
+constexpr int TC_ROWS = 128;                   // rows per tile = 4 candidates x 32 neighbours
+constexpr int TC_A_BYTES = TC_ROWS * TC_K * 4;  // one A plane (hi or lo)
+constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one B plane
+constexpr int TC_STAGES = 2;
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_B_BYTES + 256;
+
+// byte offset of element (row r, column k) in the K-major, no-swizzle canonical layout:
+// 8x(16 B) core matrices; core (r/8, k/4) at ((r/8) * (K/4) + k/4) * 128 B.
+__host__ __device__ constexpr int tc_off(int r, int k) {
+    return ((r >> 3) * (TC_K / 4) + (k >> 2)) * 128 + (r & 7) * 16 + (k & 3) * 4;
+}
+constexpr unsigned TC_LBO = 128;                  // next core matrix along K
+constexpr unsigned TC_SBO = (TC_K / 4) * 128;     // next core matrix along M / N
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
+           (1ull << 46);   // version 1 (Blackwell), base offset 0, SWIZZLE_NONE
+}
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 32
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(160, 2)
+dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__restrict__ tfeat,
+                  const float *__restrict__ kdist, const int32_t *__restrict__ kidx, int N, int64_t total_cand,
+                  int64_t Q, const float *__restrict__ Bhi, const float *__restrict__ Blo, int per_feature_weight,
+                  float *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *sA = smem;                                      // [stage][hi|lo][TC_A_BYTES]
+    unsigned char *sB = smem + TC_STAGES * 2 * TC_A_BYTES;         // [hi|lo][TC_B_BYTES]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_B_BYTES);
+    uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < TC_B_BYTES / 4; i += blockDim.x) {
+        reinterpret_cast<float *>(sB)[i] = Bhi[i];
+        reinterpret_cast<float *>(sB + TC_B_BYTES)[i] = Blo[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full[s], 4);     // one arrive per producer warp
+            mbar_init(&empty[s], 1);    // tcgen05.commit
+            mbar_init(&tfull[s], 1);    // tcgen05.commit
+            mbar_init(&tempty[s], 4);   // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(64u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // B was written with ordinary stores: make it visible to the tensor core's (async) proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t ntiles = (total_cand + 3) / 4;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 4) {
+        // ------------------------------ MMA issuer ------------------------------
+        const uint32_t a_base = smem_u32(sA), b_hi = smem_u32(sB), b_lo = smem_u32(sB + TC_B_BYTES);
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i & 1);
+            const unsigned ph = (unsigned)((i >> 1) & 1);
+            mbar_wait(&full[s], ph);            // A(i) is in shared memory
+            mbar_wait(&tempty[s], ph ^ 1);      // accumulator s drained (tile i-2)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t d = tmem_base + (uint32_t)s * 32u;   // 32 FP32 columns per accumulator
+                const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < TC_K / 8; ++ks) {
+                    const uint32_t ko = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks per MMA (K = 8)
+                    umma_tf32(d, make_desc(a_hi + ko), make_desc(b_hi + ko), ks > 0);
+                    umma_tf32(d, make_desc(a_lo + ko), make_desc(b_hi + ko), 1u);
+                    umma_tf32(d, make_desc(a_hi + ko), make_desc(b_lo + ko), 1u);
+                }
+                umma_commit(&empty[s]);   // shared-memory stage may be rewritten
+                umma_commit(&tfull[s]);   // accumulator is complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------- A producers + epilogue (warps 0-3) ----------------------
+        auto epilogue = [&](int64_t i) {
+            const int s = (int)(i & 1);
+            const unsigned ph = (unsigned)((i >> 1) & 1);
+            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + warp;
+            mbar_wait(&tfull[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)s * 32u;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[s]);
+            // max over the 32 neighbours (lanes): butterfly transpose-reduce, lane o ends with channel o
+            float y[32];
+#pragma unroll
+            for (int o = 0; o < 32; ++o) y[o] = __uint_as_float(v[o]);
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+                const bool up = (lane & st) != 0;
+#pragma unroll
+                for (int o = 0; o < st; ++o) {
+                    const float send = up ? y[o] : y[o + st];
+                    const float keep = up ? y[o + st] : y[o];
+                    y[o] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, st));
+                }
+            }
+            if (gq < total_cand) out[gq * 32 + lane] = y[0];
+        };
+
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i & 1);
+            const unsigned ph = (unsigned)((i >> 1) & 1);
+            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + warp;   // this warp's candidate
+            mbar_wait(&empty[s], ph ^ 1);   // MMAs of tile i-2 have finished reading stage s
+            unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_BYTES;
+            const int r = warp * 32 + lane;   // row of the tile = neighbour `lane` of candidate `warp`
+            float x[TC_K];
+#pragma unroll
+            for (int k = 0; k < TC_K; ++k) x[k] = 0.f;
+            if (gq < total_cand) {
+                const int b = (int)(gq / Q);
+                const int id = __ldg(kidx + gq * 32 + lane);
+                const double dj = (double)__ldg(kdist + gq * 32 + lane);
+                double sum = dj;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const double wl = dj / sum;
+                const float4 *fp = reinterpret_cast<const float4 *>(tfeat + ((int64_t)b * N + id) * 32);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 f = __ldg(fp + k4);
+                    const float fe[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ch = 4 * k4 + e;
+                        const double w = per_feature_weight ? __shfl_sync(0xffffffffu, wl, ch) : wl;
+                        x[ch] = (float)((double)fe[e] * w);
+                    }
+                }
+                x[32] = txyz.at(b, id, 0) - __ldg(cand + gq * 3);
+                x[33] = txyz.at(b, id, 1) - __ldg(cand + gq * 3 + 1);
+                x[34] = txyz.at(b, id, 2) - __ldg(cand + gq * 3 + 2);
+                x[35] = 1.0f;   // bias column
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < TC_K / 4; ++k4) {
+                float4 h, l;
+                float *hp = &h.x, *lp = &l.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = x[4 * k4 + e];
+                    const float hv = __uint_as_float(__float_as_uint(v) & 0xffffe000u);   // exact TF32
+                    hp[e] = hv;
+                    lp[e] = v - hv;
+                }
+                *reinterpret_cast<float4 *>(ahi + tc_off(r, 4 * k4)) = h;
+                *reinterpret_cast<float4 *>(alo + tc_off(r, 4 * k4)) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (i > 0) epilogue(i - 1);
+        }
+        if (my_tiles > 0) epilogue(my_tiles - 1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    }
+}
+
+}  // namespace dvcp
+
+using namespace dvcp;
+
+extern "C" int dvcp_dfe_tc_b_floats(void) { return 32 * TC_K; }
+
+// Host helper: position (in floats) of B[n][k] inside the 32 x 40 operand image.
+extern "C" int dvcp_dfe_tc_b_offset(int n, int k) {
+    if (n < 0 || n >= 32 || k < 0 || k >= TC_K) return DVCP_E_ARG;
+    return tc_off(n, k) / 4;
+}
+
+extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const float *tgt_feat, const float *knn_dist,
+                               const int32_t *knn_idx, int B, int N, int64_t Q, const float *b_hi,
+                               const float *b_lo, int quirks, float *out, dvcp_stream_t stream) {
+    if (!cand || !tgt_xyz.base || !tgt_feat || !knn_dist || !knn_idx || !b_hi || !b_lo || !out || B <= 0 || N <= 0 ||
+        Q <= 0)
+        return DVCP_E_ARG;
+    const int64_t total = (int64_t)B * Q;
+    const int64_t ntiles = (total + 3) / 4;
+    DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    int64_t grid = 2 * DVCP_NUM_SMS;
+    if (grid > ntiles) grid = ntiles;
+    // one cloud stride for the whole batch: tgt_xyz is addressed with b = candidate / Q
+    dfe_tgt_tc_kernel<<<(unsigned)grid, 160, TC_SMEM, (cudaStream_t)stream>>>(
+        cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, (quirks >> 1) & 1, out);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}

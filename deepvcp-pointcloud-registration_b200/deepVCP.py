@@ -43,6 +43,7 @@ class DeepVCP(nn.Module):
         self.group_radius = group_radius
         self.quirks = quirks
         self.last = None   # stage tensors of the most recent forward (for tests / inspection)
+        self.dfe_tensor_cores = True    # tcgen05 embedding (collapsed affine map, 3xTF32); False = FP32 CUDA-core kernel
         self.profile = False   # record a CUDA event after every stage (bench.py reads them)
         self._events = None
 
@@ -123,8 +124,13 @@ class DeepVCP(nn.Module):
                 kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
                                         want32=True)
             mark("knn")
-            tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
-                                       self.quirks)                            # [B,K*C,32]
+            if self.dfe_tensor_cores:
+                b_hi, b_lo = self.DFE.tc_operand()
+                tgt_dfe = F_.dfe_tgt_tc(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, b_hi, b_lo,
+                                        self.quirks)                           # [B,K*C,32]
+            else:
+                tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
+                                           self.quirks)
             mark("dfe")
             # corresponding point generation
             vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.view(B * K, C * 32), 1,

@@ -23,6 +23,14 @@ class feat_embedding_layer(nn.Module):
             self._cache = (key, ts, dfe_params(*ts))
         return self._cache[2]
 
+    def tc_operand(self):
+        """(b_hi, b_lo) operand images of the collapsed affine map for the tcgen05 kernel."""
+        ps = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_tc_cache", None) is None or self._tc_cache[0] != key:
+            self._tc_cache = (key, F_.dfe_tc_operand(*ps, device=self.fc1.weight.device))
+        return self._tc_cache[1]
+
     def forward(self, X, src=True):
         """src: [B,N,K,35] -> [B,N,32]; tgt: [B,N,C,K,35] -> [B,N,C,32]."""
         return F_.dfe_dense(X, self.params())

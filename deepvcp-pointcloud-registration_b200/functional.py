@@ -274,6 +274,40 @@ def dfe_tgt_fused(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, dfe, qui
     return out
 
 
+def dfe_tc_operand(W1, b1, W2, b2, W3, b3, device):
+    """Collapse the three un-activated Linear layers (float64) and lay the 32 x 40
+    operand out for the tensor-core kernel; returns (b_hi, b_lo) device tensors."""
+    W1, b1, W2, b2, W3, b3 = (t.detach().double().cpu() for t in (W1, b1, W2, b2, W3, b3))
+    Wc = W3 @ W2 @ W1                                   # [32, 35]
+    bc = W3 @ (W2 @ b1 + b2) + b3                       # [32]
+    Bm = torch.zeros(32, 40, dtype=torch.float64)
+    Bm[:, :32] = Wc[:, 3:35]
+    Bm[:, 32:35] = Wc[:, 0:3]
+    Bm[:, 35] = bc
+    Bm = Bm.float()
+    hi = (Bm.view(torch.int32) & -8192).view(torch.float32)       # clear the 13 low mantissa bits: exact TF32
+    lo = Bm - hi
+    n = torch.arange(32).view(32, 1).expand(32, 40)
+    k = torch.arange(40).view(1, 40).expand(32, 40)
+    off = ((n >> 3) * 10 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3)
+    assert int(off[9, 17]) == lib().dvcp_dfe_tc_b_offset(9, 17) and lib().dvcp_dfe_tc_b_floats() == 1280
+    img_hi = torch.zeros(1280, dtype=torch.float32)
+    img_lo = torch.zeros(1280, dtype=torch.float32)
+    img_hi[off.reshape(-1)] = hi.reshape(-1)
+    img_lo[off.reshape(-1)] = lo.reshape(-1)
+    return img_hi.to(device), img_lo.to(device)
+
+
+def dfe_tgt_tc(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, b_hi, b_lo, quirks):
+    require_cuda(cand, tgt_feat, knn_dist, knn_idx32, b_hi, b_lo)
+    Q = knn_dist.shape[1]
+    out = torch.empty(B, Q, 32, dtype=torch.float32, device=cand.device)
+    check(lib().dvcp_dfe_tgt_tc(ptr(_f32c(cand)), tgt_cloud, ptr(_f32c(tgt_feat)), ptr(knn_dist), ptr(knn_idx32), B, N,
+                                Q, ptr(b_hi), ptr(b_lo), quirks, ptr(out), stream_ptr(cand.device)), "dvcp_dfe_tgt_tc")
+    _count(1)
+    return out
+
+
 def dfe_dense(X, dfe):
     """X [..., K, 35] float32/float64 -> [..., 32]."""
     require_cuda(X)

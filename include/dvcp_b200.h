@@ -181,6 +181,20 @@ DVCP_API int dvcp_dfe_tgt_fused(const float *cand, dvcp_cloud_t tgt_xyz, const f
                        const float *knn_dist, const int32_t *knn_idx, int B, int N, int64_t Q,
                        dvcp_dfe_params_t dfe, int quirks, float *out, dvcp_stream_t stream);
 
+/* Tensor-core form of dvcp_dfe_tgt_fused (tcgen05 / TMEM, 3xTF32). The three
+ * un-activated Linear layers are collapsed by the caller into one affine map
+ * (Wc = W3 W2 W1, bc = W3 (W2 b1 + b2) + b3, float64 on the host); b_hi / b_lo are
+ * the TF32 high and low parts of the 32 x 40 operand image
+ *     Bm[n][k] = Wc[n][3 + k] (k < 32), Wc[n][k - 32] (32 <= k < 35), bc[n] (k = 35), 0
+ * stored at float offset dvcp_dfe_tc_b_offset(n, k) (UMMA K-major core-matrix
+ * layout), dvcp_dfe_tc_b_floats() floats each. Same inputs / output as the fused
+ * entry point; results agree with it to FP32 round-off of the collapsed map. */
+DVCP_API int dvcp_dfe_tc_b_floats(void);
+DVCP_API int dvcp_dfe_tc_b_offset(int n, int k);
+DVCP_API int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const float *tgt_feat, const float *knn_dist,
+                    const int32_t *knn_idx, int B, int N, int64_t Q, const float *b_hi, const float *b_lo,
+                    int quirks, float *out, dvcp_stream_t stream);
+
 /* ---- a15 feat_embedding_layer.forward on a materialised input
  *          deep_feat_embedding.py:23-61
  * X [rows,K,35] (dtype 0 float32 / 1 float64, cast like X.float()) -> out [rows,32]. */

@@ -370,6 +370,34 @@ def test_cat_feat_tgt_module_and_fused_dfe(dv, F):
     assert rel_err(out, T(g["tgt_dfe_s"])) < 1e-5
 
 
+def test_dfe_tensor_core_kernel_vs_fp32_kernel(dv, F, synthetic):
+    """tcgen05 / TMEM embedding (collapsed map, 3xTF32) against the FP32 CUDA-core kernel
+    and the oracle: within 1e-3 relative (north star), in practice ~1e-6."""
+    lib = importlib.import_module(PKG + "._lib")
+    g = load_golden("fwd_modelnet_n1024_g5")
+    sd = golden_state_dict(g)
+    dfe = dv.feat_embedding_layer()
+    dfe.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("DFE.")})
+    dfe = dfe.to(DEV)
+    cand = T(g["candidates"])
+    B, M, C, _ = cand.shape
+    tg = T(g["tgt"]).to(DEV)
+    tfeat = T(g["tgt_fe_feat"]).to(DEV)
+    cq = cand.view(B, M * C, 3).to(DEV)
+    kd, _, ki = F.knn(lib.cloud_cm(tg), tg.device, B, 1024, cq, 32, want64=False, want32=True)
+    ref = F.dfe_tgt_fused(cq, lib.cloud_cm(tg), tfeat, kd, ki, B, 1024, dfe.params(), lib.QUIRKS_REFERENCE)
+    b_hi, b_lo = dfe.tc_operand()
+    for nq in (M * C, 4 * 7 + 1, 3):                   # full, ragged tile tail, less than one tile
+        out = F.dfe_tgt_tc(cq[:, :nq].contiguous(), lib.cloud_cm(tg), tfeat, kd[:, :nq].contiguous(),
+                           ki[:, :nq].contiguous(), B, 1024, b_hi, b_lo, lib.QUIRKS_REFERENCE)
+        torch.cuda.synchronize()
+        assert rel_err(out, ref[:, :nq]) < FEAT_RTOL
+        assert rel_err(out, ref[:, :nq]) < 2e-5
+    s = int(g["stride"])
+    out = F.dfe_tgt_tc(cq, lib.cloud_cm(tg), tfeat, kd, ki, B, 1024, b_hi, b_lo, lib.QUIRKS_REFERENCE)
+    assert rel_err(out.view(B, M, C, 32)[:, :, ::s], T(g["tgt_dfe_s"])) < 2e-5
+
+
 def test_cpg_standalone_vs_reference_fixture(dv, prim):
     sd = golden_state_dict(prim, "cpg_sd/")
     net = dv.cpg()
@@ -427,10 +455,11 @@ def test_kabsch_sweep_batch(dv, F):
 
 
 # -------------------------------------------------------- whole forward ------
-def build_model(dv, g, N):
+def build_model(dv, g, N, tensor_cores=True):
     use_normal = g["src"].shape[1] == 6
     model = dv.DeepVCP(use_normal=use_normal, npoint=N, r=float(g["r"]), s=float(g["s"]))
     model.load_state_dict(golden_state_dict(g))
+    model.dfe_tensor_cores = tensor_cores
     return model.to(DEV).eval()
 
 
@@ -440,11 +469,12 @@ def topk_equivalent(scores, a, b):
     return True
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("name", ["fwd_modelnet_n1024_g5", "fwd_modelnet_n512_g6", "fwd_kitti_n2048_g7"])
-def test_forward_vs_reference_fixture(dv, name):
+def test_forward_vs_reference_fixture(dv, name, tensor_cores):
     g = load_golden(name)
     N = int(g["n_points"])
-    model = build_model(dv, g, N)
+    model = build_model(dv, g, N, tensor_cores)
     st = g["starts"]
     starts = tuple(torch.tensor([int(v)]) for v in st)
     src, tgt, R = T(g["src"]), T(g["tgt"]), T(g["R"])

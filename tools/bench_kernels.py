@@ -76,6 +76,8 @@ def main():
         "knn_indexed_kp": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=G * G * G, zline=G, want64=False, want32=True),
         "dfe": lambda: F_.dfe_tgt_fused(cand, lib.cloud_cm(tgt), tfeat, kd, ki, B, N, model.DFE.params(),
                                         lib.QUIRKS_REFERENCE),
+        "dfe_tc": lambda: F_.dfe_tgt_tc(cand, lib.cloud_cm(tgt), tfeat, kd, ki, B, N, *model.DFE.tc_operand(),
+                                        lib.QUIRKS_REFERENCE),
         "cpg": lambda: F_.cpg(L["src_dfe"].view(B * K, 32), tgt_dfe.view(B * K, Cc * 32), 1,
                               cand.view(B * K, Cc, 3), G, model.cpg.params()),
         "forward": lambda: model(src, tgt, R, torch.zeros(1, 3), starts=starts),
