@@ -107,7 +107,7 @@ __device__ __forceinline__ float warp_max_f(float v) {
 // Bucket j (32 consecutive points of the Morton order) belongs to warp j % WARPS,
 // slot j / WARPS: spatial neighbours are spread over the warps, so the few
 // buckets a round revisits are processed in parallel instead of by one warp.
-template <int WARPS, int BPW>
+template <int WARPS, int BPW, bool BATCHED>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int64_t cs, int N,
                     int npoint, const int64_t *__restrict__ start, int64_t *__restrict__ out64,
@@ -216,25 +216,36 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
     // ---- per-lane state: dist[k] = point `lane` of bucket (k*WARPS + warp);
     //      lane k additionally owns that bucket's box and (max dist, tie word). ----
     float dist[BPW];
+    unsigned idp[(BPW + 1) / 2];   // original index of my point in bucket k, two 16-bit fields per word
     float bminx = 0.f, bminy = 0.f, bminz = 0.f, bmaxx = 0.f, bmaxy = 0.f, bmaxz = 0.f;
-    unsigned bval = 0u, blo = 0u;
+    unsigned bval = 0u, blo = 0u;     // best (largest) key of my bucket: dist bits, tie word
+    unsigned sval = 0u, slo = 0u;     // second-best key of my bucket (batched kernel only)
+#pragma unroll
+    for (int k = 0; k < (BPW + 1) / 2; ++k) idp[k] = 0u;
 #pragma unroll
     for (int k = 0; k < BPW; ++k) {
         const int pos = (k * WARPS + warp) * 32 + lane;
-        const bool valid = sidx[pos] != 0xffffu;
+        const unsigned id = sidx[pos];
+        const bool valid = id != 0xffffu;
+        idp[k >> 1] |= id << (16 * (k & 1));
         dist[k] = valid ? 1e10f : 0.0f;
         const float x = sx[pos], y = sy[pos], z = sz[pos];
         const float a0 = warp_min_f(valid ? x : INFINITY), a1 = warp_min_f(valid ? y : INFINITY),
                     a2 = warp_min_f(valid ? z : INFINITY);
         const float z0 = warp_max_f(valid ? x : -INFINITY), z1 = warp_max_f(valid ? y : -INFINITY),
                     z2 = warp_max_f(valid ? z : -INFINITY);
-        unsigned hi = __float_as_uint(dist[k]);
-        unsigned lo = ((0xffffu - (unsigned)sidx[pos]) << 16) | (unsigned)pos;
+        const unsigned hi0 = __float_as_uint(dist[k]);
+        const unsigned lo0 = ((0xffffu - id) << 16) | (unsigned)pos;
+        unsigned hi = hi0, lo = lo0;
         warp_max_pair(hi, lo);
+        const bool mine = hi0 == hi && lo0 == lo;
+        unsigned h2 = mine ? 0u : hi0, l2 = mine ? 0u : lo0;
+        warp_max_pair(h2, l2);
         if (lane == k) {
             bminx = a0; bminy = a1; bminz = a2;
             bmaxx = z0; bmaxy = z1; bmaxz = z2;
             bval = hi; blo = lo;
+            sval = h2; slo = l2;
         }
         if (index.bucket_box) {
             const int cntv = __popc(__ballot_sync(0xffffffffu, valid));
@@ -245,73 +256,268 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
             }
         }
     }
+    if (npoint <= 0) return;
 
-    unsigned pos = s_startpos, idx = startidx;
-    for (int i = 0; i < npoint; ++i) {
-        if (tid == 0) {
-            if (out64) out64[(int64_t)b * npoint + i] = idx;
-            if (out32) out32[(int64_t)b * npoint + i] = (int32_t)idx;
-        }
-        const float cx = sx[pos], cy = sy[pos], cz = sz[pos];
-        // lower bound of the rounded distance to any member of my bucket
-        const float ex = fmaxf(fmaxf(__fsub_rn(bminx, cx), __fsub_rn(cx, bmaxx)), 0.0f);
-        const float ey = fmaxf(fmaxf(__fsub_rn(bminy, cy), __fsub_rn(cy, bmaxy)), 0.0f);
-        const float ez = fmaxf(fmaxf(__fsub_rn(bminz, cz), __fsub_rn(cz, bmaxz)), 0.0f);
-        const float lb = sq3_nofma(ex, ey, ez);
-        const unsigned mask = __ballot_sync(0xffffffffu, lane < BPW && lb < __uint_as_float(bval));
-        if (mask) {
+    if constexpr (!BATCHED) {
+        // ---- sequential rounds: one centroid per block-wide argmax ----
+        unsigned pos = s_startpos, idx = startidx;
+        for (int i = 0; i < npoint; ++i) {
+            if (tid == 0) {
+                if (out64) out64[(int64_t)b * npoint + i] = idx;
+                if (out32) out32[(int64_t)b * npoint + i] = (int32_t)idx;
+            }
+            const float cx = sx[pos], cy = sy[pos], cz = sz[pos];
+            // lower bound of the rounded distance to any member of my bucket
+            const float ex = fmaxf(fmaxf(__fsub_rn(bminx, cx), __fsub_rn(cx, bmaxx)), 0.0f);
+            const float ey = fmaxf(fmaxf(__fsub_rn(bminy, cy), __fsub_rn(cy, bmaxy)), 0.0f);
+            const float ez = fmaxf(fmaxf(__fsub_rn(bminz, cz), __fsub_rn(cz, bmaxz)), 0.0f);
+            const float lb = sq3_nofma(ex, ey, ez);
+            const unsigned mask = __ballot_sync(0xffffffffu, lane < BPW && lb < __uint_as_float(bval));
+            if (mask) {
 #pragma unroll
-            for (int g = 0; g < (BPW + 7) / 8; ++g) {
-                if (!(mask & (0xffu << (8 * g)))) continue;
+                for (int g = 0; g < (BPW + 7) / 8; ++g) {
+                    if (!(mask & (0xffu << (8 * g)))) continue;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const int k = g * 8 + kk;
-                    if (k >= BPW) break;
-                    if (!(mask & (1u << k))) continue;
-                    const int pp = (k * WARPS + warp) * 32 + lane;
-                    const float d = sq3_nofma(__fsub_rn(sx[pp], cx), __fsub_rn(sy[pp], cy), __fsub_rn(sz[pp], cz));
-                    if (d < dist[k]) dist[k] = d;
-                    unsigned hi = __float_as_uint(dist[k]);
-                    unsigned lo = ((0xffffu - (unsigned)sidx[pp]) << 16) | (unsigned)pp;
-                    warp_max_pair(hi, lo);
-                    if (lane == k) {
-                        bval = hi;
-                        blo = lo;
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const int k = g * 8 + kk;
+                        if (k >= BPW) break;
+                        if (!(mask & (1u << k))) continue;
+                        const int pp = (k * WARPS + warp) * 32 + lane;
+                        const float d = sq3_nofma(__fsub_rn(sx[pp], cx), __fsub_rn(sy[pp], cy), __fsub_rn(sz[pp], cz));
+                        if (d < dist[k]) dist[k] = d;
+                        unsigned hi = __float_as_uint(dist[k]);
+                        unsigned lo = ((0xffffu - ((idp[k >> 1] >> (16 * (k & 1))) & 0xffffu)) << 16) | (unsigned)pp;
+                        warp_max_pair(hi, lo);
+                        if (lane == k) {
+                            bval = hi;
+                            blo = lo;
+                        }
                     }
                 }
             }
+            unsigned hi = lane < BPW ? bval : 0u, lo = lane < BPW ? blo : 0u;
+            warp_max_pair(hi, lo);
+            if (WARPS > 1) {
+                if (lane == 0) {
+                    s_hi[i & 1][warp] = hi;
+                    s_lo[i & 1][warp] = lo;
+                }
+                __syncthreads();
+                hi = lane < WARPS ? s_hi[i & 1][lane] : 0u;
+                lo = lane < WARPS ? s_lo[i & 1][lane] : 0u;
+                warp_max_pair(hi, lo);
+            }
+            pos = lo & 0xffffu;
+            idx = 0xffffu - (lo >> 16);
         }
-        unsigned hi = lane < BPW ? bval : 0u, lo = lane < BPW ? blo : 0u;
-        warp_max_pair(hi, lo);
-        if (WARPS > 1) {
-            if (lane == 0) {
-                s_hi[i & 1][warp] = hi;
-                s_lo[i & 1][warp] = lo;
+    } else {
+        // ---- batched rounds (exact): several centroids per block-wide step ----
+        // Order all points by the key (dist, lowest index first). Let S be the largest
+        // SECOND-best key of any bucket: every point whose key exceeds S is the best of
+        // its bucket, so the bucket maxima above S are ALL the points above S. Walking
+        // those candidates in key order, a candidate whose distance no centroid accepted
+        // in this step can lower (d >= its dist for each of them) is still the global
+        // maximum when its turn comes, hence exactly the next FPS pick; a candidate that
+        // is lowered to a key <= T (T = S, or the 33rd candidate key) drops behind every
+        // remaining candidate and is skipped; a candidate lowered but still above T ends
+        // the step. Then all accepted centroids update the buckets they can reach.
+        __syncthreads();   // everyone has read sidx: its storage becomes the candidate list
+        unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(sidx);   // [CAP / 32]
+        __shared__ unsigned long long s_top[32];
+        __shared__ unsigned long long s_T;
+        __shared__ float4 s_acc[32];
+        __shared__ unsigned s_ncand, s_nacc;
+        if (tid == 0) {
+            const unsigned sp = s_startpos;
+            s_acc[0] = make_float4(sx[sp], sy[sp], sz[sp], 0.f);
+            s_nacc = 1u;
+            s_ncand = 0u;
+            if (out64) out64[(int64_t)b * npoint] = startidx;
+            if (out32) out32[(int64_t)b * npoint] = (int32_t)startidx;
+        }
+        __syncthreads();
+        int produced = 0;
+        while (true) {
+            // ---- update: the A centroids accepted in the previous step ----
+            const int A = (int)s_nacc;
+            unsigned F = 0u;   // bit a: centroid a can lower a distance in my bucket
+            {
+                const float bestval = lane < BPW ? __uint_as_float(bval) : 0.0f;
+                for (int a = 0; a < A; ++a) {
+                    const float4 c = s_acc[a];
+                    const float ex = fmaxf(fmaxf(__fsub_rn(bminx, c.x), __fsub_rn(c.x, bmaxx)), 0.0f);
+                    const float ey = fmaxf(fmaxf(__fsub_rn(bminy, c.y), __fsub_rn(c.y, bmaxy)), 0.0f);
+                    const float ez = fmaxf(fmaxf(__fsub_rn(bminz, c.z), __fsub_rn(c.z, bmaxz)), 0.0f);
+                    F |= (unsigned)(sq3_nofma(ex, ey, ez) < bestval) << a;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BPW; ++k) {
+                unsigned Fk = __shfl_sync(0xffffffffu, F, k);
+                if (Fk) {
+                    const int pp = (k * WARPS + warp) * 32 + lane;
+                    const float x = sx[pp], y = sy[pp], z = sz[pp];
+                    float dk = dist[k];
+                    do {
+                        const int a = __ffs(Fk) - 1;
+                        Fk &= Fk - 1;
+                        const float4 c = s_acc[a];
+                        const float d = sq3_nofma(__fsub_rn(x, c.x), __fsub_rn(y, c.y), __fsub_rn(z, c.z));
+                        dk = d < dk ? d : dk;
+                    } while (Fk);
+                    dist[k] = dk;
+                    const unsigned hi0 = __float_as_uint(dk);
+                    const unsigned lo0 = ((0xffffu - ((idp[k >> 1] >> (16 * (k & 1))) & 0xffffu)) << 16) | (unsigned)pp;
+                    unsigned hi = hi0, lo = lo0;
+                    warp_max_pair(hi, lo);
+                    const bool mine = hi0 == hi && lo0 == lo;
+                    unsigned h2 = mine ? 0u : hi0, l2 = mine ? 0u : lo0;
+                    warp_max_pair(h2, l2);
+                    if (lane == k) {
+                        bval = hi; blo = lo;
+                        sval = h2; slo = l2;
+                    }
+                }
+            }
+            produced += A;
+            if (produced >= npoint) break;
+            // ---- S = largest second-best key over all buckets ----
+            {
+                unsigned hi = lane < BPW ? sval : 0u, lo = lane < BPW ? slo : 0u;
+                warp_max_pair(hi, lo);
+                if (lane == 0) {
+                    s_hi[0][warp] = hi;
+                    s_lo[0][warp] = lo;
+                }
             }
             __syncthreads();
-            hi = lane < WARPS ? s_hi[i & 1][lane] : 0u;
-            lo = lane < WARPS ? s_lo[i & 1][lane] : 0u;
-            warp_max_pair(hi, lo);
+            unsigned S_hi = lane < WARPS ? s_hi[0][lane] : 0u, S_lo = lane < WARPS ? s_lo[0][lane] : 0u;
+            warp_max_pair(S_hi, S_lo);
+            const unsigned long long S = ((unsigned long long)S_hi << 32) | S_lo;
+            // ---- candidates: bucket maxima above S (never a point of distance 0) ----
+            {
+                const unsigned long long key = ((unsigned long long)bval << 32) | blo;
+                const bool isc = lane < BPW && bval != 0u && key > S;
+                const unsigned m = __ballot_sync(0xffffffffu, isc);
+                if (m) {
+                    unsigned basev = 0u;
+                    if (lane == 0) basev = atomicAdd(&s_ncand, (unsigned)__popc(m));
+                    basev = __shfl_sync(0xffffffffu, basev, 0);
+                    if (isc) s_cand[basev + __popc(m & ((1u << lane) - 1u))] = key;
+                }
+            }
+            __syncthreads();
+            const int n = (int)s_ncand;
+            if (n == 0) {
+                // every remaining distance is 0: the argmax stays the lowest index (pointnet2_utils.py:83)
+                unsigned hi = lane < BPW ? bval : 0u, lo = lane < BPW ? blo : 0u;
+                warp_max_pair(hi, lo);
+                if (lane == 0) {
+                    s_hi[1][warp] = hi;
+                    s_lo[1][warp] = lo;
+                }
+                __syncthreads();
+                hi = lane < WARPS ? s_hi[1][lane] : 0u;
+                lo = lane < WARPS ? s_lo[1][lane] : 0u;
+                warp_max_pair(hi, lo);
+                const unsigned idx = 0xffffu - (lo >> 16);
+                for (int i = produced + tid; i < npoint; i += THREADS) {
+                    if (out64) out64[(int64_t)b * npoint + i] = idx;
+                    if (out32) out32[(int64_t)b * npoint + i] = (int32_t)idx;
+                }
+                break;
+            }
+            // ---- rank the candidates; the 32 largest go to s_top in descending order ----
+            for (int t = tid; t < n; t += THREADS) {
+                const unsigned long long key = s_cand[t];
+                int rank = 0;
+                for (int u = 0; u < n; ++u) rank += s_cand[u] > key;
+                if (rank < 32) s_top[rank] = key;
+                if (rank == 32) s_T = key;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const int m = n < 32 ? n : 32;
+                const unsigned long long T = n > 32 ? s_T : S;
+                const unsigned long long key = lane < m ? s_top[lane] : 0ull;
+                const unsigned klo = (unsigned)(key & 0xffffffffu);
+                const unsigned p = klo & 0xffffu;
+                const float x = sx[p], y = sy[p], z = sz[p];
+                const float dj = __uint_as_float((unsigned)(key >> 32));
+                unsigned K = 0u, L = 0u;   // bit i: earlier candidate i lowers me / lowers me to a key <= T
+                for (int i = 0; i < m; ++i) {
+                    const float xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i),
+                                zi = __shfl_sync(0xffffffffu, z, i);
+                    const float d = sq3_nofma(__fsub_rn(x, xi), __fsub_rn(y, yi), __fsub_rn(z, zi));
+                    const bool kill = i < lane && d < dj;
+                    const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | klo;
+                    K |= (unsigned)kill << i;
+                    L |= (unsigned)(kill && nk <= T) << i;
+                }
+                // first-come resolution in key order: accepted unless an ACCEPTED earlier candidate lowers me
+                const unsigned validm = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
+                unsigned acc = 0u, rej = ~validm;
+                int state = lane < m ? 0 : 2;
+                while ((acc | rej) != 0xffffffffu) {
+                    if (state == 0) {
+                        if (K & acc) state = 2;
+                        else if ((K & ~rej) == 0u) state = 1;
+                    }
+                    acc = __ballot_sync(0xffffffffu, state == 1);
+                    rej = __ballot_sync(0xffffffffu, state == 2);
+                }
+                const bool stopper = lane < m && state == 2 && (L & acc) == 0u;
+                const unsigned stopm = __ballot_sync(0xffffffffu, stopper);
+                if (stopm) acc &= (1u << (__ffs(stopm) - 1)) - 1u;
+                const int rank = __popc(acc & ((1u << lane) - 1u));
+                const int rem = npoint - produced;
+                if (((acc >> lane) & 1u) && rank < rem) {
+                    s_acc[rank] = make_float4(x, y, z, 0.f);
+                    const unsigned idx = 0xffffu - (klo >> 16);
+                    if (out64) out64[(int64_t)b * npoint + produced + rank] = idx;
+                    if (out32) out32[(int64_t)b * npoint + produced + rank] = (int32_t)idx;
+                }
+                if (lane == 0) {
+                    const int na = __popc(acc);
+                    s_nacc = (unsigned)(na < rem ? na : rem);
+                    s_ncand = 0u;
+                }
+            }
+            __syncthreads();
         }
-        pos = lo & 0xffffu;
-        idx = 0xffffu - (lo >> 16);
     }
 }
 
-template <int WARPS, int BPW>
-static int launch_bucketed(const dvcp_cloud_t &c, int B, int N, int npoint, const int64_t *start,
+template <int WARPS, int BPW, bool BATCHED>
+static int launch_bucketed_impl(const dvcp_cloud_t &c, int B, int N, int npoint, const int64_t *start,
                            int64_t *o64, int32_t *o32, dvcp_cloud_index_t index, cudaStream_t st) {
     constexpr int CAP = WARPS * BPW * 32;
     if (index.sorted_xyz && (index.cap != CAP || !index.sorted_idx || !index.bucket_box)) return DVCP_E_ARG;
     using Sort = cub::BlockRadixSort<unsigned, WARPS * 32, BPW, unsigned>;
     size_t data = (size_t)CAP * (3 * sizeof(float) + sizeof(unsigned short));
     size_t smem = data > sizeof(typename Sort::TempStorage) ? data : sizeof(typename Sort::TempStorage);
-    auto k = fps_bucketed_kernel<WARPS, BPW>;
+    auto k = fps_bucketed_kernel<WARPS, BPW, BATCHED>;
     DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<B, WARPS * 32, smem, st>>>((const float *)c.base, c.bstride, c.pstride, c.cstride, N, npoint,
                                    start, o64, o32, index);
     DVCP_CHECK_LAUNCH();
     return 0;
+}
+
+// DVCP_FPS_SEQUENTIAL=1 selects the one-centroid-per-round loop (same results; for timing comparisons).
+static bool fps_sequential_mode() {
+    static const bool v = [] {
+        const char *e = getenv("DVCP_FPS_SEQUENTIAL");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
+template <int WARPS, int BPW>
+static int launch_bucketed(const dvcp_cloud_t &c, int B, int N, int npoint, const int64_t *start,
+                           int64_t *o64, int32_t *o32, dvcp_cloud_index_t index, cudaStream_t st) {
+    if (fps_sequential_mode()) return launch_bucketed_impl<WARPS, BPW, false>(c, B, N, npoint, start, o64, o32, index, st);
+    return launch_bucketed_impl<WARPS, BPW, true>(c, B, N, npoint, start, o64, o32, index, st);
 }
 
 static int dispatch_bucketed(const dvcp_cloud_t &xyz, int B, int N, int npoint, const int64_t *start,

@@ -87,6 +87,30 @@ def test_fps_kitti_shaped_full_size(dv, synthetic):
     assert torch.equal(out.sort()[0], torch.arange(16384).view(1, -1))   # npoint == N: a permutation
 
 
+@pytest.mark.parametrize("n,npoint,extent", [(2048, 2048, 1.0), (16384, 16384, 2.0), (4096, 1000, 0.75)])
+def test_fps_dense_lattice_heavy_ties_bit_exact(dv, n, npoint, extent):
+    """Dense 0.125 lattice: thousands of points share each distance value, so the batched
+    kernel's candidate threshold sits inside tie classes (index order decides)."""
+    xyz = lattice_cloud(n, 11, extent=extent)            # duplicates included
+    start = torch.tensor([n // 2])
+    ref = stages.farthest_point_sample(xyz, npoint, start)
+    out = dv.farthest_point_sample(xyz.to(DEV), npoint, start)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_fps_duplicates_and_padding_in_indexed_kernel(dv):
+    """Duplicate points leave distance-0 leftovers: the argmax then stays at the lowest index
+    (pointnet2_utils.py:83), also when npoint > N."""
+    g = torch.Generator().manual_seed(21)
+    base = torch.rand(1, 200, 3, generator=g)
+    xyz = torch.cat([base, base[:, :120], base[:, 50:130]], dim=1)      # 400 points, 200 distinct
+    for npoint in (150, 400, 450):
+        start = torch.tensor([333])
+        ref = stages.farthest_point_sample(xyz, npoint, start)
+        out = dv.farthest_point_sample(xyz.to(DEV), npoint, start)
+        assert torch.equal(out.cpu(), ref)
+
+
 def test_fps_plain_and_pruned_kernels_agree(dv, F):
     g = torch.Generator().manual_seed(3)
     xyz = (torch.randn(3, 3000, 3, generator=g) * 5).to(DEV)
