@@ -547,11 +547,32 @@ extern "C" int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index
     return dispatch_bucketed(xyz, B, N, 0, nullptr, nullptr, nullptr, index, (cudaStream_t)stream);
 }
 
+// fps_cluster.cu: one cloud per cluster of 8 CTAs, consuming an index that is already built.
+int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, int N, int npoint, const int64_t *start,
+                            int64_t *out64, int32_t *out32, cudaStream_t st);
+
+// Few large clouds (the K8 batch: 16 clouds for 148 SMs): spread each over a cluster. Many clouds fill
+// the GPU one CTA each, which does less total work. DVCP_FPS_CLUSTER=0/1 forces the choice.
+static bool fps_use_cluster(int B, int N) {
+    static const int forced = [] {
+        const char *e = getenv("DVCP_FPS_CLUSTER");
+        return e ? (e[0] == '1' ? 1 : 0) : -1;
+    }();
+    if (N <= 2048) return false;
+    if (forced >= 0) return forced == 1;
+    return B * 8 <= 2 * DVCP_NUM_SMS;
+}
+
 extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, const int64_t *start,
                         int64_t *out64, int32_t *out32, dvcp_cloud_index_t index, dvcp_stream_t stream) {
     using namespace dvcp;
     if (!xyz.base || !start || (!out64 && !out32) || B <= 0 || N <= 0 || npoint <= 0) return DVCP_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 0 && N <= 16384 && N >= 64 && index.sorted_xyz && !fps_sequential_mode() && fps_use_cluster(B, N)) {
+        const int rc = dispatch_bucketed(xyz, B, N, 0, nullptr, nullptr, nullptr, index, st);   // index only
+        if (rc != 0) return rc;
+        return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, st);
+    }
     if (dtype == 0 && N <= 16384 && N >= 64) return dispatch_bucketed(xyz, B, N, npoint, start, out64, out32, index, st);
     if (index.sorted_xyz) return DVCP_E_UNSUPPORTED;
     if (N > 57344) return DVCP_E_UNSUPPORTED;

@@ -72,12 +72,14 @@ class SpatialIndex:
 
 def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want32=False, index=None):
     start = _starts_to_device(start, B, device)
+    if index is None and N > 2048 and SpatialIndex.indexable(N, dtype):
+        index = SpatialIndex(B, N, device)   # workspace: lets the library spread each cloud over a cluster
     o64 = torch.empty(B, npoint, dtype=torch.int64, device=device) if want64 else None
     o32 = torch.empty(B, npoint, dtype=torch.int32, device=device) if want32 else None
     code = lib().dvcp_fps(xyz_cloud, 0 if dtype == torch.float32 else 1, B, N, npoint, ptr(start), ptr(o64),
                           ptr(o32), index.c() if index is not None else NULL_INDEX, stream_ptr(device))
     check(code, "dvcp_fps")
-    _count(1)
+    _count(2 if index is not None and N > 2048 else 1)   # index build + cluster kernel (an upper bound for huge B)
     return o64, o32
 
 

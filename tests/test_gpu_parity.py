@@ -111,6 +111,17 @@ def test_fps_duplicates_and_padding_in_indexed_kernel(dv):
         assert torch.equal(out.cpu(), ref)
 
 
+def test_fps_many_clouds_one_cta_each(dv):
+    """More clouds than clusters fit: the library falls back to one CTA per cloud (batched rounds)."""
+    g = torch.Generator().manual_seed(77)
+    xyz = torch.rand(40, 4096, 3, generator=g) * 6 - 3
+    start = torch.randint(0, 4096, (40,), generator=g)
+    ref = stages.farthest_point_sample(xyz[:3], 4096, start[:3])
+    out = dv.farthest_point_sample(xyz.to(DEV), 4096, start).cpu()
+    assert torch.equal(out[:3], ref)
+    assert torch.equal(out.sort(dim=1)[0], torch.arange(4096).expand(40, -1))
+
+
 def test_fps_plain_and_pruned_kernels_agree(dv, F):
     g = torch.Generator().manual_seed(3)
     xyz = (torch.randn(3, 3000, 3, generator=g) * 5).to(DEV)
