@@ -13,9 +13,11 @@
 //     largest second-best key, (3) pushes them, with coordinates, into the shared
 //     memory of all 8 CTAs (DSMEM stores), (4) cluster barrier, (5) every CTA
 //     resolves the same candidate list redundantly (so no second exchange is needed).
-// Exactness argument: identical to the batched rounds of fps.cu (candidates = ALL
-// points above S = the largest second-best key of any bucket; accepted in key order
-// while no accepted centroid can lower them).
+// Exactness argument: as for the batched rounds of fps.cu, generalised to FC_E exposed
+// keys per bucket: with S = the largest (FC_E+1)-th best key of any bucket, every point
+// whose key exceeds S is among the FC_E best of its bucket, so the exposed keys above S
+// are ALL the points above S; they are accepted in key order while no centroid accepted
+// in the same step can lower them.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -25,39 +27,51 @@ namespace cg = cooperative_groups;
 namespace dvcp {
 
 constexpr int FC_C = 8;         // CTAs per cluster = per cloud
-constexpr int FC_WARPS = 8;
+constexpr int FC_WARPS = 8;     // == FC_C: warp w pushes to CTA w
 constexpr int FC_THREADS = FC_WARPS * 32;
 constexpr int FC_MAXNBL = 64;   // buckets per CTA (16384 points / 32 / 8)
+constexpr int FC_E = 3;         // keys a bucket exposes per step (its FC_E best)
+constexpr int FC_CAP = 128;     // candidates resolved per step
+constexpr int FC_LCAP = 32;     // candidates one CTA pushes per step
+constexpr int FC_LBUF = FC_E * FC_MAXNBL;
 
 struct FcShared {
     // exchange area, double-buffered by step parity; written by the peers
-    unsigned long long r_key[2][FC_C][FC_MAXNBL];
-    float4 r_xyz[2][FC_C][FC_MAXNBL];
+    unsigned long long r_key[2][FC_C][FC_LCAP];
+    float4 r_xyz[2][FC_C][FC_LCAP];
     unsigned long long r_S[2][FC_C];
     unsigned r_cnt[2][FC_C];
-    // local
-    unsigned long long l_key[FC_MAXNBL];
-    float4 l_xyz[FC_MAXNBL];
-    unsigned long long c_key[FC_C * FC_MAXNBL];
-    float4 c_xyz[FC_C * FC_MAXNBL];
-    unsigned short c_top[32];
-    unsigned long long T;
-    float4 acc[32];
-    unsigned long long best[FC_MAXNBL], sec[FC_MAXNBL];
-    unsigned F[FC_MAXNBL];
+    // my exposed keys above my own threshold (and the 32 largest of them if there are more)
+    unsigned long long l_key[FC_LBUF];
+    float4 l_xyz[FC_LBUF];
+    unsigned long long l2_key[FC_LCAP];
+    float4 l2_xyz[FC_LCAP];
+    // the cluster's candidates: gathered, then in descending key order
+    unsigned long long c_key[FC_C * FC_LCAP];
+    float4 c_xyz[FC_C * FC_LCAP];
+    unsigned long long s_key[FC_CAP];
+    float4 s_xyz[FC_CAP];
+    unsigned K[FC_CAP][4], L[FC_CAP][4];   // row r, bit i: earlier candidate i lowers r / lowers r to a key <= T
+    float4 acc[FC_CAP];                    // centroids accepted in this step, in FPS order
+    unsigned long long top[FC_MAXNBL][FC_E + 1];   // per bucket: its FC_E + 1 largest keys, descending
+    unsigned F[FC_MAXNBL][4];              // per bucket: accepted centroids that can reach it
     float box[6][FC_MAXNBL];
+    unsigned long long T, l_S;
     unsigned l_cnt, n_cand, n_acc;
-    unsigned long long l_S;
 };
 
-__device__ __forceinline__ void fc_top2(unsigned hi0, unsigned lo0, unsigned long long &best, unsigned long long &sec) {
-    unsigned hi = hi0, lo = lo0;
-    warp_max_pair(hi, lo);
-    const bool mine = hi0 == hi && lo0 == lo;
-    unsigned h2 = mine ? 0u : hi0, l2 = mine ? 0u : lo0;
-    warp_max_pair(h2, l2);
-    best = ((unsigned long long)hi << 32) | lo;
-    sec = ((unsigned long long)h2 << 32) | l2;
+// the FC_E + 1 largest (dist bits, tie word) keys of the 32 points of one bucket
+__device__ __forceinline__ void fc_bucket_top(unsigned hi, unsigned lo, unsigned long long *top, int lane) {
+#pragma unroll
+    for (int e = 0; e <= FC_E; ++e) {
+        unsigned h = hi, l = lo;
+        warp_max_pair(h, l);
+        if (lane == 0) top[e] = ((unsigned long long)h << 32) | l;
+        if (hi == h && lo == l) {
+            hi = 0u;
+            lo = 0u;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 1)
@@ -81,21 +95,15 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     for (int jl = warp; jl < NBL; jl += FC_WARPS) {
         const int jg = jl * FC_C + rank, gp = jg * 32 + lane, p = jl * 32 + lane;
         const int id = __ldg(gi + gp);
-        const float x = __ldg(gx + gp), y = __ldg(gx + cap + gp), z = __ldg(gx + 2 * cap + gp);
-        s_x[p] = x;
-        s_y[p] = y;
-        s_z[p] = z;
+        s_x[p] = __ldg(gx + gp);
+        s_y[p] = __ldg(gx + cap + gp);
+        s_z[p] = __ldg(gx + 2 * cap + gp);
         const unsigned idu = id < 0 ? 0xffffu : (unsigned)id;
         s_id[p] = (unsigned short)idu;
         const float d0 = id < 0 ? 0.0f : 1e10f;
         s_d[p] = d0;
-        unsigned long long bk, sk;
-        fc_top2(__float_as_uint(d0), ((0xffffu - idu) << 16) | (unsigned)gp, bk, sk);
-        if (lane == 0) {
-            sh.best[jl] = bk;
-            sh.sec[jl] = sk;
-            sh.F[jl] = 0u;
-        }
+        fc_bucket_top(__float_as_uint(d0), ((0xffffu - idu) << 16) | (unsigned)gp, sh.top[jl], lane);
+        if (lane < 4) sh.F[jl][lane] = 0u;
         if (lane < 6) {
             const float4 b0 = __ldg(reinterpret_cast<const float4 *>(gbox + (int64_t)jg * 8));
             const float4 b1 = __ldg(reinterpret_cast<const float4 *>(gbox + (int64_t)jg * 8) + 1);
@@ -109,6 +117,7 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
         sh.acc[0] = make_float4(xyz.at(b, (int)startidx, 0), xyz.at(b, (int)startidx, 1), xyz.at(b, (int)startidx, 2), 0.f);
         sh.n_acc = 1u;
         sh.n_cand = 0u;
+        sh.l_cnt = 0u;
         if (rank == 0) {
             if (out64) out64[(int64_t)b * npoint] = startidx;
             if (out32) out32[(int64_t)b * npoint] = (int32_t)startidx;
@@ -128,84 +137,104 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                 const float ex = fmaxf(fmaxf(__fsub_rn(sh.box[0][jl], c.x), __fsub_rn(c.x, sh.box[3][jl])), 0.0f);
                 const float ey = fmaxf(fmaxf(__fsub_rn(sh.box[1][jl], c.y), __fsub_rn(c.y, sh.box[4][jl])), 0.0f);
                 const float ez = fmaxf(fmaxf(__fsub_rn(sh.box[2][jl], c.z), __fsub_rn(c.z, sh.box[5][jl])), 0.0f);
-                const float bestval = __uint_as_float((unsigned)(sh.best[jl] >> 32));
-                if (sq3_nofma(ex, ey, ez) < bestval) atomicOr(&sh.F[jl], 1u << a);
+                const float bestval = __uint_as_float((unsigned)(sh.top[jl][0] >> 32));
+                if (sq3_nofma(ex, ey, ez) < bestval) atomicOr(&sh.F[jl][a >> 5], 1u << (a & 31));
             }
         }
         __syncthreads();
-        // ---- (2) lower the distances of the reached buckets, refresh their two best keys ----
+        // ---- (2) lower the distances of the reached buckets, refresh their largest keys ----
         for (int jl = warp; jl < NBL; jl += FC_WARPS) {
-            unsigned F = sh.F[jl];
-            if (F) {
+            const uint4 Fw = *reinterpret_cast<const uint4 *>(sh.F[jl]);
+            if (Fw.x | Fw.y | Fw.z | Fw.w) {
                 const int p = jl * 32 + lane;
                 const float x = s_x[p], y = s_y[p], z = s_z[p];
                 float dk = s_d[p];
-                do {
-                    const int a = __ffs(F) - 1;
-                    F &= F - 1;
-                    const float4 c = sh.acc[a];
-                    const float d = sq3_nofma(__fsub_rn(x, c.x), __fsub_rn(y, c.y), __fsub_rn(z, c.z));
-                    dk = d < dk ? d : dk;
-                } while (F);
-                s_d[p] = dk;
-                unsigned long long bk, sk;
-                fc_top2(__float_as_uint(dk), ((0xffffu - (unsigned)s_id[p]) << 16) | (unsigned)((jl * FC_C + rank) * 32 + lane),
-                        bk, sk);
-                if (lane == 0) {
-                    sh.best[jl] = bk;
-                    sh.sec[jl] = sk;
-                    sh.F[jl] = 0u;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    unsigned F = w == 0 ? Fw.x : w == 1 ? Fw.y : w == 2 ? Fw.z : Fw.w;
+                    while (F) {
+                        const int a = w * 32 + __ffs(F) - 1;
+                        F &= F - 1;
+                        const float4 c = sh.acc[a];
+                        const float d = sq3_nofma(__fsub_rn(x, c.x), __fsub_rn(y, c.y), __fsub_rn(z, c.z));
+                        dk = d < dk ? d : dk;
+                    }
                 }
+                s_d[p] = dk;
+                fc_bucket_top(__float_as_uint(dk),
+                              ((0xffffu - (unsigned)s_id[p]) << 16) | (unsigned)((jl * FC_C + rank) * 32 + lane), sh.top[jl], lane);
+                if (lane < 4) sh.F[jl][lane] = 0u;
             }
         }
         produced += A;
         if (produced >= npoint) break;
         __syncthreads();
-        // ---- (3) my candidates: bucket maxima above my largest second-best key ----
-        if (warp == 0) {
+        // ---- (3) my candidates: exposed keys above S_c = my largest (FC_E+1)-th bucket key ----
+        unsigned long long Sc;
+        {
             unsigned shi = 0u, slo = 0u;
             for (int h = 0; h < H2; ++h) {
                 const int jl = h * 32 + lane;
-                const unsigned long long s = jl < NBL ? sh.sec[jl] : 0ull;
+                const unsigned long long s = jl < NBL ? sh.top[jl][FC_E] : 0ull;
                 const unsigned hi = (unsigned)(s >> 32), lo = (unsigned)s;
                 if (hi > shi || (hi == shi && lo > slo)) {
                     shi = hi;
                     slo = lo;
                 }
             }
-            warp_max_pair(shi, slo);
-            const unsigned long long S = ((unsigned long long)shi << 32) | slo;
-            unsigned cnt = 0u;
-            for (int h = 0; h < H2; ++h) {
-                const int jl = h * 32 + lane;
-                const unsigned long long key = jl < NBL ? sh.best[jl] : 0ull;
-                const bool isc = (key >> 32) != 0ull && key > S;
-                const unsigned m = __ballot_sync(0xffffffffu, isc);
+            warp_max_pair(shi, slo);   // every warp computes the same value
+            Sc = ((unsigned long long)shi << 32) | slo;
+        }
+        {
+            const int t = tid;   // FC_E * NBL <= 192 < FC_THREADS
+            const int jl = t % NBL, e = t / NBL;
+            const unsigned long long key = e < FC_E ? sh.top[jl][e] : 0ull;
+            const bool isc = (key >> 32) != 0ull && key > Sc;
+            const unsigned m = __ballot_sync(0xffffffffu, isc);
+            if (m) {
+                unsigned basev = 0u;
+                if (lane == 0) basev = atomicAdd(&sh.l_cnt, (unsigned)__popc(m));
+                basev = __shfl_sync(0xffffffffu, basev, 0);
                 if (isc) {
-                    const unsigned slot = cnt + __popc(m & ((1u << lane) - 1u));
+                    const unsigned slot = basev + __popc(m & ((1u << lane) - 1u));
                     const int p = jl * 32 + (int)(key & 31u);
                     sh.l_key[slot] = key;
                     sh.l_xyz[slot] = make_float4(s_x[p], s_y[p], s_z[p], 0.f);
                 }
-                cnt += __popc(m);
-            }
-            if (lane == 0) {
-                sh.l_cnt = cnt;
-                sh.l_S = S;
             }
         }
         __syncthreads();
+        unsigned lcnt = sh.l_cnt;
+        const unsigned long long *pk = sh.l_key;
+        const float4 *px = sh.l_xyz;
+        if (lcnt > FC_LCAP) {
+            // keep my 32 largest; the 33rd becomes my threshold (nothing above it is withheld)
+            for (int t = tid; t < (int)lcnt; t += FC_THREADS) {
+                const unsigned long long key = sh.l_key[t];
+                int rk = 0;
+                for (int u = 0; u < (int)lcnt; ++u) rk += sh.l_key[u] > key;
+                if (rk < FC_LCAP) {
+                    sh.l2_key[rk] = key;
+                    sh.l2_xyz[rk] = sh.l_xyz[t];
+                }
+                if (rk == FC_LCAP) sh.l_S = key;
+            }
+            __syncthreads();
+            Sc = sh.l_S;
+            lcnt = FC_LCAP;
+            pk = sh.l2_key;
+            px = sh.l2_xyz;
+        }
         // ---- (4) push them into every CTA of the cluster (warp w -> CTA w), one barrier ----
         {
             FcShared *peer = cluster.map_shared_rank(&sh, warp);
-            const unsigned cnt = sh.l_cnt;
-            for (unsigned e = lane; e < cnt; e += 32) {
-                peer->r_key[buf][rank][e] = sh.l_key[e];
-                peer->r_xyz[buf][rank][e] = sh.l_xyz[e];
+            if (lane < (int)lcnt) {
+                peer->r_key[buf][rank][lane] = pk[lane];
+                peer->r_xyz[buf][rank][lane] = px[lane];
             }
             if (lane == 0) {
-                peer->r_cnt[buf][rank] = cnt;
-                peer->r_S[buf][rank] = sh.l_S;
+                peer->r_cnt[buf][rank] = lcnt;
+                peer->r_S[buf][rank] = Sc;
             }
         }
         cluster.sync();
@@ -219,26 +248,30 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
         {
             const int c = warp;   // one warp per source CTA
             const unsigned cnt = sh.r_cnt[buf][c];
-            for (unsigned e = lane; e < cnt; e += 32) {
-                const unsigned long long key = sh.r_key[buf][c][e];
-                if (key > S) {
-                    const unsigned slot = atomicAdd(&sh.n_cand, 1u);
+            const unsigned long long key = lane < (int)cnt ? sh.r_key[buf][c][lane] : 0ull;
+            const bool keep = key > S;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                unsigned basev = 0u;
+                if (lane == 0) basev = atomicAdd(&sh.n_cand, (unsigned)__popc(m));
+                basev = __shfl_sync(0xffffffffu, basev, 0);
+                if (keep) {
+                    const unsigned slot = basev + __popc(m & ((1u << lane) - 1u));
                     sh.c_key[slot] = key;
-                    sh.c_xyz[slot] = sh.r_xyz[buf][c][e];
+                    sh.c_xyz[slot] = sh.r_xyz[buf][c][lane];
                 }
             }
         }
         __syncthreads();
         const int n = (int)sh.n_cand;
         if (n == 0) {
-            // every remaining distance is 0: the argmax stays the lowest index (pointnet2_utils.py:83),
-            // which is the largest best key anywhere. Every CTA knows only its own: take it from global order.
-            // All best keys have hi == 0 here, so the winner is the largest lo = lowest original index overall.
+            // every remaining distance is 0: the argmax stays the lowest index (pointnet2_utils.py:83).
+            // All keys have dist bits 0 now, so the winner is the largest tie word anywhere.
             if (warp == 0) {
                 unsigned hi = 0u, lo = 0u;
                 for (int h = 0; h < H2; ++h) {
                     const int jl = h * 32 + lane;
-                    const unsigned long long k2 = jl < NBL ? sh.best[jl] : 0ull;
+                    const unsigned long long k2 = jl < NBL ? sh.top[jl][0] : 0ull;
                     if ((unsigned)k2 > lo) lo = (unsigned)k2;
                 }
                 warp_max_pair(hi, lo);
@@ -249,9 +282,9 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             }
             cluster.sync();
             if (rank == 0) {
-                unsigned long long m = 0ull;
-                for (int c = 0; c < FC_C; ++c) m = sh.r_S[buf ^ 1][c] > m ? sh.r_S[buf ^ 1][c] : m;
-                const unsigned idx = 0xffffu - ((unsigned)m >> 16);
+                unsigned long long mx = 0ull;
+                for (int c = 0; c < FC_C; ++c) mx = sh.r_S[buf ^ 1][c] > mx ? sh.r_S[buf ^ 1][c] : mx;
+                const unsigned idx = 0xffffu - ((unsigned)mx >> 16);
                 for (int i = produced + tid; i < npoint; i += FC_THREADS) {
                     if (out64) out64[(int64_t)b * npoint + i] = idx;
                     if (out32) out32[(int64_t)b * npoint + i] = (int32_t)idx;
@@ -259,69 +292,126 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             }
             break;
         }
-        // more than 32 candidates (rare): keep the 32 largest, T = the 33rd
-        if (n > 32) {
-            for (int t = tid; t < n; t += FC_THREADS) {
-                const unsigned long long key = sh.c_key[t];
-                int rk = 0;
-                for (int u = 0; u < n; ++u) rk += sh.c_key[u] > key;
-                if (rk < 32) sh.c_top[rk] = (unsigned short)t;
-                if (rk == 32) sh.T = key;
+        // descending key order; beyond FC_CAP candidates the (FC_CAP+1)-th key is the threshold T
+        for (int t = tid; t < n; t += FC_THREADS) {
+            const unsigned long long key = sh.c_key[t];
+            int rk = 0;
+            for (int u = 0; u < n; ++u) rk += sh.c_key[u] > key;
+            if (rk < FC_CAP) {
+                sh.s_key[rk] = key;
+                sh.s_xyz[rk] = sh.c_xyz[t];
             }
-            __syncthreads();
+            if (rk == FC_CAP) sh.T = key;
         }
+        __syncthreads();
+        const int m = n < FC_CAP ? n : FC_CAP;
+        const unsigned long long T = n > FC_CAP ? sh.T : S;
+        // pair tests: thread (row r, half) covers the earlier candidates i of that half of the columns
+        {
+            const int r = tid & (FC_CAP - 1), half = tid >> 7;
+            if (r < m) {
+                const unsigned long long key = sh.s_key[r];
+                const float4 q = sh.s_xyz[r];
+                const unsigned klo = (unsigned)key;
+                const float dj = __uint_as_float((unsigned)(key >> 32));
+                unsigned k0 = 0u, k1 = 0u, l0 = 0u, l1 = 0u;
+                const int i0 = half * 64, i1 = r < i0 + 64 ? r : i0 + 64;
+                for (int i = i0; i < i1; ++i) {
+                    const float4 c = sh.s_xyz[i];
+                    const float d = sq3_nofma(__fsub_rn(q.x, c.x), __fsub_rn(q.y, c.y), __fsub_rn(q.z, c.z));
+                    const bool kill = d < dj;
+                    const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | klo;
+                    const unsigned kb = (unsigned)kill << (i & 31), lb2 = (unsigned)(kill && nk <= T) << (i & 31);
+                    if ((i - i0) < 32) {
+                        k0 |= kb;
+                        l0 |= lb2;
+                    } else {
+                        k1 |= kb;
+                        l1 |= lb2;
+                    }
+                }
+                sh.K[r][half * 2] = k0;
+                sh.K[r][half * 2 + 1] = k1;
+                sh.L[r][half * 2] = l0;
+                sh.L[r][half * 2 + 1] = l1;
+            }
+        }
+        __syncthreads();
         if (warp == 0) {
-            const int m = n < 32 ? n : 32;
-            const unsigned long long T = n > 32 ? sh.T : S;
-            const int src = lane < m ? (n > 32 ? (int)sh.c_top[lane] : lane) : 0;
-            const unsigned long long key = lane < m ? sh.c_key[src] : 0ull;
-            const float4 q = sh.c_xyz[src];
-            const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)(key & 0xffffffffu);
-            const float dj = __uint_as_float(khi);
-            unsigned H = 0u, K = 0u, L = 0u;
-            for (int i = 0; i < m; ++i) {
-                const float xi = __shfl_sync(0xffffffffu, q.x, i), yi = __shfl_sync(0xffffffffu, q.y, i),
-                            zi = __shfl_sync(0xffffffffu, q.z, i);
-                const unsigned hi_i = __shfl_sync(0xffffffffu, khi, i), lo_i = __shfl_sync(0xffffffffu, klo, i);
-                const bool before = hi_i > khi || (hi_i == khi && lo_i > klo);
-                const float d = sq3_nofma(__fsub_rn(q.x, xi), __fsub_rn(q.y, yi), __fsub_rn(q.z, zi));
-                const bool kill = before && d < dj;
-                const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | klo;
-                H |= (unsigned)before << i;
-                K |= (unsigned)kill << i;
-                L |= (unsigned)(kill && nk <= T) << i;
-            }
-            const unsigned validm = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
-            unsigned acc = 0u, rej = ~validm;
-            int state = lane < m ? 0 : 2;
-            while ((acc | rej) != 0xffffffffu) {
-                if (state == 0) {
-                    if (K & acc) state = 2;
-                    else if ((K & ~rej) == 0u) state = 1;
+            // lane l resolves rows l, l+32, l+64, l+96 (row r = word r/32, bit r%32 of the masks)
+            unsigned Kq[4][4], Lq[4][4];
+            int st[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q * 32 + lane;
+                st[q] = r < m ? 0 : 2;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    Kq[q][w] = (r < m && w <= q) ? sh.K[r][w] : 0u;
+                    Lq[q][w] = (r < m && w <= q) ? sh.L[r][w] : 0u;
                 }
-                acc = __ballot_sync(0xffffffffu, state == 1);
-                rej = __ballot_sync(0xffffffffu, state == 2);
             }
-            const bool stopper = lane < m && state == 2 && (L & acc) == 0u;
-            const unsigned stopm = __ballot_sync(0xffffffffu, stopper);
-            if (stopm) {
-                const int fs = __ffs(__ballot_sync(0xffffffffu, stopper && (H & stopm) == 0u)) - 1;
-                acc &= __shfl_sync(0xffffffffu, H, fs);
+            unsigned acc[4] = {0u, 0u, 0u, 0u}, rej[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rej[q] = __ballot_sync(0xffffffffu, st[q] == 2);
+            // first-come resolution in key order: accepted unless an ACCEPTED earlier candidate lowers me
+            while ((acc[0] | rej[0]) != 0xffffffffu || (acc[1] | rej[1]) != 0xffffffffu ||
+                   (acc[2] | rej[2]) != 0xffffffffu || (acc[3] | rej[3]) != 0xffffffffu) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (st[q] == 0) {
+                        unsigned kill = 0u, open = 0u;
+#pragma unroll
+                        for (int w = 0; w <= q; ++w) {
+                            kill |= Kq[q][w] & acc[w];
+                            open |= Kq[q][w] & ~rej[w];
+                        }
+                        if (kill) st[q] = 2;
+                        else if (!open) st[q] = 1;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[q] = __ballot_sync(0xffffffffu, st[q] == 1);
+                    rej[q] = __ballot_sync(0xffffffffu, st[q] == 2);
+                }
             }
-            const int rk = __popc(acc & H);
+            // a candidate lowered but still above T ends the step: keep what comes before the first such one
+            bool stopped = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned low = 0u;
+#pragma unroll
+                for (int w = 0; w <= q; ++w) low |= Lq[q][w] & acc[w];
+                const unsigned sm = __ballot_sync(0xffffffffu, q * 32 + lane < m && st[q] == 2 && low == 0u);
+                if (stopped) {
+                    acc[q] = 0u;
+                } else if (sm) {
+                    acc[q] &= (1u << (__ffs(sm) - 1)) - 1u;
+                    stopped = true;
+                }
+            }
             const int rem = npoint - produced;
-            if (((acc >> lane) & 1u) && rk < rem) {
-                sh.acc[rk] = make_float4(q.x, q.y, q.z, 0.f);
-                if (rank == 0) {
-                    const unsigned idx = 0xffffu - (klo >> 16);
-                    if (out64) out64[(int64_t)b * npoint + produced + rk] = idx;
-                    if (out32) out32[(int64_t)b * npoint + produced + rk] = (int32_t)idx;
+            int below = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q * 32 + lane;
+                const int rk = below + __popc(acc[q] & ((1u << lane) - 1u));
+                if (((acc[q] >> lane) & 1u) && rk < rem) {
+                    const float4 c = sh.s_xyz[r];
+                    sh.acc[rk] = c;
+                    if (rank == 0) {
+                        const unsigned idx = 0xffffu - ((unsigned)sh.s_key[r] >> 16);
+                        if (out64) out64[(int64_t)b * npoint + produced + rk] = idx;
+                        if (out32) out32[(int64_t)b * npoint + produced + rk] = (int32_t)idx;
+                    }
                 }
+                below += __popc(acc[q]);
             }
             if (lane == 0) {
-                const int na = __popc(acc);
-                sh.n_acc = (unsigned)(na < rem ? na : rem);
+                sh.n_acc = (unsigned)(below < rem ? below : rem);
                 sh.n_cand = 0u;
+                sh.l_cnt = 0u;
             }
         }
         __syncthreads();
