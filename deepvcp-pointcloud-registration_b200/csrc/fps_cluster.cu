@@ -26,14 +26,30 @@ namespace cg = cooperative_groups;
 
 namespace dvcp {
 
+#ifdef DVCP_FPS_TIMING
+__device__ long long g_fc_time[24];
+#define FC_TICK(slot)                                                   \
+    do {                                                                \
+        if (blockIdx.x == 0 && tid == 0) {                              \
+            const long long now__ = clock64();                          \
+            g_fc_time[slot] += now__ - t_last__;                        \
+            t_last__ = now__;                                           \
+        }                                                               \
+    } while (0)
+#else
+#define FC_TICK(slot)
+#endif
+
 constexpr int FC_C = 8;         // CTAs per cluster = per cloud
-constexpr int FC_WARPS = 8;     // == FC_C: warp w pushes to CTA w
+constexpr int FC_WARPS = 16;    // >= FC_C: warp w < FC_C pushes to CTA w
 constexpr int FC_THREADS = FC_WARPS * 32;
 constexpr int FC_MAXNBL = 64;   // buckets per CTA (16384 points / 32 / 8)
 constexpr int FC_E = 3;         // keys a bucket exposes per step (its FC_E best)
 constexpr int FC_CAP = 128;     // candidates resolved per step
 constexpr int FC_LCAP = 32;     // candidates one CTA pushes per step
 constexpr int FC_LBUF = FC_E * FC_MAXNBL;
+
+static_assert(FC_THREADS == 4 * FC_CAP && FC_WARPS >= FC_C && FC_E * FC_MAXNBL <= FC_THREADS, "thread mapping");
 
 struct FcShared {
     // exchange area, double-buffered by step parity; written by the peers
@@ -74,7 +90,7 @@ __device__ __forceinline__ void fc_bucket_top(unsigned hi, unsigned lo, unsigned
     }
 }
 
-__global__ void __launch_bounds__(FC_THREADS, 1)
+__global__ void __launch_bounds__(FC_THREADS, 2)
 fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const int64_t *__restrict__ start,
                    int64_t *__restrict__ out64, int32_t *__restrict__ out32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -126,22 +142,34 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     cluster.sync();   // peers exist and are initialised before anyone writes into them
 
     int produced = 0;
+#ifdef DVCP_FPS_TIMING
+    long long t_last__ = clock64();
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 24; ++i) g_fc_time[i] = 0;
+#endif
     for (int step = 0;; ++step) {
         const int buf = step & 1;
+        FC_TICK(15);
         // ---- (1) which of my buckets can each accepted centroid reach? ----
         const int A = (int)sh.n_acc;
-        for (int item = warp; item < A * H2; item += FC_WARPS) {
-            const int a = item / H2, jl = (item - a * H2) * 32 + lane;
-            if (jl < NBL) {
-                const float4 c = sh.acc[a];
-                const float ex = fmaxf(fmaxf(__fsub_rn(sh.box[0][jl], c.x), __fsub_rn(c.x, sh.box[3][jl])), 0.0f);
-                const float ey = fmaxf(fmaxf(__fsub_rn(sh.box[1][jl], c.y), __fsub_rn(c.y, sh.box[4][jl])), 0.0f);
-                const float ez = fmaxf(fmaxf(__fsub_rn(sh.box[2][jl], c.z), __fsub_rn(c.z, sh.box[5][jl])), 0.0f);
+        for (int h = 0; h < H2; ++h) {
+            const int jl = h * 32 + lane;
+            if (jl < NBL) {   // lane = bucket: its box stays in registers while the centroids stream by
+                const float nx = sh.box[0][jl], ny = sh.box[1][jl], nz = sh.box[2][jl];
+                const float xx = sh.box[3][jl], xy = sh.box[4][jl], xz = sh.box[5][jl];
                 const float bestval = __uint_as_float((unsigned)(sh.top[jl][0] >> 32));
-                if (sq3_nofma(ex, ey, ez) < bestval) atomicOr(&sh.F[jl][a >> 5], 1u << (a & 31));
+#pragma unroll 4
+                for (int a = warp; a < A; a += FC_WARPS) {
+                    const float4 c = sh.acc[a];
+                    const float ex = fmaxf(fmaxf(__fsub_rn(nx, c.x), __fsub_rn(c.x, xx)), 0.0f);
+                    const float ey = fmaxf(fmaxf(__fsub_rn(ny, c.y), __fsub_rn(c.y, xy)), 0.0f);
+                    const float ez = fmaxf(fmaxf(__fsub_rn(nz, c.z), __fsub_rn(c.z, xz)), 0.0f);
+                    if (sq3_nofma(ex, ey, ez) < bestval) atomicOr(&sh.F[jl][a >> 5], 1u << (a & 31));
+                }
             }
         }
+        FC_TICK(0);
         __syncthreads();
+        FC_TICK(1);
         // ---- (2) lower the distances of the reached buckets, refresh their largest keys ----
         for (int jl = warp; jl < NBL; jl += FC_WARPS) {
             const uint4 Fw = *reinterpret_cast<const uint4 *>(sh.F[jl]);
@@ -168,7 +196,9 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
         }
         produced += A;
         if (produced >= npoint) break;
+        FC_TICK(2);
         __syncthreads();
+        FC_TICK(3);
         // ---- (3) my candidates: exposed keys above S_c = my largest (FC_E+1)-th bucket key ----
         unsigned long long Sc;
         {
@@ -203,7 +233,9 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                 }
             }
         }
+        FC_TICK(4);
         __syncthreads();
+        FC_TICK(5);
         unsigned lcnt = sh.l_cnt;
         const unsigned long long *pk = sh.l_key;
         const float4 *px = sh.l_xyz;
@@ -226,7 +258,7 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             px = sh.l2_xyz;
         }
         // ---- (4) push them into every CTA of the cluster (warp w -> CTA w), one barrier ----
-        {
+        if (warp < FC_C) {
             FcShared *peer = cluster.map_shared_rank(&sh, warp);
             if (lane < (int)lcnt) {
                 peer->r_key[buf][rank][lane] = pk[lane];
@@ -237,7 +269,9 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                 peer->r_S[buf][rank] = Sc;
             }
         }
+        FC_TICK(6);
         cluster.sync();
+        FC_TICK(7);
         // ---- (5) every CTA resolves the same list: S, candidates above S ----
         unsigned long long S = 0ull;
 #pragma unroll
@@ -245,7 +279,7 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             const unsigned long long v = sh.r_S[buf][c];
             S = v > S ? v : S;
         }
-        {
+        if (warp < FC_C) {
             const int c = warp;   // one warp per source CTA
             const unsigned cnt = sh.r_cnt[buf][c];
             const unsigned long long key = lane < (int)cnt ? sh.r_key[buf][c][lane] : 0ull;
@@ -263,6 +297,7 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             }
         }
         __syncthreads();
+        FC_TICK(8);
         const int n = (int)sh.n_cand;
         if (n == 0) {
             // every remaining distance is 0: the argmax stays the lowest index (pointnet2_utils.py:83).
@@ -303,40 +338,39 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             }
             if (rk == FC_CAP) sh.T = key;
         }
+        FC_TICK(9);
         __syncthreads();
+        FC_TICK(10);
         const int m = n < FC_CAP ? n : FC_CAP;
+#ifdef DVCP_FPS_TIMING
+        if (blockIdx.x == 0 && tid == 0) { g_fc_time[16] += 1; g_fc_time[17] += n; g_fc_time[18] += A; g_fc_time[19] += sh.l_cnt; g_fc_time[20] += (n > FC_CAP); }
+#endif
         const unsigned long long T = n > FC_CAP ? sh.T : S;
-        // pair tests: thread (row r, half) covers the earlier candidates i of that half of the columns
+        // pair tests: thread (row r, quarter) covers the earlier candidates i of 32 columns = one mask word
         {
-            const int r = tid & (FC_CAP - 1), half = tid >> 7;
+            const int r = tid & (FC_CAP - 1), quarter = tid >> 7;
             if (r < m) {
                 const unsigned long long key = sh.s_key[r];
                 const float4 q = sh.s_xyz[r];
                 const unsigned klo = (unsigned)key;
                 const float dj = __uint_as_float((unsigned)(key >> 32));
-                unsigned k0 = 0u, k1 = 0u, l0 = 0u, l1 = 0u;
-                const int i0 = half * 64, i1 = r < i0 + 64 ? r : i0 + 64;
+                unsigned kw = 0u, lw = 0u;
+                const int i0 = quarter * 32, i1 = r < i0 + 32 ? r : i0 + 32;
                 for (int i = i0; i < i1; ++i) {
                     const float4 c = sh.s_xyz[i];
                     const float d = sq3_nofma(__fsub_rn(q.x, c.x), __fsub_rn(q.y, c.y), __fsub_rn(q.z, c.z));
                     const bool kill = d < dj;
                     const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | klo;
-                    const unsigned kb = (unsigned)kill << (i & 31), lb2 = (unsigned)(kill && nk <= T) << (i & 31);
-                    if ((i - i0) < 32) {
-                        k0 |= kb;
-                        l0 |= lb2;
-                    } else {
-                        k1 |= kb;
-                        l1 |= lb2;
-                    }
+                    kw |= (unsigned)kill << (i & 31);
+                    lw |= (unsigned)(kill && nk <= T) << (i & 31);
                 }
-                sh.K[r][half * 2] = k0;
-                sh.K[r][half * 2 + 1] = k1;
-                sh.L[r][half * 2] = l0;
-                sh.L[r][half * 2 + 1] = l1;
+                sh.K[r][quarter] = kw;
+                sh.L[r][quarter] = lw;
             }
         }
+        FC_TICK(11);
         __syncthreads();
+        FC_TICK(12);
         if (warp == 0) {
             // lane l resolves rows l, l+32, l+64, l+96 (row r = word r/32, bit r%32 of the masks)
             unsigned Kq[4][4], Lq[4][4];
@@ -414,7 +448,9 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                 sh.l_cnt = 0u;
             }
         }
+        FC_TICK(13);
         __syncthreads();
+        FC_TICK(14);
     }
     cluster.sync();   // nobody leaves while a peer may still address its shared memory
 }
@@ -445,3 +481,9 @@ int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, i
     DVCP_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel, as_cloud(xyz), index, N, npoint, start, out64, out32));
     return 0;
 }
+
+#ifdef DVCP_FPS_TIMING
+extern "C" __attribute__((visibility("default"))) int dvcp_debug_fps_timing(long long *host16) {
+    return (int)cudaMemcpyFromSymbol(host16, dvcp::g_fc_time, 24 * sizeof(long long));
+}
+#endif
