@@ -337,7 +337,7 @@ def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False):
     logits = torch.empty(M, C, dtype=torch.float32, device=dev) if want_logits else None
     check(lib().dvcp_cpg(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params, ptr(vcp),
                          ptr(logits), ptr(ws), nbytes, stream_ptr(dev)), "dvcp_cpg")
-    _count(5)
+    _count(1 if G <= 11 else 5)   # fused kernel up to 11^3, else cost + 3 convs + softmax
     return vcp, logits
 
 
