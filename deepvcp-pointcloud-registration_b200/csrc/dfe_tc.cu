@@ -11,15 +11,16 @@
 // 3xTF32 split (A = Ah + Al, B = Bh + Bl; Ah*Bh + Al*Bh + Ah*Bl, FP32 accumulate
 // in TMEM), which keeps FP32-level accuracy (error ~2^-21 relative).
 //
-// Roles in a CTA (5 warps), persistent over tiles:
-//   warps 0-3  build their candidate's 32 rows of A (gather the neighbours' feature
-//              rows, scale by the float64 distance weights, split hi/lo) straight
-//              into shared memory in the UMMA K-major core-matrix layout, then
-//              drain the PREVIOUS tile's accumulator: tcgen05.ld of their 32 TMEM
-//              lanes (= their candidate's 32 neighbours), butterfly max over the
-//              lanes (the max-pool over K), one coalesced 128-byte store;
-//   warp 4     allocates TMEM, waits for A, issues the 15 tcgen05.mma of a tile from
-//              one lane and commits to the mbarriers.
+// Roles in a CTA (17 warps, one persistent CTA per SM, 4 A stages + 4 TMEM accumulators):
+//   warps 0-3   epilogue: tcgen05.ld of their 32 TMEM lanes (= one candidate's 32
+//               neighbours), butterfly max over the lanes (the max-pool over K), one
+//               coalesced 128-byte store;
+//   warps 4-15  producers, 3 groups of 4 (group g builds tiles g, g+3, ...): gather the
+//               neighbours' feature rows into registers (next tile's indices are already
+//               in flight), scale by the float64 distance weights carried as float pairs,
+//               split hi/lo, store into shared memory in the UMMA K-major core-matrix layout;
+//   warp 16     allocates TMEM, waits for A, issues the 15 tcgen05.mma of a tile from
+//               one lane and commits to the mbarriers.
 // A is gathered (index-driven) and cannot be described by a TMA tensor map; the
 // operands reach the tensor core through shared-memory matrix descriptors.
 #include "common.cuh"
@@ -30,8 +31,14 @@ constexpr int TC_K = 40;                       // padded reduction length
 constexpr int TC_ROWS = 128;                   // rows per tile = 4 candidates x 32 neighbours
 constexpr int TC_A_BYTES = TC_ROWS * TC_K * 4;  // one A plane (hi or lo)
 constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one B plane
-constexpr int TC_STAGES = 2;
-constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_B_BYTES + 256;
+constexpr int TC_STAGES = 4;                   // shared-memory A stages == TMEM accumulators
+constexpr int TC_GROUPS = 3;                   // producer groups of 4 warps (one candidate per warp)
+constexpr int TC_EPI_WARPS = 4;                // warps 0-3: their TMEM lane quadrant = their warp index
+constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS - 1
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
+constexpr int TC_W_BYTES = TC_PROD_WARPS * 32 * 8;   // per producer warp: (hi, lo) distance weight of each feature
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_W_BYTES + 256;
 
 // byte offset of element (row r, column k) in the K-major, no-swizzle canonical layout:
 // 8x(16 B) core matrices; core (r/8, k/4) at ((r/8) * (K/4) + k/4) * 128 B.
@@ -80,7 +87,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                  : "memory");
 }
 
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__restrict__ tfeat,
                   const float *__restrict__ kdist, const int32_t *__restrict__ kidx, int N, int64_t total_cand,
                   int64_t Q, const float *__restrict__ Bhi, const float *__restrict__ Blo, int per_feature_weight,
@@ -88,9 +95,10 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sA = smem;                                      // [stage][hi|lo][TC_A_BYTES]
     unsigned char *sB = smem + TC_STAGES * 2 * TC_A_BYTES;         // [hi|lo][TC_B_BYTES]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_B_BYTES);
-    uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    float2 *sW = reinterpret_cast<float2 *>(sB + 2 * TC_B_BYTES);  // [producer warp][32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_B_BYTES + TC_W_BYTES);
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 3 * TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * TC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < TC_B_BYTES / 4; i += blockDim.x) {
@@ -98,17 +106,17 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         reinterpret_cast<float *>(sB + TC_B_BYTES)[i] = Blo[i];
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&full[s], 4);     // one arrive per producer warp
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full[s], 4);     // one arrive per warp of the producing group
             mbar_init(&empty[s], 1);    // tcgen05.commit
             mbar_init(&tfull[s], 1);    // tcgen05.commit
-            mbar_init(&tempty[s], 4);   // one arrive per epilogue warp
+            mbar_init(&tempty[s], TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(64u)
+                     "r"((unsigned)(32 * TC_STAGES))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -122,14 +130,14 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     const int64_t ntiles = (total_cand + 3) / 4;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         // ------------------------------ MMA issuer ------------------------------
         const uint32_t a_base = smem_u32(sA), b_hi = smem_u32(sB), b_lo = smem_u32(sB + TC_B_BYTES);
         for (int64_t i = 0; i < my_tiles; ++i) {
-            const int s = (int)(i & 1);
-            const unsigned ph = (unsigned)((i >> 1) & 1);
+            const int s = (int)(i % TC_STAGES);
+            const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
             mbar_wait(&full[s], ph);            // A(i) is in shared memory
-            mbar_wait(&tempty[s], ph ^ 1);      // accumulator s drained (tile i-2)
+            mbar_wait(&tempty[s], ph ^ 1);      // accumulator s drained (tile i - TC_STAGES)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t d = tmem_base + (uint32_t)s * 32u;   // 32 FP32 columns per accumulator
@@ -146,11 +154,11 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             }
             __syncwarp();
         }
-    } else {
-        // ---------------------- A producers + epilogue (warps 0-3) ----------------------
-        auto epilogue = [&](int64_t i) {
-            const int s = (int)(i & 1);
-            const unsigned ph = (unsigned)((i >> 1) & 1);
+    } else if (warp < TC_EPI_WARPS) {
+        // ------------------ epilogue: TMEM -> max over the 32 neighbours -> global ------------------
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i % TC_STAGES);
+            const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
             const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + warp;
             mbar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -185,43 +193,82 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 }
             }
             if (gq < total_cand) out[gq * 32 + lane] = y[0];
-        };
-
-        for (int64_t i = 0; i < my_tiles; ++i) {
-            const int s = (int)(i & 1);
-            const unsigned ph = (unsigned)((i >> 1) & 1);
-            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + warp;   // this warp's candidate
-            mbar_wait(&empty[s], ph ^ 1);   // MMAs of tile i-2 have finished reading stage s
-            unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_BYTES;
-            const int r = warp * 32 + lane;   // row of the tile = neighbour `lane` of candidate `warp`
+        }
+    } else {
+        // ---------------------- A producers: group g builds tiles g, g + TC_GROUPS, ... ----------------------
+        const int pw = warp - TC_EPI_WARPS, group = pw >> 2, cw = pw & 3;   // cw: candidate of the tile
+        float2 *myw = sW + pw * 32;
+        const int r = cw * 32 + lane;   // row of the tile = neighbour `lane` of candidate `cw`
+        // idx / dist of the first tile; the next tile's are fetched while this one is built
+        int64_t i = group;
+        int id_n = 0;
+        float dj_n = 0.f;
+        if (i < my_tiles) {
+            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + cw;
+            if (gq < total_cand) {
+                id_n = __ldg(kidx + gq * 32 + lane);
+                dj_n = __ldg(kdist + gq * 32 + lane);
+            }
+        }
+        for (; i < my_tiles; i += TC_GROUPS) {
+            const int s = (int)(i % TC_STAGES);
+            const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
+            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + cw;   // this warp's candidate
+            const int id = id_n;
+            const float djf = dj_n;
+            {
+                const int64_t i2 = i + TC_GROUPS;
+                const int64_t gq2 = (blockIdx.x + i2 * gridDim.x) * 4 + cw;
+                if (i2 < my_tiles && gq2 < total_cand) {
+                    id_n = __ldg(kidx + gq2 * 32 + lane);
+                    dj_n = __ldg(kdist + gq2 * 32 + lane);
+                }
+            }
             float x[TC_K];
 #pragma unroll
             for (int k = 0; k < TC_K; ++k) x[k] = 0.f;
             if (gq < total_cand) {
                 const int b = (int)(gq / Q);
-                const int id = __ldg(kidx + gq * 32 + lane);
-                const double dj = (double)__ldg(kdist + gq * 32 + lane);
+                // gather first (long latency), weights meanwhile
+                const float4 *fp = reinterpret_cast<const float4 *>(tfeat + ((int64_t)b * N + id) * 32);
+                float4 f[8];
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) f[k4] = __ldg(fp + k4);
+                const float px = txyz.at(b, id, 0), py = txyz.at(b, id, 1), pz = txyz.at(b, id, 2);
+                const float cx = __ldg(cand + gq * 3), cy = __ldg(cand + gq * 3 + 1), cz = __ldg(cand + gq * 3 + 2);
+                // w = dist / sum(dist) in float64 (get_cat_feat_tgt.py:57-58), carried as a float pair: the
+                // product with a float32 feature is then float32(double(f) * w) up to one rounding in 2^-48
+                const double dj = (double)djf;
                 double sum = dj;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 const double wl = dj / sum;
-                const float4 *fp = reinterpret_cast<const float4 *>(tfeat + ((int64_t)b * N + id) * 32);
+                const float whi = (float)wl, wlo = (float)(wl - (double)whi);
+                if (per_feature_weight) {
+                    __syncwarp();
+                    myw[lane] = make_float2(whi, wlo);
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int k4 = 0; k4 < 8; ++k4) {
-                    const float4 f = __ldg(fp + k4);
-                    const float fe[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int ch = 4 * k4 + e;
-                        const double w = per_feature_weight ? __shfl_sync(0xffffffffu, wl, ch) : wl;
-                        x[ch] = (float)((double)fe[e] * w);
+                    const float fe[4] = {f[k4].x, f[k4].y, f[k4].z, f[k4].w};
+                    float4 wa = make_float4(whi, wlo, whi, wlo), wb = wa;
+                    if (per_feature_weight) {
+                        wa = *reinterpret_cast<const float4 *>(myw + 4 * k4);       // (hi, lo) of channels 4k4, 4k4+1
+                        wb = *reinterpret_cast<const float4 *>(myw + 4 * k4 + 2);   // ... 4k4+2, 4k4+3
                     }
+                    x[4 * k4] = fmaf(fe[0], wa.x, fe[0] * wa.y);
+                    x[4 * k4 + 1] = fmaf(fe[1], wa.z, fe[1] * wa.w);
+                    x[4 * k4 + 2] = fmaf(fe[2], wb.x, fe[2] * wb.y);
+                    x[4 * k4 + 3] = fmaf(fe[3], wb.z, fe[3] * wb.w);
                 }
-                x[32] = txyz.at(b, id, 0) - __ldg(cand + gq * 3);
-                x[33] = txyz.at(b, id, 1) - __ldg(cand + gq * 3 + 1);
-                x[34] = txyz.at(b, id, 2) - __ldg(cand + gq * 3 + 2);
+                x[32] = px - cx;
+                x[33] = py - cy;
+                x[34] = pz - cz;
                 x[35] = 1.0f;   // bias column
             }
+            mbar_wait(&empty[s], ph ^ 1);   // MMAs of tile i - TC_STAGES have finished reading stage s
+            unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_BYTES;
 #pragma unroll
             for (int k4 = 0; k4 < TC_K / 4; ++k4) {
                 float4 h, l;
@@ -239,14 +286,14 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
-            if (i > 0) epilogue(i - 1);
         }
-        if (my_tiles > 0) epilogue(my_tiles - 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    if (warp == TC_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((unsigned)(32 * TC_STAGES))
+                     : "memory");
     }
 }
 
@@ -271,10 +318,10 @@ extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const fl
     const int64_t total = (int64_t)B * Q;
     const int64_t ntiles = (total + 3) / 4;
     DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    int64_t grid = 2 * DVCP_NUM_SMS;
+    int64_t grid = DVCP_NUM_SMS;   // persistent: one CTA per SM
     if (grid > ntiles) grid = ntiles;
     // one cloud stride for the whole batch: tgt_xyz is addressed with b = candidate / Q
-    dfe_tgt_tc_kernel<<<(unsigned)grid, 160, TC_SMEM, (cudaStream_t)stream>>>(
+    dfe_tgt_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
         cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, (quirks >> 1) & 1, out);
     DVCP_CHECK_LAUNCH();
     return 0;
