@@ -29,7 +29,9 @@ namespace dvcp {
 
 constexpr int TC_K = 40;                       // padded reduction length
 constexpr int TC_ROWS = 128;                   // rows per tile = 4 candidates x 32 neighbours
-constexpr int TC_A_BYTES = TC_ROWS * TC_K * 4;  // one A plane (hi or lo)
+constexpr int TC_A_SW_BYTES = TC_ROWS * 128;    // A plane, columns 0..31: 128-byte rows, SWIZZLE_128B (K-major)
+constexpr int TC_A_TAIL_BYTES = TC_ROWS * 32;   // A plane, columns 32..39: no-swizzle core matrices, K = 8
+constexpr int TC_A_BYTES = TC_A_SW_BYTES + TC_A_TAIL_BYTES;   // one A plane (hi or lo)
 constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one B plane
 constexpr int TC_STAGES = 4;                   // shared-memory A stages == TMEM accumulators
 constexpr int TC_GROUPS = 3;                   // producer groups of 4 warps (one candidate per warp)
@@ -38,7 +40,7 @@ constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS -
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
 constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
 constexpr int TC_W_BYTES = TC_PROD_WARPS * 32 * 8;   // per producer warp: (hi, lo) distance weight of each feature
-constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_W_BYTES + 256;
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_W_BYTES + 256 + 1024;   // + alignment slack
 
 // byte offset of element (row r, column k) in the K-major, no-swizzle canonical layout:
 // 8x(16 B) core matrices; core (r/8, k/4) at ((r/8) * (K/4) + k/4) * 128 B.
@@ -53,6 +55,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
            (1ull << 46);   // version 1 (Blackwell), base offset 0, SWIZZLE_NONE
+}
+// A, columns 0..31: rows of 128 bytes, the 16-byte chunk c of row r stored at chunk c ^ (r & 7)
+// (SWIZZLE_128B, 8-row atoms of 1024 bytes); a K = 8 step advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// A, columns 32..39: K = 8 in the no-swizzle layout (two core matrices per 8 rows)
+__host__ __device__ constexpr int tc_tail_off(int r, int k) {
+    return (r >> 3) * 256 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4;
+}
+__device__ __forceinline__ uint64_t make_desc_tail(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
+           (1ull << 46);
 }
 // kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 32
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
@@ -92,8 +108,9 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                   const float *__restrict__ kdist, const int32_t *__restrict__ kidx, int N, int64_t total_cand,
                   int64_t Q, const float *__restrict__ Bhi, const float *__restrict__ Blo, int per_feature_weight,
                   float *__restrict__ out) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sA = smem;                                      // [stage][hi|lo][TC_A_BYTES]
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
+    unsigned char *sA = smem;                                      // [stage][hi sw | lo sw | hi tail | lo tail]
     unsigned char *sB = smem + TC_STAGES * 2 * TC_A_BYTES;         // [hi|lo][TC_B_BYTES]
     float2 *sW = reinterpret_cast<float2 *>(sB + 2 * TC_B_BYTES);  // [producer warp][32]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_B_BYTES + TC_W_BYTES);
@@ -141,14 +158,19 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t d = tmem_base + (uint32_t)s * 32u;   // 32 FP32 columns per accumulator
-                const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_BYTES;
+                const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_SW_BYTES;
+                const uint32_t t_hi = a_hi + 2 * TC_A_SW_BYTES, t_lo = t_hi + TC_A_TAIL_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < TC_K / 8; ++ks) {
-                    const uint32_t ko = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks per MMA (K = 8)
-                    umma_tf32(d, make_desc(a_hi + ko), make_desc(b_hi + ko), ks > 0);
-                    umma_tf32(d, make_desc(a_lo + ko), make_desc(b_hi + ko), 1u);
-                    umma_tf32(d, make_desc(a_hi + ko), make_desc(b_lo + ko), 1u);
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ka = (uint32_t)ks * 32;          // 8 floats inside the 128-byte swizzled row
+                    const uint32_t kb = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks of B per MMA (K = 8)
+                    umma_tf32(d, make_desc_sw128(a_hi + ka), make_desc(b_hi + kb), ks > 0);
+                    umma_tf32(d, make_desc_sw128(a_lo + ka), make_desc(b_hi + kb), 1u);
+                    umma_tf32(d, make_desc_sw128(a_hi + ka), make_desc(b_lo + kb), 1u);
                 }
+                umma_tf32(d, make_desc_tail(t_hi), make_desc(b_hi + 4 * 2 * 128), 1u);
+                umma_tf32(d, make_desc_tail(t_lo), make_desc(b_hi + 4 * 2 * 128), 1u);
+                umma_tf32(d, make_desc_tail(t_hi), make_desc(b_lo + 4 * 2 * 128), 1u);
                 umma_commit(&empty[s]);   // shared-memory stage may be rewritten
                 umma_commit(&tfull[s]);   // accumulator is complete
             }
@@ -196,9 +218,24 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         }
     } else {
         // ---------------------- A producers: group g builds tiles g, g + TC_GROUPS, ... ----------------------
+        // A warp builds the 32 rows (neighbours) of one candidate. Feature rows are fetched
+        // cooperatively: lane = (rsub = lane >> 3, chunk = lane & 7) loads the 16-byte chunk of row
+        // 4g + rsub, so a quarter-warp reads one whole 128-byte line (4 wavefronts per LDG.128) and
+        // writes the 8 chunks of one swizzled 128-byte row (conflict-free STS.128).
         const int pw = warp - TC_EPI_WARPS, group = pw >> 2, cw = pw & 3;   // cw: candidate of the tile
         float2 *myw = sW + pw * 32;
-        const int r = cw * 32 + lane;   // row of the tile = neighbour `lane` of candidate `cw`
+        const int rsub = lane >> 3, chunk = lane & 7;
+        const bool xyz4 = txyz.ps == 4 && txyz.cs == 1 && txyz.bs % 4 == 0 && (reinterpret_cast<uintptr_t>(txyz.p) & 15) == 0;
+        // columns 36..39 are zero padding: written once per stage, never touched again
+        for (int s = group; s < TC_STAGES; s += TC_GROUPS) {
+            unsigned char *thi = sA + (size_t)s * 2 * TC_A_BYTES + 2 * TC_A_SW_BYTES, *tlo = thi + TC_A_TAIL_BYTES;
+            const int r0 = cw * 32 + lane;
+            *reinterpret_cast<float4 *>(thi + tc_tail_off(r0, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(tlo + tc_tail_off(r0, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // the zero columns of stage s are written by warps of different groups than the one that later
+        // arrives on full[s]: order them before any arrive with a barrier among the producer warps
+        asm volatile("bar.sync 1, %0;" ::"r"(TC_PROD_WARPS * 32) : "memory");
         // idx / dist of the first tile; the next tile's are fetched while this one is built
         int64_t i = group;
         int id_n = 0;
@@ -214,6 +251,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
             const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + cw;   // this warp's candidate
+            const bool live = gq < total_cand;
             const int id = id_n;
             const float djf = dj_n;
             {
@@ -224,64 +262,85 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                     dj_n = __ldg(kdist + gq2 * 32 + lane);
                 }
             }
-            float x[TC_K];
+            const int b = live ? (int)(gq / Q) : 0;
+            // ---- gather first (long latency) ----
+            float4 f[8];
+            const float *fbase = tfeat + (int64_t)b * N * 32;
 #pragma unroll
-            for (int k = 0; k < TC_K; ++k) x[k] = 0.f;
-            if (gq < total_cand) {
-                const int b = (int)(gq / Q);
-                // gather first (long latency), weights meanwhile
-                const float4 *fp = reinterpret_cast<const float4 *>(tfeat + ((int64_t)b * N + id) * 32);
-                float4 f[8];
-#pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) f[k4] = __ldg(fp + k4);
-                const float px = txyz.at(b, id, 0), py = txyz.at(b, id, 1), pz = txyz.at(b, id, 2);
-                const float cx = __ldg(cand + gq * 3), cy = __ldg(cand + gq * 3 + 1), cz = __ldg(cand + gq * 3 + 2);
-                // w = dist / sum(dist) in float64 (get_cat_feat_tgt.py:57-58), carried as a float pair: the
-                // product with a float32 feature is then float32(double(f) * w) up to one rounding in 2^-48
-                const double dj = (double)djf;
-                double sum = dj;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const double wl = dj / sum;
-                const float whi = (float)wl, wlo = (float)(wl - (double)whi);
-                if (per_feature_weight) {
-                    __syncwarp();
-                    myw[lane] = make_float2(whi, wlo);
-                    __syncwarp();
+            for (int g = 0; g < 8; ++g) {
+                const int rid = __shfl_sync(0xffffffffu, id, 4 * g + rsub);
+                f[g] = live ? __ldg(reinterpret_cast<const float4 *>(fbase + (int64_t)rid * 32 + chunk * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);   // my neighbour's local coordinates + bias column
+            if (live) {
+                float px, py, pz;
+                if (xyz4) {
+                    const float4 pp = __ldg(reinterpret_cast<const float4 *>(txyz.p + (int64_t)b * txyz.bs) + id);
+                    px = pp.x; py = pp.y; pz = pp.z;
+                } else {
+                    px = txyz.at(b, id, 0); py = txyz.at(b, id, 1); pz = txyz.at(b, id, 2);
                 }
+                loc = make_float4(px - __ldg(cand + gq * 3), py - __ldg(cand + gq * 3 + 1), pz - __ldg(cand + gq * 3 + 2), 1.0f);
+            }
+            // ---- w = dist / sum(dist) in float64 (get_cat_feat_tgt.py:57-58), carried as a float pair: the
+            //      product with a float32 feature is then float32(double(f) * w) up to one rounding in 2^-48 ----
+            const double dj = (double)djf;
+            double sum = dj;
 #pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    const float fe[4] = {f[k4].x, f[k4].y, f[k4].z, f[k4].w};
-                    float4 wa = make_float4(whi, wlo, whi, wlo), wb = wa;
-                    if (per_feature_weight) {
-                        wa = *reinterpret_cast<const float4 *>(myw + 4 * k4);       // (hi, lo) of channels 4k4, 4k4+1
-                        wb = *reinterpret_cast<const float4 *>(myw + 4 * k4 + 2);   // ... 4k4+2, 4k4+3
-                    }
-                    x[4 * k4] = fmaf(fe[0], wa.x, fe[0] * wa.y);
-                    x[4 * k4 + 1] = fmaf(fe[1], wa.z, fe[1] * wa.w);
-                    x[4 * k4 + 2] = fmaf(fe[2], wb.x, fe[2] * wb.y);
-                    x[4 * k4 + 3] = fmaf(fe[3], wb.z, fe[3] * wb.w);
-                }
-                x[32] = px - cx;
-                x[33] = py - cy;
-                x[34] = pz - cz;
-                x[35] = 1.0f;   // bias column
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const double wl = live ? dj / sum : 0.0;
+            const float whi = (float)wl, wlo = (float)(wl - (double)whi);
+            float4 wq[2];   // per-feature mode: (hi, lo) of my 4 channels 4 * chunk .. 4 * chunk + 3
+            if (per_feature_weight) {
+                __syncwarp();
+                myw[lane] = make_float2(whi, wlo);
+                __syncwarp();
+                wq[0] = *reinterpret_cast<const float4 *>(myw + chunk * 4);
+                wq[1] = *reinterpret_cast<const float4 *>(myw + chunk * 4 + 2);
             }
             mbar_wait(&empty[s], ph ^ 1);   // MMAs of tile i - TC_STAGES have finished reading stage s
-            unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_BYTES;
+            unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_SW_BYTES;
+            unsigned char *thi = ahi + 2 * TC_A_SW_BYTES, *tlo = thi + TC_A_TAIL_BYTES;
 #pragma unroll
-            for (int k4 = 0; k4 < TC_K / 4; ++k4) {
-                float4 h, l;
-                float *hp = &h.x, *lp = &l.x;
+            for (int g = 0; g < 8; ++g) {
+                const int row = 4 * g + rsub, trow = cw * 32 + row;
+                const float fe[4] = {f[g].x, f[g].y, f[g].z, f[g].w};
+                float wh[4], wlw[4];
+                if (per_feature_weight) {
+                    wh[0] = wq[0].x; wlw[0] = wq[0].y; wh[1] = wq[0].z; wlw[1] = wq[0].w;
+                    wh[2] = wq[1].x; wlw[2] = wq[1].y; wh[3] = wq[1].z; wlw[3] = wq[1].w;
+                } else {
+                    const float rhi = __shfl_sync(0xffffffffu, whi, row), rlo = __shfl_sync(0xffffffffu, wlo, row);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { wh[e] = rhi; wlw[e] = rlo; }
+                }
+                float4 hv, lv;
+                float *hp = &hv.x, *lp = &lv.x;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float v = x[4 * k4 + e];
-                    const float hv = __uint_as_float(__float_as_uint(v) & 0xffffe000u);   // exact TF32
-                    hp[e] = hv;
-                    lp[e] = v - hv;
+                    const float v = fmaf(fe[e], wh[e], fe[e] * wlw[e]);
+                    const float t = __uint_as_float(__float_as_uint(v) & 0xffffe000u);   // exact TF32
+                    hp[e] = t;
+                    lp[e] = v - t;
                 }
-                *reinterpret_cast<float4 *>(ahi + tc_off(r, 4 * k4)) = h;
-                *reinterpret_cast<float4 *>(alo + tc_off(r, 4 * k4)) = l;
+                const int off = trow * 128 + ((chunk ^ (trow & 7)) << 4);   // SWIZZLE_128B
+                *reinterpret_cast<float4 *>(ahi + off) = hv;
+                *reinterpret_cast<float4 *>(alo + off) = lv;
+            }
+            {
+                float4 hv, lv;
+                const float le[4] = {loc.x, loc.y, loc.z, loc.w};
+                float *hp = &hv.x, *lp = &lv.x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float t = __uint_as_float(__float_as_uint(le[e]) & 0xffffe000u);
+                    hp[e] = t;
+                    lp[e] = le[e] - t;
+                }
+                const int off = tc_tail_off(cw * 32 + lane, 0);
+                *reinterpret_cast<float4 *>(thi + off) = hv;
+                *reinterpret_cast<float4 *>(tlo + off) = lv;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();

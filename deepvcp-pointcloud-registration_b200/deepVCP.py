@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
-from ._lib import QUIRKS_REFERENCE, cloud_cm, require_cuda
+from ._lib import QUIRKS_REFERENCE, cloud_cm, cloud_pm, require_cuda
 from .cpg import cpg
 from .deep_feat_embedding import feat_embedding_layer
 from .deep_feat_extraction import feat_extraction_layer
@@ -126,7 +126,9 @@ class DeepVCP(nn.Module):
             mark("knn")
             if self.dfe_tensor_cores:
                 b_hi, b_lo = self.DFE.tc_operand()
-                tgt_dfe = F_.dfe_tgt_tc(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, b_hi, b_lo,
+                # point-major float4 copy of the target xyz: one 16-byte load per gathered neighbour
+                tgt4 = torch.nn.functional.pad(tgt[:, :3].transpose(1, 2), (0, 1)).contiguous()
+                tgt_dfe = F_.dfe_tgt_tc(cand.view(B, K * C, 3), cloud_pm(tgt4), tfeat, kd, ki32, B, N, b_hi, b_lo,
                                         self.quirks)                           # [B,K*C,32]
             else:
                 tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
