@@ -225,6 +225,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         const int pw = warp - TC_EPI_WARPS, group = pw >> 2, cw = pw & 3;   // cw: candidate of the tile
         float2 *myw = sW + pw * 32;
         const int rsub = lane >> 3, chunk = lane & 7;
+        const bool small = total_cand < (1ll << 31);
         const bool xyz4 = txyz.ps == 4 && txyz.cs == 1 && txyz.bs % 4 == 0 && (reinterpret_cast<uintptr_t>(txyz.p) & 15) == 0;
         // columns 36..39 are zero padding: written once per stage, never touched again
         for (int s = group; s < TC_STAGES; s += TC_GROUPS) {
@@ -262,7 +263,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                     dj_n = __ldg(kdist + gq2 * 32 + lane);
                 }
             }
-            const int b = live ? (int)(gq / Q) : 0;
+            const int b = live ? (small ? (int)((unsigned)gq / (unsigned)Q) : (int)(gq / Q)) : 0;
             // ---- gather first (long latency) ----
             float4 f[8];
             const float *fbase = tfeat + (int64_t)b * N * 32;
