@@ -24,7 +24,7 @@ class Cloud(ctypes.Structure):
 
 
 class CloudIndex(ctypes.Structure):
-    _fields_ = [("sorted_xyz", c_vp), ("sorted_idx", c_vp), ("bucket_box", c_vp), ("cap", c_i32)]
+    _fields_ = [("sorted_pt", c_vp), ("bucket_box", c_vp), ("cap", c_i32)]
 
 
 class MlpLayer(ctypes.Structure):
@@ -132,7 +132,7 @@ def cloud_cm(t: torch.Tensor) -> Cloud:
 
 
 NULL_CLOUD = Cloud(None, 0, 0, 0)
-NULL_INDEX = CloudIndex(None, None, None, 0)
+NULL_INDEX = CloudIndex(None, None, 0)
 
 
 def dfe_params(w1, b1, w2, b2, w3, b3) -> DfeParams:

@@ -276,8 +276,7 @@ sa_layer_pruned_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict_
     const float qn = sqrtf(qq) * 1.0001f;
     const int cap = index.cap, NB = cap / 32, T = NB / 32;
     const float *box = index.bucket_box + (int64_t)b * NB * 8;
-    const float *sxp = index.sorted_xyz + (int64_t)b * 3 * cap;
-    const int32_t *sip = index.sorted_idx + (int64_t)b * cap;
+    const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
     // can a box (min n*, max x*) hold a member?  lb <= r2 + E, E = rounding bound of the expanded form
     auto box_may_hold = [&](float nx, float ny, float nz, float xx, float xy, float xz) -> bool {
         const float ex = fmaxf(fmaxf(nx - qx, qx - xx), 0.f);
@@ -315,8 +314,9 @@ sa_layer_pruned_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict_
             const int j2 = sl * T + __ffs(fm) - 1;
             fm &= fm - 1;
             const int pos = j2 * 32 + lane;
-            const float px = __ldg(sxp + pos), py = __ldg(sxp + cap + pos), pz = __ldg(sxp + 2 * cap + pos);
-            const int id = __ldg(sip + pos);
+            const float4 P = __ldg(spt + pos);
+            const int id = __float_as_int(P.w);
+            const float px = id < 0 ? 0.f : P.x, py = id < 0 ? 0.f : P.y, pz = id < 0 ? 0.f : P.z;
             const float d2 = sqdist_expanded(qx, qy, qz, qq, px, py, pz, norm2_nofma(px, py, pz));
             const bool in = id >= 0 && !(d2 > r2);
             const unsigned m = __ballot_sync(0xffffffffu, in);
@@ -402,8 +402,7 @@ sa_layer_fast_kernel(Cloud xyz, Cloud feats, const int32_t *__restrict__ cidx, i
     unsigned char *mslot = sm.slot[warp];
     const int cap = index.cap, NB = cap / 32, T = NB / 32;
     const float *box = index.bucket_box + (int64_t)b * NB * 8;
-    const float *sxp = index.sorted_xyz + (int64_t)b * 3 * cap;
-    const int32_t *sip = index.sorted_idx + (int64_t)b * cap;
+    const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
     // union box of this lane's T Morton-consecutive buckets
     float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
     for (int t = 0; t < T; ++t) {
@@ -454,8 +453,9 @@ sa_layer_fast_kernel(Cloud xyz, Cloud feats, const int32_t *__restrict__ cidx, i
                 while (fm) {
                     const int pos = (sl * T + __ffs(fm) - 1) * 32 + lane;
                     fm &= fm - 1;
-                    const float px = __ldg(sxp + pos), py = __ldg(sxp + cap + pos), pz = __ldg(sxp + 2 * cap + pos);
-                    const int id = __ldg(sip + pos);
+                    const float4 P = __ldg(spt + pos);
+                    const int id = __float_as_int(P.w);
+                    const float px = id < 0 ? 0.f : P.x, py = id < 0 ? 0.f : P.y, pz = id < 0 ? 0.f : P.z;
                     const float d2 = sqdist_expanded(qx, qy, qz, qq, px, py, pz, norm2_nofma(px, py, pz));
                     const bool in = id >= 0 && !(d2 > r2);
                     const unsigned m = __ballot_sync(0xffffffffu, in);
@@ -750,10 +750,10 @@ extern "C" int dvcp_sa_layer(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const 
     const size_t smem = (4 * BQ_TILE + wfloats) * sizeof(float);
     DVCP_CUDA(cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int items = B * ((S + SA_WARPS - 1) / SA_WARPS);
-    const bool pruned = index.sorted_xyz != nullptr;
+    const bool pruned = index.sorted_pt != nullptr;
     const int grid = pruned ? (items < 2 * DVCP_NUM_SMS ? items : 2 * DVCP_NUM_SMS) : items;
     if (pruned) {
-        if (!index.sorted_idx || !index.bucket_box || index.cap < N || !overflow_ws) return DVCP_E_ARG;
+        if (!index.bucket_box || index.cap < N || !overflow_ws) return DVCP_E_ARG;
         const bool fast = n_layers == 3 && P.cout[0] == 16 && P.cout[1] == 16 && P.cout[2] == 32 && (D == 0 || D == 3);
         if (fast) {
             const int groups = (S + SAF_CPW - 1) / SAF_CPW;

@@ -202,14 +202,12 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
     }
     __syncthreads();
     // optional: publish the Morton-ordered cloud as a spatial index (ball query / KNN reuse it)
-    if (index.sorted_xyz) {
-        float *ox = index.sorted_xyz + (int64_t)b * 3 * CAP;
-        int32_t *oi = index.sorted_idx + (int64_t)b * CAP;
+    if (index.sorted_pt) {
+        float4 *op = reinterpret_cast<float4 *>(index.sorted_pt) + (int64_t)b * CAP;
         for (int i = tid; i < CAP; i += THREADS) {
-            ox[i] = sx[i];
-            ox[CAP + i] = sy[i];
-            ox[2 * CAP + i] = sz[i];
-            oi[i] = sidx[i] == 0xffffu ? -1 : (int32_t)sidx[i];
+            const bool used = sidx[i] != 0xffffu;
+            op[i] = used ? make_float4(sx[i], sy[i], sz[i], __int_as_float((int)sidx[i]))
+                         : make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
         }
     }
 
@@ -492,7 +490,7 @@ template <int WARPS, int BPW, bool BATCHED>
 static int launch_bucketed_impl(const dvcp_cloud_t &c, int B, int N, int npoint, const int64_t *start,
                            int64_t *o64, int32_t *o32, dvcp_cloud_index_t index, cudaStream_t st) {
     constexpr int CAP = WARPS * BPW * 32;
-    if (index.sorted_xyz && (index.cap != CAP || !index.sorted_idx || !index.bucket_box)) return DVCP_E_ARG;
+    if (index.sorted_pt && (index.cap != CAP || !index.bucket_box)) return DVCP_E_ARG;
     using Sort = cub::BlockRadixSort<unsigned, WARPS * 32, BPW, unsigned>;
     size_t data = (size_t)CAP * (3 * sizeof(float) + sizeof(unsigned short));
     size_t smem = data > sizeof(typename Sort::TempStorage) ? data : sizeof(typename Sort::TempStorage);
@@ -542,7 +540,7 @@ extern "C" int dvcp_index_capacity(int N) {
 
 extern "C" int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index_t index, dvcp_stream_t stream) {
     using namespace dvcp;
-    if (!xyz.base || !index.sorted_xyz || !index.sorted_idx || !index.bucket_box || B <= 0) return DVCP_E_ARG;
+    if (!xyz.base || !index.sorted_pt || !index.bucket_box || B <= 0) return DVCP_E_ARG;
     if (dvcp_index_capacity(N) == 0) return DVCP_E_UNSUPPORTED;
     return dispatch_bucketed(xyz, B, N, 0, nullptr, nullptr, nullptr, index, (cudaStream_t)stream);
 }
@@ -568,13 +566,13 @@ extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, c
     using namespace dvcp;
     if (!xyz.base || !start || (!out64 && !out32) || B <= 0 || N <= 0 || npoint <= 0) return DVCP_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == 0 && N <= 16384 && N >= 64 && index.sorted_xyz && !fps_sequential_mode() && fps_use_cluster(B, N)) {
+    if (dtype == 0 && N <= 16384 && N >= 64 && index.sorted_pt && !fps_sequential_mode() && fps_use_cluster(B, N)) {
         const int rc = dispatch_bucketed(xyz, B, N, 0, nullptr, nullptr, nullptr, index, st);   // index only
         if (rc != 0) return rc;
         return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, st);
     }
     if (dtype == 0 && N <= 16384 && N >= 64) return dispatch_bucketed(xyz, B, N, npoint, start, out64, out32, index, st);
-    if (index.sorted_xyz) return DVCP_E_UNSUPPORTED;
+    if (index.sorted_pt) return DVCP_E_UNSUPPORTED;
     if (N > 57344) return DVCP_E_UNSUPPORTED;
     size_t smem = (size_t)N * sizeof(float);
     if (dtype == 0) {

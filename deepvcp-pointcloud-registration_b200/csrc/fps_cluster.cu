@@ -105,15 +105,15 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     unsigned short *s_id = reinterpret_cast<unsigned short *>(s_d + NBL * 32);
 
     // ---- load my buckets (bucket jl of this CTA = global bucket jl * 8 + rank) ----
-    const float *gx = index.sorted_xyz + (int64_t)b * 3 * cap;
-    const int32_t *gi = index.sorted_idx + (int64_t)b * cap;
+    const float4 *gpt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
     const float *gbox = index.bucket_box + (int64_t)b * NB * 8;
     for (int jl = warp; jl < NBL; jl += FC_WARPS) {
         const int jg = jl * FC_C + rank, gp = jg * 32 + lane, p = jl * 32 + lane;
-        const int id = __ldg(gi + gp);
-        s_x[p] = __ldg(gx + gp);
-        s_y[p] = __ldg(gx + cap + gp);
-        s_z[p] = __ldg(gx + 2 * cap + gp);
+        const float4 P = __ldg(gpt + gp);
+        const int id = __float_as_int(P.w);
+        s_x[p] = id < 0 ? 0.f : P.x;
+        s_y[p] = id < 0 ? 0.f : P.y;
+        s_z[p] = id < 0 ? 0.f : P.z;
         const unsigned idu = id < 0 ? 0xffffu : (unsigned)id;
         s_id[p] = (unsigned short)idu;
         const float d0 = id < 0 ? 0.0f : 1e10f;

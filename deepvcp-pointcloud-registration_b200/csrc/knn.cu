@@ -209,17 +209,16 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     const unsigned long long INF = 0xffffffffffffffffull;
     const int cap = index.cap;
     const float *box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
-    const float *sxp = index.sorted_xyz + (int64_t)b * 3 * cap;
-    const int32_t *sip = index.sorted_idx + (int64_t)b * cap;
+    const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
     unsigned long long *buf = s_buf[warp];
     const Box6 sb = load_super_box(box, T, lane);
     const int64_t nchains = (Q + chain - 1) / chain;
 
     // key of point at sorted slot `pos` for query (qx,qy,qz): bits(d2) << 32 | id << 16 | pos
     auto point_key = [&](int pos, float qx, float qy, float qz, float &d2) -> unsigned long long {
-        const float px = __ldg(sxp + pos), py = __ldg(sxp + cap + pos), pz = __ldg(sxp + 2 * cap + pos);
-        const int id = __ldg(sip + pos);
-        d2 = sqdist_direct(px - qx, py - qy, pz - qz);
+        const float4 P = __ldg(spt + pos);   // unused slots hold +inf coordinates and id -1
+        const int id = __float_as_int(P.w);
+        d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
         return id >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned)id << 16) | (unsigned)pos) : INF;
     };
 
@@ -297,13 +296,18 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
                 while (bm) {
                     const int j = sl * T + __ffs(bm) - 1;
                     bm &= bm - 1;
-                    float d2;
-                    const unsigned long long key = point_key(j * 32 + lane, qx, qy, qz, d2);
-                    const bool qual = key != INF && d2 <= thr;
+                    const int pos = j * 32 + lane;
+                    const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never within thr
+                    const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+                    const bool qual = d2 <= thr;
                     const unsigned m = __ballot_sync(0xffffffffu, qual);
-                    const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                    if (qual && slot < KNI_BUF) buf[slot] = key;
-                    cnt += __popc(m);
+                    if (m) {
+                        const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                        if (qual && slot < KNI_BUF)
+                            buf[slot] = ((unsigned long long)__float_as_uint(d2) << 32) |
+                                        ((unsigned)__float_as_int(P.w) << 16) | (unsigned)pos;
+                        cnt += __popc(m);
+                    }
                 }
             }
             __syncwarp();
@@ -399,7 +403,7 @@ extern "C" int dvcp_candidates(const double *centres, int64_t M, double r, doubl
 extern "C" int dvcp_knn_indexed(dvcp_cloud_index_t index, const float *query, int B, int N, int64_t Q, int K,
                                 int chain, int zline, float *dist, int64_t *idx64, int32_t *idx32,
                                 dvcp_stream_t stream) {
-    if (!index.sorted_xyz || !index.sorted_idx || !index.bucket_box || !query || !dist || (!idx64 && !idx32) ||
+    if (!index.sorted_pt || !index.bucket_box || !query || !dist || (!idx64 && !idx32) ||
         B <= 0 || N <= 0 || Q <= 0 || chain < 1)
         return DVCP_E_ARG;
     if (zline < 1 || zline > chain) zline = chain;

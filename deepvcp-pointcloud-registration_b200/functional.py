@@ -55,15 +55,13 @@ class SpatialIndex:
         self.cap = lib().dvcp_index_capacity(N)
         if self.cap == 0:
             raise RuntimeError("clouds of %d points cannot be indexed (64..16384)" % N)
-        self.sorted_xyz = torch.empty(B, 3, self.cap, dtype=torch.float32, device=device)
-        self.sorted_idx = torch.empty(B, self.cap, dtype=torch.int32, device=device)
+        self.sorted_pt = torch.empty(B, self.cap, 4, dtype=torch.float32, device=device)   # x, y, z, index bits
         self.bucket_box = torch.empty(B, self.cap // 32, 8, dtype=torch.float32, device=device)
         self.B = B
 
     def c(self, lo=0):
         """ctypes view starting at batch item `lo`."""
-        return CloudIndex(self.sorted_xyz[lo:].data_ptr(), self.sorted_idx[lo:].data_ptr(),
-                          self.bucket_box[lo:].data_ptr(), self.cap)
+        return CloudIndex(self.sorted_pt[lo:].data_ptr(), self.bucket_box[lo:].data_ptr(), self.cap)
 
     @staticmethod
     def indexable(N, dtype=torch.float32):

@@ -68,10 +68,10 @@ typedef struct {
  * anyway); consumed by the pruned ball-query / SA / KNN kernels. Pruning never
  * changes results: members are always decided by the exact arithmetic. */
 typedef struct {
-    float *sorted_xyz;   /* [B, 3, cap]  x[], y[], z[] in Morton order; unused slots 0   */
-    int32_t *sorted_idx; /* [B, cap]     original index of each slot; -1 = unused slot   */
-    float *bucket_box;   /* [B, cap/32, 8] minx,miny,minz,maxx,maxy,maxz,count,0          */
-    int cap;             /* dvcp_index_capacity(N)                                        */
+    float *sorted_pt;    /* [B, cap, 4]  x, y, z, original index (int32 bits) in Morton order;
+                            unused slots +inf, +inf, +inf, -1: one 16-byte load per point       */
+    float *bucket_box;   /* [B, cap/32, 8] minx,miny,minz,maxx,maxy,maxz,count,0                */
+    int cap;             /* dvcp_index_capacity(N)                                              */
 } dvcp_cloud_index_t;
 
 DVCP_API int dvcp_abi_version(void);

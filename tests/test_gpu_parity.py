@@ -328,10 +328,12 @@ def test_spatial_index_is_a_permutation_with_tight_boxes(F):
     n = 5000
     pts = lattice_cloud(n, 3).to(DEV)
     index = F.build_index(lib.cloud_pm(pts), pts.device, 1, n)
-    sid = index.sorted_idx[0].cpu()
+    spt = index.sorted_pt[0].cpu()                        # [cap, 4]: x, y, z, index bits
+    sid = spt[:, 3].contiguous().view(torch.int32)
     valid = sid >= 0
     assert int(valid.sum()) == n and torch.equal(sid[valid].sort()[0], torch.arange(n, dtype=torch.int32))
-    sxyz = index.sorted_xyz[0].cpu()                      # [3, cap]
+    assert bool(torch.isinf(spt[~valid, :3]).all())       # unused slots are unreachable
+    sxyz = spt[:, :3].T                                   # [3, cap]
     assert torch.equal(sxyz[:, valid].T, pts[0].cpu()[sid[valid].long()])
     box = index.bucket_box[0].cpu()
     for j in (0, 7, index.cap // 32 - 1):
