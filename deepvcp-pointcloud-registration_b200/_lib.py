@@ -44,12 +44,14 @@ SIGNATURES = {
     "dvcp_abi_version": (c_i32, []),
     "dvcp_error_string": (ctypes.c_char_p, [c_i32]),
     "dvcp_fps": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_vp]),
+    "dvcp_fps_indexed": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_vp]),
     "dvcp_index_capacity": (c_i32, [c_i32]),
     "dvcp_build_index": (c_i32, [Cloud, c_i32, c_i32, CloudIndex, c_vp]),
     "dvcp_fps_plain": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_square_distance": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_ball_query": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp]),
     "dvcp_index_points": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp]),
+    "dvcp_index_points_i32": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "dvcp_sa_layer": (c_i32, [Cloud, Cloud, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32,
                               ctypes.POINTER(MlpLayer), c_i32, CloudIndex, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_weighting_scores": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

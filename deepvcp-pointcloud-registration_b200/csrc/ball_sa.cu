@@ -612,6 +612,20 @@ __global__ void index_points_kernel(const float *__restrict__ pts, const int64_t
     }
 }
 
+__global__ void index_points_i32_kernel(const float *__restrict__ pts, const int32_t *__restrict__ idx, int N,
+                                        int C4, int64_t M, float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int64_t total = M * C4;   // float4 elements
+    const float4 *src = reinterpret_cast<const float4 *>(pts) + (int64_t)b * N * C4;
+    float4 *dst = reinterpret_cast<float4 *>(out) + (int64_t)b * total;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / C4;
+        const int c = (int)(i - m * C4);
+        dst[i] = __ldg(src + (int64_t)__ldg(idx + (int64_t)b * M + m) * C4 + c);
+    }
+}
+
 // ---------------------------------------------------- weighting MLP ----------
 // One thread per point: 32 -> 16 (ReLU) -> 8 (ReLU) -> 1 (Softplus, beta 1,
 // threshold 20 as torch.nn.Softplus). Weights staged in shared memory.
@@ -806,6 +820,18 @@ extern "C" int dvcp_index_points(const float *points, const int64_t *idx, int B,
     int64_t gx = (total + 255) / 256; if (gx > 148 * 16) gx = 148 * 16;
     dim3 grid((unsigned)gx, B);
     index_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, idx, N, C, M, out);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dvcp_index_points_i32(const float *points, const int32_t *idx, int B, int N, int C, int64_t M,
+                                     float *out, dvcp_stream_t stream) {
+    if (!points || !idx || !out || B <= 0 || N <= 0 || C <= 0 || M <= 0) return DVCP_E_ARG;
+    if (B > 65535 || C % 4 != 0) return DVCP_E_UNSUPPORTED;
+    const int64_t total = M * (C / 4);
+    int64_t gx = (total + 255) / 256; if (gx > 148 * 16) gx = 148 * 16;
+    dim3 grid((unsigned)gx, B);
+    index_points_i32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, idx, N, C / 4, M, out);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

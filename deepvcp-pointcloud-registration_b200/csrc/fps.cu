@@ -592,6 +592,21 @@ extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, c
     return 0;
 }
 
+extern "C" int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
+                                int32_t *out32, dvcp_cloud_index_t index, dvcp_stream_t stream) {
+    using namespace dvcp;
+    if (!xyz.base || !start || (!out64 && !out32) || B <= 0 || N <= 0 || npoint <= 0 || !index.sorted_pt ||
+        !index.bucket_box)
+        return DVCP_E_ARG;
+    if (index.cap != dvcp_index_capacity(N) || index.cap == 0) return DVCP_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!fps_sequential_mode() && fps_use_cluster(B, N))
+        return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, st);
+    // one CTA per cloud: that kernel sorts the cloud itself; it must not rewrite an index others are reading
+    dvcp_cloud_index_t none = {nullptr, nullptr, 0};
+    return dispatch_bucketed(xyz, B, N, npoint, start, out64, out32, none, st);
+}
+
 // Test hook: force the plain kernel for float32 clouds (parity of the two paths).
 extern "C" int dvcp_fps_plain(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start,
                               int64_t *out64, dvcp_stream_t stream) {

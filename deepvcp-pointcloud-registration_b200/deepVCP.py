@@ -47,6 +47,17 @@ class DeepVCP(nn.Module):
         self.profile = False   # record a CUDA event after every stage (bench.py reads them)
         self._events = None
 
+    def _side_stream(self, dev):
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev, priority=-1)
+        return self._side
+
+    def _identity(self, B, N, dev):
+        t = getattr(self, "_ident", None)
+        if t is None or t.shape != (B, N) or t.device != dev:
+            self._ident = torch.arange(N, dtype=torch.int32, device=dev).repeat(B, 1).contiguous()
+        return self._ident
+
     def draw_starts(self, B, N):
         """The three FPS start draws of one forward in the reference's order:
         FE(src) -> key-point grouping -> FE(tgt) (deepVCP.py:29,54,72)."""
@@ -94,14 +105,39 @@ class DeepVCP(nn.Module):
             # launch (2B independent clouds); features come out in FPS order
             both = torch.cat([src, tgt], dim=0)
             st2 = torch.cat([torch.as_tensor(starts[0]).reshape(-1), torch.as_tensor(starts[2]).reshape(-1)])
-            index = F_.SpatialIndex(2 * B, N, dev) if F_.SpatialIndex.indexable(N) else None
-            _, fps2 = F_.fps(cloud_cm(both), dev, both.dtype, 2 * B, N, S, st2, want64=False, want32=True,
-                             index=index)
-            mark("fps")
             feat_cloud = cloud_cm(both[:, 3:, :]) if D else None
-            _, feat2 = F_.sa_layer(cloud_cm(both), feat_cloud, D, fps2, 2 * B, N, S, sa.radius, sa.nsample, mlp,
-                                   dev, want_xyz=False, index=index)
-            mark("sa_layer")
+            if F_.SpatialIndex.indexable(N) and N > 2048 and 2 * S >= N:
+                # FPS is a chain of dependent selections that leaves most of the GPU idle, and the SA
+                # features of a point do not depend on its FPS rank: build the index, then run the SA
+                # layer over the points in their ORIGINAL order on a side stream beside the sampling,
+                # and put the rows into FPS order afterwards (feat_fps[s] = feat_orig[fps[s]]).
+                index = F_.build_index(cloud_cm(both), dev, 2 * B, N)
+                main = torch.cuda.current_stream(dev)
+                ev_index = torch.cuda.Event()
+                ev_index.record(main)
+                # the sampling goes to a HIGH-priority stream and is enqueued first: its clusters of 8
+                # co-scheduled CTAs must get their SMs before the SA layer's many small CTAs fill the GPU
+                hp = self._side_stream(dev)
+                with torch.cuda.stream(hp):
+                    hp.wait_event(ev_index)
+                    _, fps2 = F_.fps_indexed(cloud_cm(both), dev, 2 * B, N, S, st2, index)
+                    ev_fps = torch.cuda.Event()
+                    ev_fps.record(hp)
+                _, feat_orig = F_.sa_layer(cloud_cm(both), feat_cloud, D, self._identity(2 * B, N, dev), 2 * B, N, N,
+                                           sa.radius, sa.nsample, mlp, dev, want_xyz=False, index=index)
+                main.wait_event(ev_fps)
+                fps2.record_stream(main)
+                mark("fps")
+                feat2 = F_.gather_rows(feat_orig, fps2)
+                mark("sa_layer")
+            else:
+                index = F_.SpatialIndex(2 * B, N, dev) if F_.SpatialIndex.indexable(N) else None
+                _, fps2 = F_.fps(cloud_cm(both), dev, both.dtype, 2 * B, N, S, st2, want64=False, want32=True,
+                                 index=index)
+                mark("fps")
+                _, feat2 = F_.sa_layer(cloud_cm(both), feat_cloud, D, fps2, 2 * B, N, S, sa.radius, sa.nsample, mlp,
+                                       dev, want_xyz=False, index=index)
+                mark("sa_layer")
             sfps, tfps = fps2[:B], fps2[B:]
             sfeat, tfeat = feat2[:B], feat2[B:]
             # key-point selection

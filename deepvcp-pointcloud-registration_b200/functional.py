@@ -81,6 +81,29 @@ def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want3
     return o64, o32
 
 
+def fps_indexed(xyz_cloud: Cloud, device, B, N, npoint, start, index, want64=False, want32=True):
+    """FPS of float32 clouds whose spatial index is already built (the index is only read)."""
+    start = _starts_to_device(start, B, device)
+    o64 = torch.empty(B, npoint, dtype=torch.int64, device=device) if want64 else None
+    o32 = torch.empty(B, npoint, dtype=torch.int32, device=device) if want32 else None
+    check(lib().dvcp_fps_indexed(xyz_cloud, B, N, npoint, ptr(start), ptr(o64), ptr(o32), index.c(),
+                                 stream_ptr(device)), "dvcp_fps_indexed")
+    _count(1)
+    return o64, o32
+
+
+def gather_rows(points, idx32):
+    """points [B,N,C] float32 (C % 4 == 0), idx32 [B,M] int32 -> [B,M,C]."""
+    require_cuda(points, idx32)
+    B, N, C = points.shape
+    M = idx32.shape[1]
+    out = torch.empty(B, M, C, dtype=torch.float32, device=points.device)
+    check(lib().dvcp_index_points_i32(ptr(_f32c(points)), ptr(idx32.contiguous()), B, N, C, M, ptr(out),
+                                      stream_ptr(points.device)), "dvcp_index_points_i32")
+    _count(1)
+    return out
+
+
 def build_index(xyz_cloud: Cloud, device, B, N):
     index = SpatialIndex(B, N, device)
     check(lib().dvcp_build_index(xyz_cloud, B, N, index.c(), stream_ptr(device)), "dvcp_build_index")

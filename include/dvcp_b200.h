@@ -85,6 +85,12 @@ DVCP_API const char *dvcp_error_string(int code);
 DVCP_API int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, const int64_t *start,
              int64_t *out64, int32_t *out32, dvcp_cloud_index_t index_out, dvcp_stream_t stream);
 
+/* Same as dvcp_fps for float32 clouds whose spatial index is ALREADY built (dvcp_build_index on
+ * the same stream or ordered before this call): the index is consumed, not rewritten, so other
+ * kernels may read it concurrently (DeepVCP.forward runs the SA layer beside the sampling). */
+DVCP_API int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
+                     int32_t *out32, dvcp_cloud_index_t index, dvcp_stream_t stream);
+
 /* Capacity (slots) of the spatial index of an N-point cloud; 0 = N not indexable. */
 DVCP_API int dvcp_index_capacity(int N);
 DVCP_API int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index_t index_out, dvcp_stream_t stream);
@@ -110,6 +116,10 @@ DVCP_API int dvcp_ball_query(dvcp_cloud_t xyz, dvcp_cloud_t new_xyz, int B, int 
  * points [B,N,C] contiguous float32, idx [B,M] int64 -> out [B,M,C]. */
 DVCP_API int dvcp_index_points(const float *points, const int64_t *idx, int B, int N, int C, int64_t M,
                       float *out, dvcp_stream_t stream);
+
+/* index_points with int32 indices (the FPS order as the kernels keep it): out[b,m,:] = points[b,idx[b,m],:]. */
+DVCP_API int dvcp_index_points_i32(const float *points, const int32_t *idx, int B, int N, int C, int64_t M,
+                          float *out, dvcp_stream_t stream);
 
 /* ---- a5+a6  PointNetSetAbstraction.forward (group_all=False), eval mode
  *             pointnet2_utils.py:110-138,176-202
