@@ -147,14 +147,6 @@ def run_ours(args):
         R2, t2 = dv.pose_from_forward(kp, vcp, d_R, d_t)
         return dv.sharding.pack_poses(R2, t2)
 
-    def step_e2e():
-        s_, t_, R_, tt_ = (x.to(dev, non_blocking=True) for x in (h_src, h_tgt, h_R, h_t))
-        kp, vcp = model(s_, t_, R_, t_init, starts=starts)
-        R2, t2 = dv.pose_from_forward(kp, vcp, R_, tt_)
-        h_pose.copy_(dv.sharding.pack_poses(R2, t2), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return h_pose
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -164,40 +156,62 @@ def run_ours(args):
         poses = step_device()
     torch.cuda.synchronize(dev)
 
-    # ---- timed region: K steps, device time, per-stage events, clocks sampled ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # ---- per-stage device times: a few UNPIPELINED steps with an event after every stage ----
     model.profile = True
-    stage_ms = {}
-    launches0 = F_.LAUNCHES
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    per_step_events = []
-    for a, b in ev:
-        flush.fill_(1)                                                     # L2 flush between timed iterations
+    stage_ms, lat_ms, prof_steps = {}, [], 3
+    for _ in range(prof_steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         poses = step_device()
         b.record()
-        per_step_events.append(model._events)
-    barrier()
-    launches = F_.LAUNCHES - launches0
-    model.profile = False
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
-    for evs in per_step_events:
+        torch.cuda.synchronize(dev)
+        lat_ms.append(a.elapsed_time(b))
+        evs = model._events
         for (_, e0), (name, e1) in zip(evs, evs[1:]):
             stage_ms[name] = stage_ms.get(name, 0.0) + e0.elapsed_time(e1)
+    model.profile = False
+    latency_ms = sum(lat_ms) / len(lat_ms)
+
+    # ---- timed region: K steps through the streamed API (batch i+1's sampling overlaps batch i's dense
+    #      stages; --depth 1 = strictly one batch at a time), device time, clocks sampled ----
+    pipe = dv.StreamedRegistration(model, depth=args.depth)
+    for _ in range(2):
+        pipe.submit(d_src, d_tgt, d_R, d_R, d_t, starts=starts)
+    pipe.collect()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = F_.LAUNCHES
+    barrier()
+    cur = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for _ in range(args.steps):
+        flush.fill_(1)                                                     # L2 flush between timed iterations
+        pipe.submit(d_src, d_tgt, d_R, d_R, d_t, starts=starts)
+    for st in pipe.streams:
+        cur.wait_stream(st)
+    e1.record(cur)
+    poses = pipe.collect()[-1]
+    barrier()
+    launches = F_.LAUNCHES - launches0
+    ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e leg: host buffers in, poses out, wall clock around synchronised steps ----
-    for _ in range(2):
-        step_e2e()
+    # ---- e2e leg: pinned host buffers in, poses back in pinned host memory, wall clock ----
+    h_poses = [torch.empty(B, 12, dtype=torch.float64).pin_memory() for _ in range(args.steps)]
+    for i in range(2):
+        pipe.submit(h_src, h_tgt, h_R, h_R, h_t, starts=starts, host_out=h_poses[i])
+    pipe.collect()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    for i in range(args.steps):
+        pipe.submit(h_src, h_tgt, h_R, h_R, h_t, starts=starts, host_out=h_poses[i])
+    pipe.collect()
     barrier()
     e2e_s = time.perf_counter() - t0
+    h_pose = h_poses[-1]
 
     # multi-GPU: the one collective of the path, then max over ranks
     all_poses = dv.sharding.all_gather_poses(poses, B * world)
@@ -214,9 +228,9 @@ def run_ours(args):
         ab = algorithmic_bytes(B, N, N, Q, w["k"], 3)
         kernels = {}
         for name, tot in stage_ms.items():
-            avg = tot / args.steps
+            avg = tot / prof_steps
             gbs = ab[name] / (avg * 1e-3) / 1e9 if name in ab and avg > 0 else None
-            kernels[name] = {"ms": round(avg, 4), "share": round(avg / ms_step, 4),
+            kernels[name] = {"ms": round(avg, 4), "share": round(avg / latency_ms, 4),
                              "algorithmic_mb": round(ab.get(name, 0) / 1e6, 3),
                              "achieved_gbs": None if gbs is None else round(gbs, 2),
                              "frac_hbm": None if gbs is None else round(gbs / peak, 5)}
@@ -231,8 +245,13 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "b200",
             "config": {"workload": WORKLOAD_NAME, "pairs_per_gpu": B, "n_points": N, "keypoints": 64,
-                       "grid": "11^3", "k": 32, "timing": "CUDA events per step, L2 flushed (256 MiB write) "
-                       "between timed steps", "parallelism": "pairs sharded by rank, all-gather of poses only"},
+                       "grid": "11^3", "k": 32, "timing": "CUDA events around the K steps, L2 flushed (256 MiB write) "
+                       "before every step", "pipeline_depth": args.depth,
+                       "pipeline": "StreamedRegistration: batches alternate between %d streams, so the sampling of "
+                                   "batch i+1 overlaps the dense stages of batch i; every batch runs the complete "
+                                   "forward + pose solve" % args.depth,
+                       "parallelism": "pairs sharded by rank, all-gather of poses only"},
+            "latency_ms_per_step_unpipelined": round(latency_ms, 4),
             "roofline": roofline, "kernels": kernels,
             "e2e": {"value": round(pairs / (e2e_ms * 1e-3 / args.steps), 3), "unit": "pairs/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_pose.numel() * 8},
@@ -312,6 +331,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, help="batches in flight (1 = one at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

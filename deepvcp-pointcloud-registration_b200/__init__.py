@@ -8,7 +8,7 @@
 
 Everything numeric runs in libdvcp_b200.so (include/dvcp_b200.h); see DESIGN.md.
 """
-from . import functional, sharding, synthetic                                    # noqa: F401
+from . import functional, pipeline, sharding, synthetic                                    # noqa: F401
 from ._lib import (QUIRK_KEYPOINT_VIEW, QUIRK_PER_FEATURE_WEIGHT, QUIRKS_REFERENCE, lib, lib_path)  # noqa: F401
 from .build import build                                               # noqa: F401
 from .cpg import cpg                                                   # noqa: F401
@@ -18,6 +18,7 @@ from .deepVCP import DeepVCP                                           # noqa: F
 from .deepVCP_loss import get_rigid_transform, pose_from_forward, svd_optimization  # noqa: F401
 from .get_cat_feat_src import Get_Cat_Feat_Src                         # noqa: F401
 from .get_cat_feat_tgt import Get_Cat_Feat_Tgt                         # noqa: F401
+from .pipeline import StreamedRegistration                             # noqa: F401
 from .knn_cuda import KNN                                              # noqa: F401
 from .pointnet2_utils import (PointNetSetAbstraction, farthest_point_sample, index_points,  # noqa: F401
                               query_ball_point, sample_and_group, square_distance)

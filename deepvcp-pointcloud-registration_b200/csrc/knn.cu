@@ -200,6 +200,182 @@ __device__ __forceinline__ float box_lb(float qx, float qy, float qz, float nx, 
 
 constexpr int KNI_BUF = 128;   // qualifying points collected per query before the sort
 
+// What one warp needs to search one cloud.
+struct KnnCtx {
+    const float *box;          // bucket boxes of the cloud
+    const float4 *spt;         // points in Morton order
+    unsigned long long *buf;   // this warp's KNI_BUF-entry scratch list in shared memory
+    int K;
+};
+
+// key of point at sorted slot `pos` for query (qx,qy,qz): bits(d2) << 32 | id << 16 | pos
+__device__ __forceinline__ unsigned long long knn_point_key(const float4 *spt, int pos, float qx, float qy, float qz,
+                                                            float &d2) {
+    const float4 P = __ldg(spt + pos);   // unused slots hold +inf coordinates and id -1
+    const int id = __float_as_int(P.w);
+    d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+    return id >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned)id << 16) | (unsigned)pos)
+                   : 0xffffffffffffffffull;
+}
+
+// the K smallest of `cnt` keys in buf[], ascending across the lanes (lanes >= cnt of the last chunk hold INF)
+__device__ __forceinline__ unsigned long long knn_select_sorted(const unsigned long long *buf, int cnt, int lane) {
+    const unsigned long long INF = 0xffffffffffffffffull;
+    unsigned long long res = INF;
+    for (int g = 0; g < cnt; g += 32) {
+        unsigned long long k = g + lane < cnt ? buf[g + lane] : INF;
+        k = bitonic_sort32(k, lane);
+        if (g == 0) {
+            res = k;
+        } else {
+            const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
+            res = u64min(res, r);
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, res, j);
+                res = (lane & j) == 0 ? u64min(res, other) : u64max(res, other);
+            }
+        }
+    }
+    return res;
+}
+
+// One exact query by one warp. `list`: K points already known (the result of a nearby query; all-INF = none):
+// re-evaluated for this query they bound its K-th distance. sb: this lane's super-box. Returns the K nearest
+// keys ascending across the lanes (lanes >= K hold INF).
+template <int T>
+__device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const Box6 &sb, float qx, float qy, float qz,
+                                                        unsigned long long list, int lane) {
+    const unsigned long long INF = 0xffffffffffffffffull;
+    const float *box = c.box;
+    const float4 *spt = c.spt;
+    unsigned long long *buf = c.buf;
+    const int K = c.K;
+    auto point_key = [&](int pos, float qx_, float qy_, float qz_, float &d2) -> unsigned long long {
+        return knn_point_key(spt, pos, qx_, qy_, qz_, d2);
+    };
+    const float lbs = box_lb(qx, qy, qz, sb.nx, sb.ny, sb.nz, sb.xx, sb.xy, sb.xz);
+    // ---- bound thr on the K-th squared distance: K known points, evaluated exactly ----
+    float thr;
+    {
+        unsigned long long k0;
+        float d2 = 0.f;
+        if (__any_sync(0xffffffffu, list != INF)) {
+            // previous neighbours re-evaluated for this query
+            k0 = (lane < K && list != INF) ? point_key((int)(list & 0xffffu), qx, qy, qz, d2) : 0ull;
+            const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)(k0 >> 32));
+            thr = __uint_as_float(mx);
+        } else {
+            thr = INFINITY;   // first query of a chain: best-first streaming search below
+        }
+    }
+    unsigned long long res = INF;
+    if (!(thr < INFINITY)) {
+        // ---- best-first over the bucket groups, streaming merge; exact for any start ----
+        unsigned long long worst = INF;
+        float rem = lbs;   // this lane's group lower bound; +inf once processed
+        while (true) {
+            const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(rem));
+            const float now = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
+            if (mb == 0x7f800000u || !(__uint_as_float(mb) <= now)) break;
+            const int sl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(rem) == mb)) - 1;
+            if (lane == sl) rem = INFINITY;
+            float l = INFINITY;
+            if (lane < T) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+                if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+            }
+            // the group's buckets in increasing order of their own bound
+            while (true) {
+                const unsigned lm = __reduce_min_sync(0xffffffffu, __float_as_uint(l));
+                const float now2 = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
+                if (lm == 0x7f800000u || !(__uint_as_float(lm) <= now2)) break;
+                const int bl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(l) == lm)) - 1;
+                if (lane == bl) l = INFINITY;
+                float d2;
+                const unsigned long long key = point_key((sl * T + bl) * 32 + lane, qx, qy, qz, d2);
+                const unsigned m = __ballot_sync(0xffffffffu, key < worst);
+                if (m) knn_merge(res, worst, key, m, K, lane);
+            }
+        }
+    } else {
+    // ---- collect every point with d2 <= thr from the buckets whose box allows it ----
+    int cnt = 0;
+    unsigned sm = __ballot_sync(0xffffffffu, lbs <= thr);
+    while (sm) {
+        const int sl = __ffs(sm) - 1;
+        sm &= sm - 1;
+        float l = INFINITY;
+        if (lane < T) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+            if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+        }
+        unsigned bm = __ballot_sync(0xffffffffu, l <= thr);
+        while (bm) {
+            const int j = sl * T + __ffs(bm) - 1;
+            bm &= bm - 1;
+            const int pos = j * 32 + lane;
+            const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never within thr
+            const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+            const bool qual = d2 <= thr;
+            const unsigned m = __ballot_sync(0xffffffffu, qual);
+            if (m) {
+                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                if (qual && slot < KNI_BUF)
+                    buf[slot] = ((unsigned long long)__float_as_uint(d2) << 32) |
+                                ((unsigned)__float_as_int(P.w) << 16) | (unsigned)pos;
+                cnt += __popc(m);
+            }
+        }
+    }
+    __syncwarp();
+    // ---- the K smallest keys, ascending across the lanes ----
+    if (cnt <= KNI_BUF) {
+        for (int g = 0; g < cnt; g += 32) {
+            unsigned long long k = g + lane < cnt ? buf[g + lane] : INF;
+            k = bitonic_sort32(k, lane);
+            if (g == 0) {
+                res = k;
+            } else {
+                const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
+                res = u64min(res, r);
+#pragma unroll
+                for (int j = 16; j > 0; j >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, res, j);
+                    res = (lane & j) == 0 ? u64min(res, other) : u64max(res, other);
+                }
+            }
+        }
+    } else {
+        // too many qualifying points for the buffer (loose bound): streaming merge over the same buckets
+        unsigned long long worst = INF;
+        unsigned sm2 = __ballot_sync(0xffffffffu, lbs <= thr);
+        while (sm2) {
+            const int sl = __ffs(sm2) - 1;
+            sm2 &= sm2 - 1;
+            for (int t = 0; t < T; ++t) {
+                const int j = sl * T + t;
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
+                if (!(b1.z > 0.f)) continue;
+                const float l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                const float now = worst == INF ? thr : fminf(thr, __uint_as_float((unsigned)(worst >> 32)));
+                if (!(l <= now)) continue;
+                float d2;
+                const unsigned long long key = point_key(j * 32 + lane, qx, qy, qz, d2);
+                const unsigned m = __ballot_sync(0xffffffffu, key < worst && d2 <= thr);
+                if (m) knn_merge(res, worst, key, m, K, lane);
+            }
+        }
+    }
+    }
+    __syncwarp();
+    if (lane >= K) res = INF;
+    return res;
+}
+
 template <int T>   // T = buckets / 32
 __global__ void __launch_bounds__(KNI_WARPS * 32)
 knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, int64_t Q, int K, int chain,
@@ -208,20 +384,13 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long INF = 0xffffffffffffffffull;
     const int cap = index.cap;
-    const float *box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
-    const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
-    unsigned long long *buf = s_buf[warp];
-    const Box6 sb = load_super_box(box, T, lane);
+    KnnCtx ctx;
+    ctx.box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
+    ctx.spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
+    ctx.buf = s_buf[warp];
+    ctx.K = K;
+    const Box6 sb = load_super_box(ctx.box, T, lane);
     const int64_t nchains = (Q + chain - 1) / chain;
-
-    // key of point at sorted slot `pos` for query (qx,qy,qz): bits(d2) << 32 | id << 16 | pos
-    auto point_key = [&](int pos, float qx, float qy, float qz, float &d2) -> unsigned long long {
-        const float4 P = __ldg(spt + pos);   // unused slots hold +inf coordinates and id -1
-        const int id = __float_as_int(P.w);
-        d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
-        return id >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned)id << 16) | (unsigned)pos) : INF;
-    };
-
     for (int64_t ch = (int64_t)blockIdx.x * KNI_WARPS + warp; ch < nchains; ch += (int64_t)gridDim.x * KNI_WARPS) {
         const int64_t q0 = ch * chain, q1 = min(q0 + chain, Q);
         unsigned long long list = INF;   // result of the previous query of the chain (lane j: j-th neighbour)
@@ -234,125 +403,7 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
             }
             const float *qp = query + ((int64_t)b * Q + q) * 3;
             const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-            const float lbs = box_lb(qx, qy, qz, sb.nx, sb.ny, sb.nz, sb.xx, sb.xy, sb.xz);
-            // ---- bound thr on the K-th squared distance: K known points, evaluated exactly ----
-            float thr;
-            {
-                unsigned long long k0;
-                float d2 = 0.f;
-                if (__any_sync(0xffffffffu, list != INF)) {
-                    // previous neighbours re-evaluated for this query
-                    k0 = (lane < K && list != INF) ? point_key((int)(list & 0xffffu), qx, qy, qz, d2) : 0ull;
-                    const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)(k0 >> 32));
-                    thr = __uint_as_float(mx);
-                } else {
-                    thr = INFINITY;   // first query of a chain: best-first streaming search below
-                }
-            }
-            unsigned long long res = INF;
-            if (!(thr < INFINITY)) {
-                // ---- best-first over the bucket groups, streaming merge; exact for any start ----
-                unsigned long long worst = INF;
-                float rem = lbs;   // this lane's group lower bound; +inf once processed
-                while (true) {
-                    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(rem));
-                    const float now = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
-                    if (mb == 0x7f800000u || !(__uint_as_float(mb) <= now)) break;
-                    const int sl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(rem) == mb)) - 1;
-                    if (lane == sl) rem = INFINITY;
-                    float l = INFINITY;
-                    if (lane < T) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
-                        if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-                    }
-                    // the group's buckets in increasing order of their own bound
-                    while (true) {
-                        const unsigned lm = __reduce_min_sync(0xffffffffu, __float_as_uint(l));
-                        const float now2 = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
-                        if (lm == 0x7f800000u || !(__uint_as_float(lm) <= now2)) break;
-                        const int bl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(l) == lm)) - 1;
-                        if (lane == bl) l = INFINITY;
-                        float d2;
-                        const unsigned long long key = point_key((sl * T + bl) * 32 + lane, qx, qy, qz, d2);
-                        const unsigned m = __ballot_sync(0xffffffffu, key < worst);
-                        if (m) knn_merge(res, worst, key, m, K, lane);
-                    }
-                }
-            } else {
-            // ---- collect every point with d2 <= thr from the buckets whose box allows it ----
-            int cnt = 0;
-            unsigned sm = __ballot_sync(0xffffffffu, lbs <= thr);
-            while (sm) {
-                const int sl = __ffs(sm) - 1;
-                sm &= sm - 1;
-                float l = INFINITY;
-                if (lane < T) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
-                    if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-                }
-                unsigned bm = __ballot_sync(0xffffffffu, l <= thr);
-                while (bm) {
-                    const int j = sl * T + __ffs(bm) - 1;
-                    bm &= bm - 1;
-                    const int pos = j * 32 + lane;
-                    const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never within thr
-                    const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
-                    const bool qual = d2 <= thr;
-                    const unsigned m = __ballot_sync(0xffffffffu, qual);
-                    if (m) {
-                        const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                        if (qual && slot < KNI_BUF)
-                            buf[slot] = ((unsigned long long)__float_as_uint(d2) << 32) |
-                                        ((unsigned)__float_as_int(P.w) << 16) | (unsigned)pos;
-                        cnt += __popc(m);
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- the K smallest keys, ascending across the lanes ----
-            if (cnt <= KNI_BUF) {
-                for (int g = 0; g < cnt; g += 32) {
-                    unsigned long long k = g + lane < cnt ? buf[g + lane] : INF;
-                    k = bitonic_sort32(k, lane);
-                    if (g == 0) {
-                        res = k;
-                    } else {
-                        const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
-                        res = u64min(res, r);
-#pragma unroll
-                        for (int j = 16; j > 0; j >>= 1) {
-                            const unsigned long long other = __shfl_xor_sync(0xffffffffu, res, j);
-                            res = (lane & j) == 0 ? u64min(res, other) : u64max(res, other);
-                        }
-                    }
-                }
-            } else {
-                // too many qualifying points for the buffer (loose bound): streaming merge over the same buckets
-                unsigned long long worst = INF;
-                unsigned sm2 = __ballot_sync(0xffffffffu, lbs <= thr);
-                while (sm2) {
-                    const int sl = __ffs(sm2) - 1;
-                    sm2 &= sm2 - 1;
-                    for (int t = 0; t < T; ++t) {
-                        const int j = sl * T + t;
-                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
-                        if (!(b1.z > 0.f)) continue;
-                        const float l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-                        const float now = worst == INF ? thr : fminf(thr, __uint_as_float((unsigned)(worst >> 32)));
-                        if (!(l <= now)) continue;
-                        float d2;
-                        const unsigned long long key = point_key(j * 32 + lane, qx, qy, qz, d2);
-                        const unsigned m = __ballot_sync(0xffffffffu, key < worst && d2 <= thr);
-                        if (m) knn_merge(res, worst, key, m, K, lane);
-                    }
-                }
-            }
-            }
-            __syncwarp();
-            if (lane >= K) res = INF;
+            const unsigned long long res = knn_query<T>(ctx, sb, qx, qy, qz, list, lane);
             if (lane < K) {
                 const int64_t o = ((int64_t)b * Q + q) * K + lane;
                 dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(res >> 32)));

@@ -622,3 +622,50 @@ def test_kitti_shaped_forward_full_size_properties(dv, synthetic):
     assert torch.equal(L["src_fps"][:1].cpu().long(), ref)
     R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(2, 3, 1).to(DEV))
     assert torch.isfinite(R2).all() and torch.isfinite(t2).all()
+
+
+def test_overlapped_sa_equals_sequential_path(dv, F, synthetic):
+    """K8-shaped forward: the SA layer that runs beside the sampling (original point order, rows
+    gathered into FPS order afterwards) must give the features of the plain FPS -> SA sequence."""
+    lib = importlib.import_module(PKG + "._lib")
+    N = 16384
+    src, tgt, R, _ = synthetic.make_batch("kitti", [3], N)
+    torch.manual_seed(5)
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=2.0, s=0.4).to(DEV).eval()
+    starts = (torch.tensor([7]), torch.tensor([8]), torch.tensor([9]))
+    model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True)
+    L = model.last
+    both = torch.cat([src, tgt], 0).to(DEV)
+    st2 = torch.cat([starts[0], starts[2]])
+    index = F.SpatialIndex(2, N, both.device)
+    _, fps2 = F.fps(lib.cloud_cm(both), both.device, both.dtype, 2, N, N, st2, want64=False, want32=True, index=index)
+    sa = model.FE1.sa1
+    _, feat2 = F.sa_layer(lib.cloud_cm(both), None, 0, fps2, 2, N, N, sa.radius, sa.nsample, sa.folded(), both.device,
+                          want_xyz=False, index=index)
+    assert torch.equal(fps2[:1], L["src_fps"]) and torch.equal(fps2[1:], L["tgt_fps"])
+    assert torch.equal(feat2[:1], L["src_fe_feat"]) and torch.equal(feat2[1:], L["tgt_fe_feat"])
+
+
+def test_streamed_registration_equals_one_batch_at_a_time(dv, synthetic):
+    """Throughput mode (batches alternating between streams) returns, in order, exactly the poses
+    of the same batches registered one after the other."""
+    N = 4096
+    torch.manual_seed(9)
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=1.2, s=0.4).to(DEV).eval()
+    batches = []
+    for i in range(5):
+        src, tgt, R, t = synthetic.make_batch("kitti", [2 * i, 2 * i + 1], N)
+        starts = (torch.tensor([i, i + 1]), torch.tensor([i + 2, i + 3]), torch.tensor([i + 4, i + 5]))
+        batches.append((src, tgt, R, t.view(2, 3, 1), starts))
+    ref = []
+    for src, tgt, R, t, starts in batches:
+        kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts)
+        R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.to(DEV))
+        ref.append(dv.sharding.pack_poses(R2, t2).cpu())
+    pipe = dv.StreamedRegistration(model, depth=2)
+    hosts = [torch.empty(2, 12, dtype=torch.float64).pin_memory() for _ in batches]
+    for (src, tgt, R, t, starts), h in zip(batches, hosts):
+        pipe.submit(src, tgt, R, R, t, starts=starts, host_out=h)
+    out = pipe.collect()
+    for a, b, h in zip(out, ref, hosts):
+        assert torch.equal(a.cpu(), b) and torch.equal(h, b)
