@@ -181,8 +181,9 @@ __device__ __forceinline__ void sa_member_mlp(const SaParams &P, const SaWeights
 __global__ void __launch_bounds__(SA_WARPS * 32)
 sa_layer_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict__ cidx, int B, int N, int S, float r2,
                 int nsample, SaParams P, const unsigned char *__restrict__ need, float *__restrict__ out_feat,
-                float *__restrict__ out_xyz) {
+                float *__restrict__ out_xyz, const unsigned *__restrict__ any_needed = nullptr) {
     extern __shared__ float smem[];
+    if (any_needed && *any_needed == 0u) return;   // overflow pass with nothing to redo (the usual case)
     float *sx = smem, *sy = sx + BQ_TILE, *sz = sy + BQ_TILE, *sp = sz + BQ_TILE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SaWeights w;
@@ -587,6 +588,212 @@ sa_layer_fast_kernel(Cloud xyz, Cloud feats, const int32_t *__restrict__ cidx, i
     (void)N;
 }
 
+// ------------------------------------------- SA layer of EVERY point, by bucket --
+// When every point of the cloud is a centroid (DeepVCP: npoint == N) the search can be
+// shared: a warp takes one Morton bucket, lane = centroid, finds the few buckets whose box
+// some lane's ball can reach, stages each in shared memory and lets every lane test the 32
+// staged points with the exact arithmetic. Members go to a per-lane list; the shared MLP is
+// then evaluated member after member with the 32 running maxima of the lane's centroid in
+// registers (no transposition). Output row = the centroid's ORIGINAL index. Centroids with
+// more than SAB_CAPL members are flagged for the brute-force pass.
+constexpr int SAB_WARPS = 8;
+constexpr int SAB_CAPL = 8;
+
+template <int CIN>
+struct SabSmem {
+    static constexpr int LD1 = (CIN + 3) / 4 * 4;
+    float w1[16 * LD1], w2[16 * 16], w3[32 * 16];
+    float bn1[3 * 16], bn2[3 * 16], bn3[3 * 32];   // bias, alpha, beta
+    float4 pts[SAB_WARPS][32];                     // staged bucket: x, y, z, |p|^2
+    int pid[SAB_WARPS][32];
+    float4 lst[SAB_WARPS][SAB_CAPL][32];           // member k of lane's centroid: p - q, index bits
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(SAB_WARPS * 32)
+sa_layer_bucket_kernel(Cloud feats, int N, float r2, int nsample, SaParams P, dvcp_cloud_index_t index,
+                       unsigned char *__restrict__ need, unsigned *__restrict__ any_needed,
+                       float *__restrict__ out_feat) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SabSmem<CIN> &sm = *reinterpret_cast<SabSmem<CIN> *>(smem_raw);
+    constexpr int LD1 = SabSmem<CIN>::LD1;
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 16 * LD1; i += blockDim.x) {
+        const int o = i / LD1, k = i - o * LD1;
+        sm.w1[i] = k < CIN ? P.W[0][o * CIN + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.w2[i] = P.W[1][i];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sm.w3[i] = P.W[2][i];
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) {
+        sm.bn1[i] = P.b[0][i]; sm.bn1[16 + i] = P.alpha[0][i]; sm.bn1[32 + i] = P.beta[0][i];
+        sm.bn2[i] = P.b[1][i]; sm.bn2[16 + i] = P.alpha[1][i]; sm.bn2[32 + i] = P.beta[1][i];
+    }
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+        sm.bn3[i] = P.b[2][i]; sm.bn3[32 + i] = P.alpha[2][i]; sm.bn3[64 + i] = P.beta[2][i];
+    }
+    __syncthreads();
+    const int cap = index.cap, NB = cap / 32, T = NB / 32;
+    const float *box = index.bucket_box + (int64_t)b * NB * 8;
+    const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
+    // union box of this lane's T Morton-consecutive buckets
+    float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8) + 1);
+        if (b1.z > 0.f) {
+            snx = fminf(snx, b0.x); sny = fminf(sny, b0.y); snz = fminf(snz, b0.z);
+            sxx = fmaxf(sxx, b0.w); sxy = fmaxf(sxy, b1.x); sxz = fmaxf(sxz, b1.y);
+        }
+    }
+    float4 *pts = sm.pts[warp];
+    int *pid = sm.pid[warp];
+    for (int j = blockIdx.x * SAB_WARPS + warp; j < NB; j += gridDim.x * SAB_WARPS) {
+        const float4 bj0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
+        const float4 bj1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
+        if (!(bj1.z > 0.f)) continue;   // empty bucket (uniform)
+        const float4 Pq = __ldg(spt + j * 32 + lane);
+        const int cid = __float_as_int(Pq.w);
+        const bool valid = cid >= 0;
+        const float qx = valid ? Pq.x : bj0.x, qy = valid ? Pq.y : bj0.y, qz = valid ? Pq.z : bj0.z;
+        const float qq = norm2_nofma(qx, qy, qz);
+        const float qn = sqrtf(qq) * 1.0001f;
+        // can a box hold a member of MY centroid? (same bound as the per-centroid kernels)
+        auto box_may_hold = [&](float nx, float ny, float nz, float xx, float xy, float xz) -> bool {
+            const float ex = fmaxf(fmaxf(nx - qx, qx - xx), 0.f);
+            const float ey = fmaxf(fmaxf(ny - qy, qy - xy), 0.f);
+            const float ez = fmaxf(fmaxf(nz - qz, qz - xz), 0.f);
+            const float lb = ex * ex + ey * ey + ez * ez;
+            const float ax = fmaxf(fabsf(nx), fabsf(xx)), ay = fmaxf(fabsf(ny), fabsf(xy)), az = fmaxf(fabsf(nz), fabsf(xz));
+            const float pn = sqrtf(ax * ax + ay * ay + az * az) * 1.0001f;
+            const float E = 8e-7f * (qn + pn) * (qn + pn);
+            return lb * 0.9999f <= r2 + E;
+        };
+        // box-to-box form of the same test, with the bucket's own box standing for all its centroids
+        const float jn = sqrtf(fmaxf(fabsf(bj0.x), fabsf(bj0.w)) * fmaxf(fabsf(bj0.x), fabsf(bj0.w)) +
+                               fmaxf(fabsf(bj0.y), fabsf(bj1.x)) * fmaxf(fabsf(bj0.y), fabsf(bj1.x)) +
+                               fmaxf(fabsf(bj0.z), fabsf(bj1.y)) * fmaxf(fabsf(bj0.z), fabsf(bj1.y))) * 1.0001f;
+        auto box_may_reach = [&](float nx, float ny, float nz, float xx, float xy, float xz) -> bool {
+            const float ex = fmaxf(fmaxf(nx - bj0.w, bj0.x - xx), 0.f);
+            const float ey = fmaxf(fmaxf(ny - bj1.x, bj0.y - xy), 0.f);
+            const float ez = fmaxf(fmaxf(nz - bj1.y, bj0.z - xz), 0.f);
+            const float lb = ex * ex + ey * ey + ez * ez;
+            const float ax = fmaxf(fabsf(nx), fabsf(xx)), ay = fmaxf(fabsf(ny), fabsf(xy)), az = fmaxf(fabsf(nz), fabsf(xz));
+            const float pn = sqrtf(ax * ax + ay * ay + az * az) * 1.0001f;
+            const float E = 8e-7f * (jn + pn) * (jn + pn);
+            return lb * 0.9999f <= r2 + E;
+        };
+        int cnt = 0;
+        // level 1: lane g tests the union box of bucket group g against this bucket's box
+        unsigned smk = __ballot_sync(0xffffffffu, snx <= sxx && box_may_reach(snx, sny, snz, sxx, sxy, sxz));
+        while (smk) {
+            const int sl = __ffs(smk) - 1;
+            smk &= smk - 1;
+            bool flag = false;
+            if (lane < T) {   // level 2: the buckets of that group, one per lane
+                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
+                const float4 c1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
+                flag = c1.z > 0.f && box_may_reach(c0.x, c0.y, c0.z, c0.w, c1.x, c1.y);
+            }
+            unsigned fm = __ballot_sync(0xffffffffu, flag);
+            while (fm) {
+                const int nb = sl * T + __ffs(fm) - 1;
+                fm &= fm - 1;
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)nb * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)nb * 8) + 1);
+                const bool mine = valid && box_may_hold(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                if (!__any_sync(0xffffffffu, mine)) continue;
+                __syncwarp();
+                {
+                    const float4 Pn = __ldg(spt + nb * 32 + lane);
+                    const int idn = __float_as_int(Pn.w);
+                    const float px = idn < 0 ? 0.f : Pn.x, py = idn < 0 ? 0.f : Pn.y, pz = idn < 0 ? 0.f : Pn.z;
+                    pts[lane] = make_float4(px, py, pz, norm2_nofma(px, py, pz));
+                    pid[lane] = idn;
+                }
+                __syncwarp();
+                if (mine) {
+#pragma unroll 4
+                    for (int i = 0; i < 32; ++i) {
+                        const float4 p = pts[i];
+                        const int idi = pid[i];
+                        const float d2 = sqdist_expanded(qx, qy, qz, qq, p.x, p.y, p.z, p.w);
+                        if (idi >= 0 && !(d2 > r2)) {
+                            if (cnt < SAB_CAPL)
+                                sm.lst[warp][cnt][lane] = make_float4(p.x - qx, p.y - qy, p.z - qz, __int_as_float(idi));
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        const bool over = cnt > SAB_CAPL || cnt > nsample;
+        if (valid) need[(int64_t)b * N + cid] = over ? 1 : 0;
+        if (valid && over) atomicAdd(any_needed, 1u);
+        // ---- shared MLP, member after member; the lane keeps the 32 maxima of its centroid ----
+        const int mine_n = (valid && !over) ? cnt : 0;
+        const int maxn = __reduce_max_sync(0xffffffffu, mine_n);
+        float best[32];
+#pragma unroll
+        for (int o = 0; o < 32; ++o) best[o] = 0.f;   // ReLU outputs are >= 0 and a ball always holds its centre
+        for (int k = 0; k < maxn; ++k) {
+            if (k < mine_n) {
+                const float4 m = sm.lst[warp][k][lane];
+                float x[LD1];
+                x[0] = m.x; x[1] = m.y; x[2] = m.z;
+#pragma unroll
+                for (int c = 3; c < LD1; ++c) x[c] = c < CIN ? feats.at(b, __float_as_int(m.w), c - 3) : 0.f;
+                float h1[16], h2[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < LD1 / 4; ++k4) {
+                        const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[o * LD1 + 4 * k4]);
+                        acc = fmaf(w.x, x[4 * k4], acc);
+                        acc = fmaf(w.y, x[4 * k4 + 1], acc);
+                        acc = fmaf(w.z, x[4 * k4 + 2], acc);
+                        acc = fmaf(w.w, x[4 * k4 + 3], acc);
+                    }
+                    h1[o] = fmaxf(fmaf(acc + sm.bn1[o], sm.bn1[16 + o], sm.bn1[32 + o]), 0.f);
+                }
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 w = *reinterpret_cast<const float4 *>(&sm.w2[o * 16 + 4 * k4]);
+                        acc = fmaf(w.x, h1[4 * k4], acc);
+                        acc = fmaf(w.y, h1[4 * k4 + 1], acc);
+                        acc = fmaf(w.z, h1[4 * k4 + 2], acc);
+                        acc = fmaf(w.w, h1[4 * k4 + 3], acc);
+                    }
+                    h2[o] = fmaxf(fmaf(acc + sm.bn2[o], sm.bn2[16 + o], sm.bn2[32 + o]), 0.f);
+                }
+#pragma unroll
+                for (int o = 0; o < 32; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 w = *reinterpret_cast<const float4 *>(&sm.w3[o * 16 + 4 * k4]);
+                        acc = fmaf(w.x, h2[4 * k4], acc);
+                        acc = fmaf(w.y, h2[4 * k4 + 1], acc);
+                        acc = fmaf(w.z, h2[4 * k4 + 2], acc);
+                        acc = fmaf(w.w, h2[4 * k4 + 3], acc);
+                    }
+                    best[o] = fmaxf(best[o], fmaxf(fmaf(acc + sm.bn3[o], sm.bn3[32 + o], sm.bn3[64 + o]), 0.f));
+                }
+            }
+        }
+        if (mine_n > 0) {
+            float4 *o4 = reinterpret_cast<float4 *>(out_feat + ((int64_t)b * N + cid) * 32);
+#pragma unroll
+            for (int o = 0; o < 8; ++o) o4[o] = make_float4(best[4 * o], best[4 * o + 1], best[4 * o + 2], best[4 * o + 3]);
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------ square_distance -----
 __global__ void square_distance_kernel(Cloud src, Cloud dst, int S, int N, float *__restrict__ out) {
     const int b = blockIdx.z, s = blockIdx.y;
@@ -820,6 +1027,60 @@ extern "C" int dvcp_index_points(const float *points, const int64_t *idx, int B,
     int64_t gx = (total + 255) / 256; if (gx > 148 * 16) gx = 148 * 16;
     dim3 grid((unsigned)gx, B);
     index_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, idx, N, C, M, out);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dvcp_sa_layer_all(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *identity_idx, int B, int N,
+                                 float radius2, int nsample, const dvcp_mlp_layer_t *layers, int n_layers,
+                                 dvcp_cloud_index_t index, unsigned char *overflow_ws, float *out_feat,
+                                 dvcp_stream_t stream) {
+    if (!xyz.base || !identity_idx || !layers || !out_feat || !overflow_ws || !index.sorted_pt || !index.bucket_box ||
+        B <= 0 || N <= 0 || nsample <= 0)
+        return DVCP_E_ARG;
+    const bool shape = n_layers == 3 && layers[0].out_ch == 16 && layers[1].out_ch == 16 && layers[2].out_ch == 32 &&
+                       (D == 0 || D == 3) && layers[0].in_ch == 3 + D && nsample >= SAB_CAPL && index.cap >= N &&
+                       index.cap >= 1024 && B <= 65535;
+    if (!shape)   // any other layer shape: the general entry point with every point as a centroid
+        return dvcp_sa_layer(xyz, feats, D, identity_idx, B, N, N, radius2, nsample, layers, n_layers, index,
+                             overflow_ws, out_feat, nullptr, stream);
+    SaParams P;
+    P.n_layers = 3;
+    int cin = 3 + D;
+    size_t wfloats = 0;
+    for (int l = 0; l < 3; ++l) {
+        P.W[l] = layers[l].W; P.b[l] = layers[l].b; P.alpha[l] = layers[l].alpha; P.beta[l] = layers[l].beta;
+        if (!P.W[l] || !P.b[l] || !P.alpha[l] || !P.beta[l]) return DVCP_E_ARG;
+        P.cin[l] = cin; P.cout[l] = layers[l].out_ch;
+        wfloats += (size_t)cin * layers[l].out_ch + 3 * layers[l].out_ch;
+        cin = layers[l].out_ch;
+    }
+    Cloud f = D > 0 ? as_cloud(feats) : Cloud{nullptr, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NB = index.cap / 32;
+    dim3 grid((NB + SAB_WARPS - 1) / SAB_WARPS, B);
+    // counter of flagged centroids behind the B*N flags (16-byte aligned)
+    unsigned *any_needed = reinterpret_cast<unsigned *>(overflow_ws + (((size_t)B * N + 15) & ~(size_t)15));
+    DVCP_CUDA(cudaMemsetAsync(any_needed, 0, sizeof(unsigned), st));
+    if (D == 0) {
+        auto k = sa_layer_bucket_kernel<3>;
+        const int fs = (int)sizeof(SabSmem<3>);
+        DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+        k<<<grid, SAB_WARPS * 32, fs, st>>>(f, N, radius2, nsample, P, index, overflow_ws, any_needed, out_feat);
+    } else {
+        auto k = sa_layer_bucket_kernel<6>;
+        const int fs = (int)sizeof(SabSmem<6>);
+        DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+        k<<<grid, SAB_WARPS * 32, fs, st>>>(f, N, radius2, nsample, P, index, overflow_ws, any_needed, out_feat);
+    }
+    DVCP_CHECK_LAUNCH();
+    // centroids with too many members for the fast path: the brute-force kernel redoes exactly those
+    const size_t smem = (4 * BQ_TILE + wfloats) * sizeof(float);
+    DVCP_CUDA(cudaFuncSetAttribute(sa_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int items = B * ((N + SA_WARPS - 1) / SA_WARPS);
+    const int g2 = items < 2 * DVCP_NUM_SMS ? items : 2 * DVCP_NUM_SMS;
+    sa_layer_kernel<<<g2, SA_WARPS * 32, smem, st>>>(as_cloud(xyz), f, D, identity_idx, B, N, N, radius2, nsample, P,
+                                                    overflow_ws, out_feat, nullptr, any_needed);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

@@ -123,8 +123,8 @@ class DeepVCP(nn.Module):
                     _, fps2 = F_.fps_indexed(cloud_cm(both), dev, 2 * B, N, S, st2, index)
                     ev_fps = torch.cuda.Event()
                     ev_fps.record(hp)
-                _, feat_orig = F_.sa_layer(cloud_cm(both), feat_cloud, D, self._identity(2 * B, N, dev), 2 * B, N, N,
-                                           sa.radius, sa.nsample, mlp, dev, want_xyz=False, index=index)
+                feat_orig = F_.sa_layer_all(cloud_cm(both), feat_cloud, D, self._identity(2 * B, N, dev), 2 * B, N,
+                                            sa.radius, sa.nsample, mlp, dev, index)
                 main.wait_event(ev_fps)
                 fps2.record_stream(main)
                 mark("fps")

@@ -195,6 +195,18 @@ def sa_layer(xyz_cloud, feats_cloud, D, centroid_idx32, B, N, S, radius, nsample
     return oxyz, out
 
 
+def sa_layer_all(xyz_cloud, feats_cloud, D, identity_idx32, B, N, radius, nsample, mlp: FoldedMlp, device, index):
+    """SA features of every point in original order: [B,N,out_ch]."""
+    out = torch.empty(B, N, mlp.out_ch, dtype=torch.float32, device=device)
+    ws = torch.empty(B * N + 32, dtype=torch.uint8, device=device)
+    code = lib().dvcp_sa_layer_all(xyz_cloud, feats_cloud if D > 0 else NULL_CLOUD, D, ptr(identity_idx32), B, N,
+                                   radius2_f32(radius), nsample, mlp.layers, mlp.n, index.c(), ptr(ws), ptr(out),
+                                   stream_ptr(device))
+    check(code, "dvcp_sa_layer_all")
+    _count(2)
+    return out
+
+
 def weighting_scores(X, W1, b1, W2, b2, W3, b3):
     require_cuda(X)
     B, S, _ = X.shape

@@ -134,6 +134,16 @@ DVCP_API int dvcp_sa_layer(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const in
                   int n_layers, dvcp_cloud_index_t index, unsigned char *overflow_ws, float *out_feat,
                   float *out_xyz, dvcp_stream_t stream);
 
+/* The same layer with EVERY point of the cloud as a centroid, in original point order
+ * (out_feat [B,N,out_ch_last]); DeepVCP uses npoint == N, and the features of a point do not
+ * depend on its FPS rank, so this runs beside the sampling and the rows are gathered into FPS
+ * order afterwards. identity_idx [B,N] int32 = 0..N-1 per cloud (caller-provided constant);
+ * index and overflow_ws ([B*N + 32] bytes) are required. */
+DVCP_API int dvcp_sa_layer_all(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *identity_idx, int B, int N,
+                      float radius2, int nsample, const dvcp_mlp_layer_t *layers_host, int n_layers,
+                      dvcp_cloud_index_t index, unsigned char *overflow_ws, float *out_feat,
+                      dvcp_stream_t stream);
+
 /* ---- a8  weighting_layer.forward(X, K)              weighting_layer.py:26-33
  * X [B,S,32]; W1[16,32] b1 W2[8,16] b2 W3[1,8] b3; scores [B,S] (softplus
  * output, may be null if only indices are wanted -> then `scores` is still
