@@ -71,6 +71,19 @@ class DeepVCP(nn.Module):
     def forward(self, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=False, topk_override=None):
         """src_pts, tgt_pts [B,C_in,N]; R_init [B,3,3] float64; t_init [1,3] (unused by
         the reference, quirk Q6) -> (src_keypts [B,K,3], tgt_vcp [B,K,3])."""
+        fe = self.extract_features(src_pts, tgt_pts, starts)
+        return self.match(fe, R_init, keep_stages=keep_stages, topk_override=topk_override)
+
+    def _mark(self, name, dev):
+        if self._events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(dev))
+            self._events.append((name, e))
+
+    def extract_features(self, src_pts, tgt_pts, starts=None):
+        """First half of forward(): feature extraction of both clouds (deepVCP.py:29,72). Returns the
+        state match() continues from. Split out so that a stream of batches can run this half (few SMs,
+        long) beside the second half of the previous batch (pipeline.StreamedRegistration)."""
         if self.training:
             raise RuntimeError("DeepVCP (b200) is the inference path: call .eval() first")
         if src_pts.dtype != torch.float32 or tgt_pts.dtype != torch.float32:
@@ -84,20 +97,13 @@ class DeepVCP(nn.Module):
         # host tensors (pinned or not) are accepted at the boundary and copied once
         src = src_pts.to(dev, non_blocking=True).contiguous()
         tgt = tgt_pts.to(dev, non_blocking=True).contiguous()
-        R = R_init.to(dev, non_blocking=True)
-        require_cuda(src, tgt, R)
+        require_cuda(src, tgt)
         S = self.FE1.sa1.npoint
-        K, ns = self.K_topk, self.nsample
         sa = self.FE1.sa1
         mlp = sa.folded()
         D = C_in - 3
-        ev = self._events = [] if self.profile else None
-
-        def mark(name):
-            if ev is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(torch.cuda.current_stream(dev))
-                ev.append((name, e))
+        self._events = [] if self.profile else None
+        mark = lambda name: self._mark(name, dev)
 
         with torch.no_grad():
             mark("begin")
@@ -109,8 +115,8 @@ class DeepVCP(nn.Module):
             if F_.SpatialIndex.indexable(N) and N > 2048 and 2 * S >= N:
                 # FPS is a chain of dependent selections that leaves most of the GPU idle, and the SA
                 # features of a point do not depend on its FPS rank: build the index, then run the SA
-                # layer over the points in their ORIGINAL order on a side stream beside the sampling,
-                # and put the rows into FPS order afterwards (feat_fps[s] = feat_orig[fps[s]]).
+                # layer over the points in their ORIGINAL order beside the sampling, and put the rows
+                # into FPS order afterwards (feat_fps[s] = feat_orig[fps[s]]).
                 index = F_.build_index(cloud_cm(both), dev, 2 * B, N)
                 main = torch.cuda.current_stream(dev)
                 ev_index = torch.cuda.Event()
@@ -138,6 +144,19 @@ class DeepVCP(nn.Module):
                 _, feat2 = F_.sa_layer(cloud_cm(both), feat_cloud, D, fps2, 2 * B, N, S, sa.radius, sa.nsample, mlp,
                                        dev, want_xyz=False, index=index)
                 mark("sa_layer")
+        return dict(src=src, tgt=tgt, both=both, index=index, fps2=fps2, feat2=feat2, starts=starts, B=B, N=N,
+                    C_in=C_in, dev=dev)
+
+    def match(self, fe, R_init, keep_stages=False, topk_override=None):
+        """Second half of forward(): key-point selection, candidates, KNN, embedding, CPG
+        (deepVCP.py:33-110) on the state extract_features() returned."""
+        src, tgt, index, fps2, feat2, starts = fe["src"], fe["tgt"], fe["index"], fe["fps2"], fe["feat2"], fe["starts"]
+        B, N, dev = fe["B"], fe["N"], fe["dev"]
+        K, ns = self.K_topk, self.nsample
+        R = R_init.to(dev, non_blocking=True)
+        require_cuda(R)
+        mark = lambda name: self._mark(name, dev)
+        with torch.no_grad():
             sfps, tfps = fps2[:B], fps2[B:]
             sfeat, tfeat = feat2[:B], feat2[B:]
             # key-point selection
