@@ -44,7 +44,7 @@ SIGNATURES = {
     "dvcp_abi_version": (c_i32, []),
     "dvcp_error_string": (ctypes.c_char_p, [c_i32]),
     "dvcp_fps": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_vp]),
-    "dvcp_fps_indexed": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_vp]),
+    "dvcp_fps_indexed": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_i32, c_vp]),
     "dvcp_index_capacity": (c_i32, [c_i32]),
     "dvcp_build_index": (c_i32, [Cloud, c_i32, c_i32, CloudIndex, c_vp]),
     "dvcp_fps_plain": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),

@@ -547,7 +547,7 @@ extern "C" int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index
 
 // fps_cluster.cu: one cloud per cluster of 8 CTAs, consuming an index that is already built.
 int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, int N, int npoint, const int64_t *start,
-                            int64_t *out64, int32_t *out32, cudaStream_t st);
+                            int64_t *out64, int32_t *out32, int small_cta, cudaStream_t st);
 
 // Few large clouds (the K8 batch: 16 clouds for 148 SMs): spread each over a cluster. Many clouds fill
 // the GPU one CTA each, which does less total work. DVCP_FPS_CLUSTER=0/1 forces the choice.
@@ -569,7 +569,7 @@ extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, c
     if (dtype == 0 && N <= 16384 && N >= 64 && index.sorted_pt && !fps_sequential_mode() && fps_use_cluster(B, N)) {
         const int rc = dispatch_bucketed(xyz, B, N, 0, nullptr, nullptr, nullptr, index, st);   // index only
         if (rc != 0) return rc;
-        return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, st);
+        return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, 0, st);
     }
     if (dtype == 0 && N <= 16384 && N >= 64) return dispatch_bucketed(xyz, B, N, npoint, start, out64, out32, index, st);
     if (index.sorted_pt) return DVCP_E_UNSUPPORTED;
@@ -593,7 +593,7 @@ extern "C" int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, c
 }
 
 extern "C" int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
-                                int32_t *out32, dvcp_cloud_index_t index, dvcp_stream_t stream) {
+                                int32_t *out32, dvcp_cloud_index_t index, int concurrent, dvcp_stream_t stream) {
     using namespace dvcp;
     if (!xyz.base || !start || (!out64 && !out32) || B <= 0 || N <= 0 || npoint <= 0 || !index.sorted_pt ||
         !index.bucket_box)
@@ -601,7 +601,7 @@ extern "C" int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, cons
     if (index.cap != dvcp_index_capacity(N) || index.cap == 0) return DVCP_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (!fps_sequential_mode() && fps_use_cluster(B, N))
-        return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, st);
+        return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, concurrent, st);
     // one CTA per cloud: that kernel sorts the cloud itself; it must not rewrite an index others are reading
     dvcp_cloud_index_t none = {nullptr, nullptr, 0};
     return dispatch_bucketed(xyz, B, N, npoint, start, out64, out32, none, st);

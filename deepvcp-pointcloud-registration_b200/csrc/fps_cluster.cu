@@ -41,15 +41,15 @@ __device__ long long g_fc_time[24];
 #endif
 
 constexpr int FC_C = 8;         // CTAs per cluster = per cloud
-constexpr int FC_WARPS = 16;    // >= FC_C: warp w < FC_C pushes to CTA w
-constexpr int FC_THREADS = FC_WARPS * 32;
+// warps per CTA is a template parameter W (>= FC_C: warp w < FC_C pushes to CTA w): 16 is fastest for a kernel
+// running alone; 8 halves the CTA's registers / threads so that other kernels keep most of each SM
 constexpr int FC_MAXNBL = 64;   // buckets per CTA (16384 points / 32 / 8)
 constexpr int FC_E = 3;         // keys a bucket exposes per step (its FC_E best)
 constexpr int FC_CAP = 128;     // candidates resolved per step
 constexpr int FC_LCAP = 32;     // candidates one CTA pushes per step
 constexpr int FC_LBUF = FC_E * FC_MAXNBL;
 
-static_assert(FC_THREADS == 4 * FC_CAP && FC_WARPS >= FC_C && FC_E * FC_MAXNBL <= FC_THREADS, "thread mapping");
+static_assert(FC_CAP == 128 && FC_E * FC_MAXNBL <= 8 * 32, "thread mapping");
 
 struct FcShared {
     // exchange area, double-buffered by step parity; written by the peers
@@ -90,10 +90,13 @@ __device__ __forceinline__ void fc_bucket_top(unsigned hi, unsigned lo, unsigned
     }
 }
 
-__global__ void __launch_bounds__(FC_THREADS, 2)
+template <int FC_WARPS>
+__global__ void __launch_bounds__(FC_WARPS * 32, FC_WARPS == 16 ? 2 : 4)
 fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const int64_t *__restrict__ start,
                    int64_t *__restrict__ out64, int32_t *__restrict__ out32) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int FC_THREADS = FC_WARPS * 32;
+    static_assert(FC_WARPS >= FC_C && FC_THREADS % FC_CAP == 0 && FC_THREADS <= 4 * FC_CAP, "thread mapping");
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / FC_C;
@@ -346,26 +349,31 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
         if (blockIdx.x == 0 && tid == 0) { g_fc_time[16] += 1; g_fc_time[17] += n; g_fc_time[18] += A; g_fc_time[19] += sh.l_cnt; g_fc_time[20] += (n > FC_CAP); }
 #endif
         const unsigned long long T = n > FC_CAP ? sh.T : S;
-        // pair tests: thread (row r, quarter) covers the earlier candidates i of 32 columns = one mask word
+        // pair tests: thread (row r, part) covers the earlier candidates i of its share of the 4 mask words
         {
-            const int r = tid & (FC_CAP - 1), quarter = tid >> 7;
+            constexpr int PARTS = FC_THREADS / FC_CAP, WPP = 4 / PARTS;   // words per part
+            const int r = tid & (FC_CAP - 1), part = tid / FC_CAP;
             if (r < m) {
                 const unsigned long long key = sh.s_key[r];
                 const float4 q = sh.s_xyz[r];
                 const unsigned klo = (unsigned)key;
                 const float dj = __uint_as_float((unsigned)(key >> 32));
-                unsigned kw = 0u, lw = 0u;
-                const int i0 = quarter * 32, i1 = r < i0 + 32 ? r : i0 + 32;
-                for (int i = i0; i < i1; ++i) {
-                    const float4 c = sh.s_xyz[i];
-                    const float d = sq3_nofma(__fsub_rn(q.x, c.x), __fsub_rn(q.y, c.y), __fsub_rn(q.z, c.z));
-                    const bool kill = d < dj;
-                    const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | klo;
-                    kw |= (unsigned)kill << (i & 31);
-                    lw |= (unsigned)(kill && nk <= T) << (i & 31);
+#pragma unroll
+                for (int ww = 0; ww < WPP; ++ww) {
+                    const int w = part * WPP + ww;
+                    unsigned kw = 0u, lw = 0u;
+                    const int i0 = w * 32, i1 = r < i0 + 32 ? r : i0 + 32;
+                    for (int i = i0; i < i1; ++i) {
+                        const float4 c = sh.s_xyz[i];
+                        const float d = sq3_nofma(__fsub_rn(q.x, c.x), __fsub_rn(q.y, c.y), __fsub_rn(q.z, c.z));
+                        const bool kill = d < dj;
+                        const unsigned long long nk = ((unsigned long long)__float_as_uint(d) << 32) | klo;
+                        kw |= (unsigned)kill << (i & 31);
+                        lw |= (unsigned)(kill && nk <= T) << (i & 31);
+                    }
+                    sh.K[r][w] = kw;
+                    sh.L[r][w] = lw;
                 }
-                sh.K[r][quarter] = kw;
-                sh.L[r][quarter] = lw;
             }
         }
         FC_TICK(11);
@@ -458,17 +466,15 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
 }  // namespace dvcp
 
 // Launcher used by dvcp_fps (fps.cu). The index must already hold the cloud (dvcp_build_index).
-int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, int N, int npoint, const int64_t *start,
-                            int64_t *out64, int32_t *out32, cudaStream_t st) {
+template <int W>
+static int fps_cluster_launch_w(dvcp::Cloud xyz, dvcp_cloud_index_t index, int B, int N, int npoint, const int64_t *start,
+                                int64_t *out64, int32_t *out32, size_t smem, cudaStream_t st) {
     using namespace dvcp;
-    const int NB = index.cap / 32;
-    if (NB % FC_C != 0 || NB / FC_C > FC_MAXNBL || NB / FC_C < 1) return DVCP_E_UNSUPPORTED;
-    const int NBL = NB / FC_C;
-    const size_t smem = sizeof(FcShared) + (size_t)NBL * 32 * (4 * sizeof(float) + sizeof(unsigned short));
-    DVCP_CUDA(cudaFuncSetAttribute(fps_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto k = fps_cluster_kernel<W>;
+    DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * FC_C));
-    cfg.blockDim = dim3(FC_THREADS);
+    cfg.blockDim = dim3(W * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -478,8 +484,20 @@ int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DVCP_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel, as_cloud(xyz), index, N, npoint, start, out64, out32));
+    DVCP_CUDA(cudaLaunchKernelEx(&cfg, k, xyz, index, N, npoint, start, out64, out32));
     return 0;
+}
+
+// small_cta != 0: 8 warps per CTA instead of 16 (slower alone, friendlier to concurrent kernels)
+int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, int N, int npoint, const int64_t *start,
+                            int64_t *out64, int32_t *out32, int small_cta, cudaStream_t st) {
+    using namespace dvcp;
+    const int NB = index.cap / 32;
+    if (NB % FC_C != 0 || NB / FC_C > FC_MAXNBL || NB / FC_C < 1) return DVCP_E_UNSUPPORTED;
+    const int NBL = NB / FC_C;
+    const size_t smem = sizeof(FcShared) + (size_t)NBL * 32 * (4 * sizeof(float) + sizeof(unsigned short));
+    if (small_cta) return fps_cluster_launch_w<8>(as_cloud(xyz), index, B, N, npoint, start, out64, out32, smem, st);
+    return fps_cluster_launch_w<16>(as_cloud(xyz), index, B, N, npoint, start, out64, out32, smem, st);
 }
 
 #ifdef DVCP_FPS_TIMING

@@ -80,7 +80,7 @@ class DeepVCP(nn.Module):
             e.record(torch.cuda.current_stream(dev))
             self._events.append((name, e))
 
-    def extract_features(self, src_pts, tgt_pts, starts=None):
+    def extract_features(self, src_pts, tgt_pts, starts=None, concurrent=False):
         """First half of forward(): feature extraction of both clouds (deepVCP.py:29,72). Returns the
         state match() continues from. Split out so that a stream of batches can run this half (few SMs,
         long) beside the second half of the previous batch (pipeline.StreamedRegistration)."""
@@ -126,7 +126,7 @@ class DeepVCP(nn.Module):
                 hp = self._side_stream(dev)
                 with torch.cuda.stream(hp):
                     hp.wait_event(ev_index)
-                    _, fps2 = F_.fps_indexed(cloud_cm(both), dev, 2 * B, N, S, st2, index)
+                    _, fps2 = F_.fps_indexed(cloud_cm(both), dev, 2 * B, N, S, st2, index, concurrent=concurrent)
                     ev_fps = torch.cuda.Event()
                     ev_fps.record(hp)
                 feat_orig = F_.sa_layer_all(cloud_cm(both), feat_cloud, D, self._identity(2 * B, N, dev), 2 * B, N,

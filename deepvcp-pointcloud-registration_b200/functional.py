@@ -81,13 +81,13 @@ def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want3
     return o64, o32
 
 
-def fps_indexed(xyz_cloud: Cloud, device, B, N, npoint, start, index, want64=False, want32=True):
+def fps_indexed(xyz_cloud: Cloud, device, B, N, npoint, start, index, want64=False, want32=True, concurrent=False):
     """FPS of float32 clouds whose spatial index is already built (the index is only read)."""
     start = _starts_to_device(start, B, device)
     o64 = torch.empty(B, npoint, dtype=torch.int64, device=device) if want64 else None
     o32 = torch.empty(B, npoint, dtype=torch.int32, device=device) if want32 else None
     check(lib().dvcp_fps_indexed(xyz_cloud, B, N, npoint, ptr(start), ptr(o64), ptr(o32), index.c(),
-                                 stream_ptr(device)), "dvcp_fps_indexed")
+                                 1 if concurrent else 0, stream_ptr(device)), "dvcp_fps_indexed")
     _count(1)
     return o64, o32
 

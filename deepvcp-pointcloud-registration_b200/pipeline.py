@@ -35,6 +35,7 @@ class StreamedRegistration:
         self.done = []         # completion event of every batch submitted since the last collect()
         self.pending = []      # (done event, poses) in submission order
         self.t_init = torch.zeros(1, 3)
+        self.small_sampling_ctas = False   # sampling with half-size CTAs (measured: no gain on B200 at K8)
         self.timing = False    # development: completion events carry timestamps
         self.trace = []
 
@@ -42,6 +43,11 @@ class StreamedRegistration:
         """Enqueue one batch: src, tgt [B,C_in,N], R_init / R_true [B,3,3], t_true [B,3,1] (host or
         device tensors). host_out: optional pinned [B,12] float64 tensor the poses are copied into."""
         k = len(self.done)
+        # The host may run at most depth + 1 batches ahead of the device: beyond that the caching allocator
+        # cannot yet reuse the blocks of finished batches (their stream-use events have not completed), every
+        # batch would get freshly cudaMalloc'ed memory, and the pool would grow with the queue length.
+        if k > self.depth:
+            self.done[k - self.depth - 1].synchronize()
         cur = torch.cuda.current_stream(self.dev)
         to = lambda x: x.to(self.dev, non_blocking=True)
         if self.depth == 1:
@@ -53,7 +59,7 @@ class StreamedRegistration:
         with torch.cuda.stream(fs):
             if self.depth > 1 and k >= self.depth:
                 fs.wait_event(self.done[k - self.depth])      # run ahead by at most `depth` batches
-            fe = self.model.extract_features(to(src), to(tgt), starts)
+            fe = self.model.extract_features(to(src), to(tgt), starts, concurrent=self.small_sampling_ctas)
             Ri, Rt, tt = to(R_init), to(R_true), to(t_true)
             ev_fe = torch.cuda.Event(enable_timing=self.timing)
             ev_fe.record(fs)

@@ -87,9 +87,11 @@ DVCP_API int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, con
 
 /* Same as dvcp_fps for float32 clouds whose spatial index is ALREADY built (dvcp_build_index on
  * the same stream or ordered before this call): the index is consumed, not rewritten, so other
- * kernels may read it concurrently (DeepVCP.forward runs the SA layer beside the sampling). */
+ * kernels may read it concurrently (DeepVCP.forward runs the SA layer beside the sampling).
+ * concurrent != 0: the sampling will share the GPU with other work (a stream of batches): smaller
+ * CTAs that leave most of every SM free, at the price of a longer kernel. Same results. */
 DVCP_API int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
-                     int32_t *out32, dvcp_cloud_index_t index, dvcp_stream_t stream);
+                     int32_t *out32, dvcp_cloud_index_t index, int concurrent, dvcp_stream_t stream);
 
 /* Capacity (slots) of the spatial index of an N-point cloud; 0 = N not indexable. */
 DVCP_API int dvcp_index_capacity(int N);
