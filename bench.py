@@ -206,8 +206,8 @@ def run_ours(args):
     # beside the previous batch and perturb it; the unpipelined per-stage pass above does flush.)
     n_rot = max(2, int(160e6 // (d_src.numel() * 4 + d_tgt.numel() * 4)) + 1)
     rot = [(d_src.clone(), d_tgt.clone()) for _ in range(n_rot)]
-    for i in range(2):
-        pipe.submit(rot[i][0], rot[i][1], d_R, d_R, d_t, starts=starts)
+    for i in range(3 * args.depth + 2):      # steady state of the pipeline AND of the caching allocator's pools
+        pipe.submit(rot[i % n_rot][0], rot[i % n_rot][1], d_R, d_R, d_t, starts=starts)
     pipe.collect()
     if rank == 0:
         sampler.wait_first()
@@ -235,8 +235,8 @@ def run_ours(args):
 
     # ---- e2e leg: pinned host buffers in, poses back in pinned host memory, wall clock ----
     h_poses = [torch.empty(B, 12, dtype=torch.float64).pin_memory() for _ in range(args.steps)]
-    for i in range(2):
-        pipe.submit(h_src, h_tgt, h_R, h_R, h_t, starts=starts, host_out=h_poses[i])
+    for i in range(3 * args.depth + 2):
+        pipe.submit(h_src, h_tgt, h_R, h_R, h_t, starts=starts, host_out=h_poses[i % len(h_poses)])
     pipe.collect()
     barrier()
     t0 = time.perf_counter()

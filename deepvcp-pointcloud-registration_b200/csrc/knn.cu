@@ -124,7 +124,7 @@ knn_kernel(Cloud ref, const float *__restrict__ query, int N, int64_t Q, int K, 
 //   * the K best are one 64-bit key per lane, sorted across the lanes; a visited
 //     bucket (one point per lane) is merged by serial insertion when few points
 //     qualify, else by a bitonic sort + merge.
-constexpr int KNI_WARPS = 8;
+constexpr int KNI_WARPS = 4;
 
 __device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
