@@ -150,7 +150,8 @@ cpg_softmax_vcp_kernel(const float *__restrict__ logits, const float *__restrict
 // registers across the two halves (thread = 4 consecutive z voxels x 16 output
 // channels: per (dx, dy, cin) 6 input LDS + 12 broadcast LDS.128 of weights feed 192
 // FMAs), its output overwrites the volume, conv2 / conv3 / softmax follow in place.
-constexpr int CF_THREADS = 384;
+constexpr int CF_THREADS = 768;   // two threads per (line, z-group): 8 of conv1's 16 output channels each
+constexpr int CF_ITEMS = 384;     // >= G * G * ceil(G / 4) for G <= 11
 constexpr int CF_MAXG = 11;
 
 __device__ __forceinline__ float cf_block_sum(float v, float *red, int tid) {
@@ -194,27 +195,38 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
 
     // thread = (line (x, y), group of 4 z)
     const int NG = (G + 3) >> 2, items = G * G * NG;
-    const bool active = tid < items;
-    const int line = active ? tid / NG : 0, zg = active ? tid - line * NG : 0;
+    const int it = tid % CF_ITEMS, ch = tid / CF_ITEMS;   // ch: which half of conv1's output channels (uniform per warp)
+    const bool active = it < items;
+    const int line = active ? it / NG : 0, zg = active ? it - line * NG : 0;
     const int x = line / G, y = line - x * G, z0 = zg * 4;
     const float *t = tgt + m * 32 * (int64_t)C;
 
-    float acc[4][16];
+    float acc[4][8];
 #pragma unroll
     for (int v = 0; v < 4; ++v)
 #pragma unroll
-        for (int o = 0; o < 16; ++o) acc[v][o] = __ldg(p.b1 + o);
+        for (int o = 0; o < 8; ++o) acc[v][o] = __ldg(p.b1 + ch * 8 + o);
 
     for (int half = 0; half < 2; ++half) {
         __syncthreads();   // weights / s_src staged; the previous half's reads of A are finished
         // cost[c', f'] = (src[f'] - T'[c', f'])^2 with c' * 32 + f' = the element's position in the
         // LOGICAL row-major [32, C] order (quirk Q4). Memory is walked in its own order (coalesced).
-        for (int e = tid; e < 32 * C; e += CF_THREADS) {
-            const int L = layout == 0 ? e : (e & 31) * C + (e >> 5);
-            const int f = L & 31, c = L >> 5;
-            if ((f >> 4) == half) {
-                const float d = s_src[f] - __ldg(t + e);
-                A[(f & 15) * Cp + c] = d * d;
+        for (int e0 = tid; e0 < 32 * C; e0 += CF_THREADS * 8) {   // 8 loads in flight per thread
+            float tv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * CF_THREADS;
+                tv[u] = e < 32 * C ? __ldg(t + e) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * CF_THREADS;
+                const int L = layout == 0 ? e : (e & 31) * C + (e >> 5);
+                const int f = L & 31, c = L >> 5;
+                if (e < 32 * C && (f >> 4) == half) {
+                    const float d = s_src[f] - tv[u];
+                    A[(f & 15) * Cp + c] = d * d;
+                }
             }
         }
         __syncthreads();
@@ -227,7 +239,7 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
                     if (yy < 0 || yy >= G) continue;
                     const int tap0 = ((dx + 1) * 3 + (dy + 1)) * 3;
                     const float *col = A + (xx * G + yy) * G + z0 - 1;
-                    const float *wt = W1 + (tap0 * 32 + half * 16) * 16;
+                    const float *wt = W1 + (tap0 * 32 + half * 16) * 16 + ch * 8;
 #pragma unroll 2
                     for (int ci = 0; ci < 16; ++ci) {
                         float in[6];
@@ -240,7 +252,7 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
                         for (int dz = 0; dz < 3; ++dz) {
                             const float4 *w4 = reinterpret_cast<const float4 *>(wt + (dz * 32 + ci) * 16);
 #pragma unroll
-                            for (int o4 = 0; o4 < 4; ++o4) {
+                            for (int o4 = 0; o4 < 2; ++o4) {
                                 const float4 w = w4[o4];
 #pragma unroll
                                 for (int v = 0; v < 4; ++v) {
@@ -263,12 +275,12 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
         for (int v = 0; v < 4; ++v)
             if (z0 + v < G) {
 #pragma unroll
-                for (int o = 0; o < 16; ++o) A[o * Cp + c0 + v] = acc[v][o];
+                for (int o = 0; o < 8; ++o) A[(ch * 8 + o) * Cp + c0 + v] = acc[v][o];
             }
     }
     __syncthreads();
     // ---- conv2 16 -> 4 ----
-    if (active) {
+    if (active && ch == 0) {
         float a2[4][4];
 #pragma unroll
         for (int v = 0; v < 4; ++v)
