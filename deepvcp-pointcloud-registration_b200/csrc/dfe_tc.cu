@@ -273,16 +273,16 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 f[g] = live ? __ldg(reinterpret_cast<const float4 *>(fbase + (int64_t)rid * 32 + chunk * 4))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);   // my neighbour's local coordinates + bias column
+            // raw coordinate loads are issued here, consumed after the weight arithmetic below
+            float px = 0.f, py = 0.f, pz = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
             if (live) {
-                float px, py, pz;
                 if (xyz4) {
                     const float4 pp = __ldg(reinterpret_cast<const float4 *>(txyz.p + (int64_t)b * txyz.bs) + id);
                     px = pp.x; py = pp.y; pz = pp.z;
                 } else {
                     px = txyz.at(b, id, 0); py = txyz.at(b, id, 1); pz = txyz.at(b, id, 2);
                 }
-                loc = make_float4(px - __ldg(cand + gq * 3), py - __ldg(cand + gq * 3 + 1), pz - __ldg(cand + gq * 3 + 2), 1.0f);
+                cx = __ldg(cand + gq * 3); cy = __ldg(cand + gq * 3 + 1); cz = __ldg(cand + gq * 3 + 2);
             }
             // ---- w = dist / sum(dist) in float64 (get_cat_feat_tgt.py:57-58), carried as a float pair: the
             //      product with a float32 feature is then float32(double(f) * w) up to one rounding in 2^-48 ----
@@ -300,6 +300,8 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 wq[0] = *reinterpret_cast<const float4 *>(myw + chunk * 4);
                 wq[1] = *reinterpret_cast<const float4 *>(myw + chunk * 4 + 2);
             }
+            // my neighbour's local coordinates + bias column
+            const float4 loc = live ? make_float4(px - cx, py - cy, pz - cz, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(&empty[s], ph ^ 1);   // MMAs of tile i - TC_STAGES have finished reading stage s
             unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_SW_BYTES;
             unsigned char *thi = ahi + 2 * TC_A_SW_BYTES, *tlo = thi + TC_A_TAIL_BYTES;

@@ -669,3 +669,32 @@ def test_streamed_registration_equals_one_batch_at_a_time(dv, synthetic):
     out = pipe.collect()
     for a, b, h in zip(out, ref, hosts):
         assert torch.equal(a.cpu(), b) and torch.equal(h, b)
+
+
+def test_reference_native_shape_with_normals_vs_oracle(dv, synthetic):
+    """The reference's own operating point (deepVCP.py:76-77, deep_feat_extraction.py:10): N = 10000
+    points WITH normals, r = 1.0, s = 0.4 (6^3 candidates). Exercises the overlapped feature half
+    (cluster FPS, by-bucket SA layer with 6 input channels, row gather) against the CPU oracle."""
+    N = 10000
+    src, tgt, R, t = synthetic.make_batch("modelnet", [21], N)
+    src[:, :3] *= 8.0                       # unit ball -> 8 m: balls of 0.1 m hold a handful of points
+    tgt[:, :3] *= 8.0
+    torch.manual_seed(3)
+    model = dv.DeepVCP(use_normal=True).eval()           # all reference literals: npoint 10000, r 1.0, s 0.4
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    starts = (torch.tensor([17]), torch.tensor([5]), torch.tensor([4242]))
+    ref = stages.deepvcp_forward(sd, src, tgt, R, 1.0, 0.4, starts)
+    model = model.to(DEV)
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True,
+                    topk_override=ref["topk_idx"])
+    L = model.last
+    assert torch.equal(L["src_fps"].cpu().long(), ref["src_fps"]) and torch.equal(L["tgt_fps"].cpu().long(), ref["tgt_fps"])
+    assert rel_err(L["src_fe_feat"].cpu(), ref["src_fe_feat"]) < 1e-5
+    assert rel_err(L["tgt_fe_feat"].cpu(), ref["tgt_fe_feat"]) < 1e-5
+    assert torch.equal(kp.cpu(), ref["src_keypts"])
+    assert torch.equal(L["candidates"].cpu(), ref["candidates"])
+    assert torch.equal(L["knn_idx"].cpu(), ref["knn_idx"])
+    assert (vcp.cpu() - ref["vcp"]).abs().max() < 1e-4
+    R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(1, 3, 1).to(DEV))
+    R2r, t2r, _, _, _ = stages.pose_from_forward(ref["src_keypts"], ref["vcp"], R, t.view(1, 3, 1))
+    assert rot_angle_deg(R2, R2r) < ROT_TOL_DEG and (t2.cpu() - t2r).abs().max() < TRANS_TOL
