@@ -166,22 +166,21 @@ __device__ __forceinline__ float cf_block_sum(float v, float *red, int tid) {
     return t;
 }
 
+constexpr int CF_MAXVPC = 8;   // volumes one CTA works on at a time (small grids)
+
 __global__ void __launch_bounds__(CF_THREADS, 1)
 cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, int layout,
-                 const float *__restrict__ cand, int G, dvcp_cpg_params_t p, float *__restrict__ vcp,
-                 float *__restrict__ logits_out) {
+                 const float *__restrict__ cand, int64_t M, int G, int VPC, dvcp_cpg_params_t p,
+                 float *__restrict__ vcp, float *__restrict__ logits_out) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[CF_THREADS / 32];
-    __shared__ float s_src[32];
-    const int C = G * G * G, Cp = (C + 3) & ~3;
-    float *A = sm;                    // cost volume half [16][Cp], later conv1 output [16][Cp]
-    float *O2 = A + 16 * Cp;          // conv2 output [4][Cp]
-    float *LG = O2 + 4 * Cp;          // logits [Cp]
-    float *W1 = LG + Cp;              // [27][32][16]
+    __shared__ float s_src[CF_MAXVPC][32];
+    const int C = G * G * G, Cp = (C + 3) & ~3, VB = 21 * Cp;
+    float *W1 = sm;                   // [27][32][16]
     float *W2 = W1 + 27 * 32 * 16;    // [27][16][4]
-    float *W3 = W2 + 27 * 16 * 4;     // [27][4]
+    float *W3 = W2 + 27 * 16 * 4;     // [27][4]  (108 floats, padded to 112)
+    float *VOL = W3 + 112;            // per volume: cost half / conv1 out [16][Cp], conv2 out [4][Cp], logits [Cp]
     const int tid = threadIdx.x;
-    const int64_t m = blockIdx.x;
     for (int i = tid; i < 27 * 32 * 16; i += CF_THREADS) {
         const int co = i & 15, ci = (i >> 4) & 31, tap = i >> 9;
         W1[i] = __ldg(p.w1 + (co * 32 + ci) * 27 + tap);
@@ -191,46 +190,110 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
         W2[i] = __ldg(p.w2 + (co * 16 + ci) * 27 + tap);
     }
     for (int i = tid; i < 27 * 4; i += CF_THREADS) W3[i] = __ldg(p.w3 + (i & 3) * 27 + (i >> 2));
-    if (tid < 32) s_src[tid] = __ldg(src + m * 32 + tid);
 
-    // thread = (line (x, y), group of 4 z)
+    // thread = (local volume, line (x, y), group of 4 z, half of conv1's output channels)
     const int NG = (G + 3) >> 2, items = G * G * NG;
-    const int it = tid % CF_ITEMS, ch = tid / CF_ITEMS;   // ch: which half of conv1's output channels (uniform per warp)
-    const bool active = it < items;
-    const int line = active ? it / NG : 0, zg = active ? it - line * NG : 0;
+    const int it = tid % CF_ITEMS, ch = tid / CF_ITEMS;   // ch is uniform per warp
+    const int vl = it / items, item = it - vl * items;
+    const int line = item / NG, zg = item - line * NG;
     const int x = line / G, y = line - x * G, z0 = zg * 4;
-    const float *t = tgt + m * 32 * (int64_t)C;
+    float *A = VOL + (vl < VPC ? vl : 0) * VB, *O2 = A + 16 * Cp;
+    const float b3 = __ldg(p.b3);
 
-    float acc[4][8];
+    for (int64_t m0 = (int64_t)blockIdx.x * VPC; m0 < M; m0 += (int64_t)gridDim.x * VPC) {
+        const int nv = (int)(M - m0 < VPC ? M - m0 : VPC);   // volumes of this round
+        const bool active = vl < nv;
+        __syncthreads();   // weights staged / the previous round is finished with the shared volumes
+        if (tid < 32 * nv) s_src[tid >> 5][tid & 31] = __ldg(src + (m0 + (tid >> 5)) * 32 + (tid & 31));
+        float acc[4][8];
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
+        for (int v = 0; v < 4; ++v)
 #pragma unroll
-        for (int o = 0; o < 8; ++o) acc[v][o] = __ldg(p.b1 + ch * 8 + o);
+            for (int o = 0; o < 8; ++o) acc[v][o] = __ldg(p.b1 + ch * 8 + o);
 
-    for (int half = 0; half < 2; ++half) {
-        __syncthreads();   // weights / s_src staged; the previous half's reads of A are finished
-        // cost[c', f'] = (src[f'] - T'[c', f'])^2 with c' * 32 + f' = the element's position in the
-        // LOGICAL row-major [32, C] order (quirk Q4). Memory is walked in its own order (coalesced).
-        for (int e0 = tid; e0 < 32 * C; e0 += CF_THREADS * 8) {   // 8 loads in flight per thread
-            float tv[8];
+        for (int half = 0; half < 2; ++half) {
+            __syncthreads();   // s_src staged; the previous half's reads of the cost volumes are finished
+            // cost[c', f'] = (src[f'] - T'[c', f'])^2 with c' * 32 + f' = the element's position in the
+            // LOGICAL row-major [32, C] order (quirk Q4). Memory is walked in its own order (coalesced).
+            for (int v = 0; v < nv; ++v) {
+                const float *t = tgt + (m0 + v) * 32 * (int64_t)C;
+                float *Av = VOL + v * VB;
+                for (int e0 = tid; e0 < 32 * C; e0 += CF_THREADS * 8) {   // 8 loads in flight per thread
+                    float tv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * CF_THREADS;
-                tv[u] = e < 32 * C ? __ldg(t + e) : 0.f;
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = e0 + u * CF_THREADS;
+                        tv[u] = e < 32 * C ? __ldg(t + e) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int e = e0 + u * CF_THREADS;
+                        const int L = layout == 0 ? e : (e & 31) * C + (e >> 5);
+                        const int f = L & 31, c = L >> 5;
+                        if (e < 32 * C && (f >> 4) == half) {
+                            const float d = s_src[v][f] - tv[u];
+                            Av[(f & 15) * Cp + c] = d * d;
+                        }
+                    }
+                }
             }
+            __syncthreads();
+            if (active) {
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = x + dx;
+                    if (xx < 0 || xx >= G) continue;
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int yy = y + dy;
+                        if (yy < 0 || yy >= G) continue;
+                        const int tap0 = ((dx + 1) * 3 + (dy + 1)) * 3;
+                        const float *col = A + (xx * G + yy) * G + z0 - 1;
+                        const float *wt = W1 + (tap0 * 32 + half * 16) * 16 + ch * 8;
+#pragma unroll 2
+                        for (int ci = 0; ci < 16; ++ci) {
+                            float in[6];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * CF_THREADS;
-                const int L = layout == 0 ? e : (e & 31) * C + (e >> 5);
-                const int f = L & 31, c = L >> 5;
-                if (e < 32 * C && (f >> 4) == half) {
-                    const float d = s_src[f] - tv[u];
-                    A[(f & 15) * Cp + c] = d * d;
+                            for (int k = 0; k < 6; ++k) {
+                                const int z = z0 - 1 + k;
+                                in[k] = (z >= 0 && z < G) ? col[ci * Cp + k] : 0.f;
+                            }
+#pragma unroll
+                            for (int dz = 0; dz < 3; ++dz) {
+                                const float4 *w4 = reinterpret_cast<const float4 *>(wt + (dz * 32 + ci) * 16);
+#pragma unroll
+                                for (int o4 = 0; o4 < 2; ++o4) {
+                                    const float4 w = w4[o4];
+#pragma unroll
+                                    for (int v = 0; v < 4; ++v) {
+                                        acc[v][4 * o4] = fmaf(w.x, in[v + dz], acc[v][4 * o4]);
+                                        acc[v][4 * o4 + 1] = fmaf(w.y, in[v + dz], acc[v][4 * o4 + 1]);
+                                        acc[v][4 * o4 + 2] = fmaf(w.z, in[v + dz], acc[v][4 * o4 + 2]);
+                                        acc[v][4 * o4 + 3] = fmaf(w.w, in[v + dz], acc[v][4 * o4 + 3]);
+                                    }
+                                }
+                            }
+                        }
+                    }
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // every read of the cost volumes is done: they become conv1's output [16][Cp]
         if (active) {
+            const int c0 = (x * G + y) * G + z0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                if (z0 + v < G) {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) A[(ch * 8 + o) * Cp + c0 + v] = acc[v][o];
+                }
+        }
+        __syncthreads();
+        // ---- conv2 16 -> 4 ----
+        if (active && ch == 0) {
+            float a2[4][4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) a2[v][o] = __ldg(p.b2 + o);
             for (int dx = -1; dx <= 1; ++dx) {
                 const int xx = x + dx;
                 if (xx < 0 || xx >= G) continue;
@@ -239,8 +302,7 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
                     if (yy < 0 || yy >= G) continue;
                     const int tap0 = ((dx + 1) * 3 + (dy + 1)) * 3;
                     const float *col = A + (xx * G + yy) * G + z0 - 1;
-                    const float *wt = W1 + (tap0 * 32 + half * 16) * 16 + ch * 8;
-#pragma unroll 2
+#pragma unroll 4
                     for (int ci = 0; ci < 16; ++ci) {
                         float in[6];
 #pragma unroll
@@ -250,138 +312,90 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
                         }
 #pragma unroll
                         for (int dz = 0; dz < 3; ++dz) {
-                            const float4 *w4 = reinterpret_cast<const float4 *>(wt + (dz * 32 + ci) * 16);
+                            const float4 w = *reinterpret_cast<const float4 *>(W2 + ((tap0 + dz) * 16 + ci) * 4);
 #pragma unroll
-                            for (int o4 = 0; o4 < 2; ++o4) {
-                                const float4 w = w4[o4];
-#pragma unroll
-                                for (int v = 0; v < 4; ++v) {
-                                    acc[v][4 * o4] = fmaf(w.x, in[v + dz], acc[v][4 * o4]);
-                                    acc[v][4 * o4 + 1] = fmaf(w.y, in[v + dz], acc[v][4 * o4 + 1]);
-                                    acc[v][4 * o4 + 2] = fmaf(w.z, in[v + dz], acc[v][4 * o4 + 2]);
-                                    acc[v][4 * o4 + 3] = fmaf(w.w, in[v + dz], acc[v][4 * o4 + 3]);
-                                }
+                            for (int v = 0; v < 4; ++v) {
+                                a2[v][0] = fmaf(w.x, in[v + dz], a2[v][0]);
+                                a2[v][1] = fmaf(w.y, in[v + dz], a2[v][1]);
+                                a2[v][2] = fmaf(w.z, in[v + dz], a2[v][2]);
+                                a2[v][3] = fmaf(w.w, in[v + dz], a2[v][3]);
                             }
                         }
                     }
                 }
             }
+            const int c0 = (x * G + y) * G + z0;
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                if (z0 + v < G) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) O2[o * Cp + c0 + v] = a2[v][o];
+                }
         }
-    }
-    __syncthreads();   // every read of the cost volume is done: A becomes conv1's output [16][Cp]
-    if (active) {
-        const int c0 = (x * G + y) * G + z0;
+        __syncthreads();
+        // ---- conv3 4 -> 1: thread per voxel of every volume of the round ----
+        for (int i = tid; i < nv * C; i += CF_THREADS) {
+            const int v = i / C, c = i - v * C;
+            const float *O2v = VOL + v * VB + 16 * Cp;
+            const int iz = c % G, iy = (c / G) % G, ix = c / (G * G);
+            float a3 = b3;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = ix + dx;
+                if (xx < 0 || xx >= G) continue;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = iy + dy;
+                    if (yy < 0 || yy >= G) continue;
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-            if (z0 + v < G) {
-#pragma unroll
-                for (int o = 0; o < 8; ++o) A[(ch * 8 + o) * Cp + c0 + v] = acc[v][o];
-            }
-    }
-    __syncthreads();
-    // ---- conv2 16 -> 4 ----
-    if (active && ch == 0) {
-        float a2[4][4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-#pragma unroll
-            for (int o = 0; o < 4; ++o) a2[v][o] = __ldg(p.b2 + o);
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= G) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int yy = y + dy;
-                if (yy < 0 || yy >= G) continue;
-                const int tap0 = ((dx + 1) * 3 + (dy + 1)) * 3;
-                const float *col = A + (xx * G + yy) * G + z0 - 1;
-#pragma unroll 4
-                for (int ci = 0; ci < 16; ++ci) {
-                    float in[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const int z = z0 - 1 + k;
-                        in[k] = (z >= 0 && z < G) ? col[ci * Cp + k] : 0.f;
-                    }
-#pragma unroll
-                    for (int dz = 0; dz < 3; ++dz) {
-                        const float4 w = *reinterpret_cast<const float4 *>(W2 + ((tap0 + dz) * 16 + ci) * 4);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            a2[v][0] = fmaf(w.x, in[v + dz], a2[v][0]);
-                            a2[v][1] = fmaf(w.y, in[v + dz], a2[v][1]);
-                            a2[v][2] = fmaf(w.z, in[v + dz], a2[v][2]);
-                            a2[v][3] = fmaf(w.w, in[v + dz], a2[v][3]);
-                        }
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        const int zz = iz + dz;
+                        if (zz < 0 || zz >= G) continue;
+                        const int tap = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
+                        const float4 w = *reinterpret_cast<const float4 *>(W3 + tap * 4);
+                        const int cc = (xx * G + yy) * G + zz;
+                        a3 = fmaf(w.x, O2v[cc], a3);
+                        a3 = fmaf(w.y, O2v[Cp + cc], a3);
+                        a3 = fmaf(w.z, O2v[2 * Cp + cc], a3);
+                        a3 = fmaf(w.w, O2v[3 * Cp + cc], a3);
                     }
                 }
             }
+            VOL[v * VB + 20 * Cp + c] = a3;
+            if (logits_out) logits_out[(m0 + v) * C + c] = a3;
         }
-        const int c0 = (x * G + y) * G + z0;
+        __syncthreads();
+        // ---- softmax over the C voxels + weighted candidate sum, volume after volume ----
+        for (int v = 0; v < nv; ++v) {
+            const float *LG = VOL + v * VB + 20 * Cp;
+            float mx = -INFINITY;
+            for (int c = tid; c < C; c += CF_THREADS) mx = fmaxf(mx, LG[c]);
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-            if (z0 + v < G) {
+            for (int s = 16; s; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+            __syncthreads();
+            if ((tid & 31) == 0) red[tid >> 5] = mx;
+            __syncthreads();
+            mx = red[0];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) O2[o * Cp + c0 + v] = a2[v][o];
+            for (int w = 1; w < CF_THREADS / 32; ++w) mx = fmaxf(mx, red[w]);
+            float zp = 0.f;
+            for (int c = tid; c < C; c += CF_THREADS) zp += expf(LG[c] - mx);
+            const float Z = cf_block_sum(zp, red, tid);
+            const float *cp = cand + (m0 + v) * C * 3;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = tid; c < C; c += CF_THREADS) {
+                const float w = expf(LG[c] - mx) / Z;
+                a[0] = fmaf(w, __ldg(cp + 3 * c), a[0]);
+                a[1] = fmaf(w, __ldg(cp + 3 * c + 1), a[1]);
+                a[2] = fmaf(w, __ldg(cp + 3 * c + 2), a[2]);
+                a[3] += w;
             }
-    }
-    __syncthreads();
-    // ---- conv3 4 -> 1: thread per voxel ----
-    const float b3 = __ldg(p.b3);
-    for (int c = tid; c < C; c += CF_THREADS) {
-        const int iz = c % G, iy = (c / G) % G, ix = c / (G * G);
-        float a3 = b3;
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = ix + dx;
-            if (xx < 0 || xx >= G) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int yy = iy + dy;
-                if (yy < 0 || yy >= G) continue;
-#pragma unroll
-                for (int dz = -1; dz <= 1; ++dz) {
-                    const int zz = iz + dz;
-                    if (zz < 0 || zz >= G) continue;
-                    const int tap = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
-                    const float4 w = *reinterpret_cast<const float4 *>(W3 + tap * 4);
-                    const int cc = (xx * G + yy) * G + zz;
-                    a3 = fmaf(w.x, O2[cc], a3);
-                    a3 = fmaf(w.y, O2[Cp + cc], a3);
-                    a3 = fmaf(w.z, O2[2 * Cp + cc], a3);
-                    a3 = fmaf(w.w, O2[3 * Cp + cc], a3);
-                }
+            const float sx = cf_block_sum(a[0], red, tid), sy = cf_block_sum(a[1], red, tid),
+                        sz = cf_block_sum(a[2], red, tid), sw = cf_block_sum(a[3], red, tid);
+            if (tid == 0) {
+                vcp[(m0 + v) * 3] = sx / sw;
+                vcp[(m0 + v) * 3 + 1] = sy / sw;
+                vcp[(m0 + v) * 3 + 2] = sz / sw;
             }
         }
-        LG[c] = a3;
-        if (logits_out) logits_out[m * C + c] = a3;
-    }
-    __syncthreads();
-    // ---- softmax over the C voxels + weighted candidate sum ----
-    float mx = -INFINITY;
-    for (int c = tid; c < C; c += CF_THREADS) mx = fmaxf(mx, LG[c]);
-#pragma unroll
-    for (int s = 16; s; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-#pragma unroll
-    for (int w = 1; w < CF_THREADS / 32; ++w) mx = fmaxf(mx, red[w]);
-    float zp = 0.f;
-    for (int c = tid; c < C; c += CF_THREADS) zp += expf(LG[c] - mx);
-    const float Z = cf_block_sum(zp, red, tid);
-    const float *cp = cand + m * C * 3;
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = tid; c < C; c += CF_THREADS) {
-        const float w = expf(LG[c] - mx) / Z;
-        a[0] = fmaf(w, __ldg(cp + 3 * c), a[0]);
-        a[1] = fmaf(w, __ldg(cp + 3 * c + 1), a[1]);
-        a[2] = fmaf(w, __ldg(cp + 3 * c + 2), a[2]);
-        a[3] += w;
-    }
-    const float sx = cf_block_sum(a[0], red, tid), sy = cf_block_sum(a[1], red, tid), sz = cf_block_sum(a[2], red, tid),
-                sw = cf_block_sum(a[3], red, tid);
-    if (tid == 0) {
-        vcp[m * 3] = sx / sw;
-        vcp[m * 3 + 1] = sy / sw;
-        vcp[m * 3 + 2] = sz / sw;
     }
 }
 
@@ -405,9 +419,15 @@ extern "C" int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, 
     const int C = G * G * G;
     if (G <= CF_MAXG) {
         const int Cp = (C + 3) & ~3;
-        const int smem = (21 * Cp + 27 * 32 * 16 + 27 * 16 * 4 + 27 * 4) * (int)sizeof(float);
+        const int items = G * G * ((G + 3) / 4);
+        int VPC = CF_ITEMS / items;          // volumes per CTA round: all 384 item threads busy on small grids
+        if (VPC > CF_MAXVPC) VPC = CF_MAXVPC;
+        if (VPC < 1) VPC = 1;
+        const int smem = (27 * 32 * 16 + 27 * 16 * 4 + 112 + VPC * 21 * Cp) * (int)sizeof(float);
         DVCP_CUDA(cudaFuncSetAttribute(cpg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        cpg_fused_kernel<<<(unsigned)M, CF_THREADS, smem, st>>>(src_dfe, tgt_dfe, layout, cand, G, p, vcp, logits);
+        int64_t grid = (M + VPC - 1) / VPC;
+        if (VPC > 1 && grid > DVCP_NUM_SMS) grid = DVCP_NUM_SMS;   // persistent over rounds: weights staged once
+        cpg_fused_kernel<<<(unsigned)grid, CF_THREADS, smem, st>>>(src_dfe, tgt_dfe, layout, cand, M, G, VPC, p, vcp, logits);
         DVCP_CHECK_LAUNCH();
         return 0;
     }
