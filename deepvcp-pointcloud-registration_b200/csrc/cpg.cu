@@ -422,6 +422,7 @@ extern "C" int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, 
         const int items = G * G * ((G + 3) / 4);
         int VPC = CF_ITEMS / items;          // volumes per CTA round: all 384 item threads busy on small grids
         if (VPC > CF_MAXVPC) VPC = CF_MAXVPC;
+        if ((int64_t)VPC * DVCP_NUM_SMS > M) VPC = (int)(M / DVCP_NUM_SMS);   // few volumes: one CTA each first
         if (VPC < 1) VPC = 1;
         const int smem = (27 * 32 * 16 + 27 * 16 * 4 + 112 + VPC * 21 * Cp) * (int)sizeof(float);
         DVCP_CUDA(cudaFuncSetAttribute(cpg_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
