@@ -5,10 +5,11 @@
 //   volume [32, G, G, G] -> Conv3d 32->16 -> 16->4 -> 4->1 (k=3, pad=1, bias, no
 //   activation) -> softmax over the C voxels -> vcp = sum w_c cand_c / sum w_c.
 //
-// v1: one thread per output voxel and layer; activations travel through an
-// L2-resident workspace laid out [M][channel][voxel] so that neighbouring threads
-// read neighbouring addresses; weights are re-ordered in shared memory to
-// [tap][cin][cout] so one LDS.128 feeds four FMAs.
+// Two paths: up to 11^3 voxels the whole chain runs in ONE kernel with the volume in
+// shared memory (cpg_fused_kernel below); larger grids use one kernel per layer (one
+// thread per output voxel; activations travel through an L2-resident workspace laid
+// out [M][channel][voxel]; weights re-ordered in shared memory to [tap][cin][cout] so
+// one LDS.128 feeds four FMAs).
 #include "common.cuh"
 
 namespace dvcp {

@@ -8,7 +8,7 @@
 // 0-based. The order is made total by the 64-bit key (bits(d2) << 32 | index), so
 // the result does not depend on the order points are visited in.
 //
-// v1 kernel: the reference cloud is staged tile by tile into shared memory as
+// Brute-force kernel (any N): the reference cloud is staged tile by tile into shared memory as
 // x[], y[], z[] (coalesced loads, conflict-free LDS); each warp owns KNN_QPW
 // queries and keeps each query's current K best as ONE key per lane, sorted
 // across the lanes. A step evaluates 32 points; lanes whose key beats the current
