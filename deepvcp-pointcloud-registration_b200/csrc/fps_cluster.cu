@@ -28,6 +28,7 @@ namespace dvcp {
 
 #ifdef DVCP_FPS_TIMING
 __device__ long long g_fc_time[24];
+__device__ int g_fc_smid[1024];
 #define FC_TICK(slot)                                                   \
     do {                                                                \
         if (blockIdx.x == 0 && tid == 0) {                              \
@@ -147,6 +148,7 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     int produced = 0;
 #ifdef DVCP_FPS_TIMING
     long long t_last__ = clock64();
+    if (tid == 0 && blockIdx.x < 1024) { unsigned sid; asm volatile("mov.u32 %0, %%smid;" : "=r"(sid)); g_fc_smid[blockIdx.x] = (int)sid; }
     if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 24; ++i) g_fc_time[i] = 0;
 #endif
     for (int step = 0;; ++step) {
@@ -501,6 +503,9 @@ int dvcp_fps_cluster_launch(dvcp_cloud_t xyz, dvcp_cloud_index_t index, int B, i
 }
 
 #ifdef DVCP_FPS_TIMING
+extern "C" __attribute__((visibility("default"))) int dvcp_debug_fps_smid(int *host1024) {
+    return (int)cudaMemcpyFromSymbol(host1024, dvcp::g_fc_smid, 1024 * sizeof(int));
+}
 extern "C" __attribute__((visibility("default"))) int dvcp_debug_fps_timing(long long *host16) {
     return (int)cudaMemcpyFromSymbol(host16, dvcp::g_fc_time, 24 * sizeof(long long));
 }

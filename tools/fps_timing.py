@@ -24,3 +24,9 @@ tot = sum(buf[:16])
 for n, v in zip(names, buf):
     print("%-18s %12d %5.1f%%" % (n, v, 100.0 * v / tot))
 print("total cycles", tot, "steps", buf[16], "sum n", buf[17], "sum A", buf[18], "sum local cnt", buf[19], "n>CAP", buf[20])
+
+sm = (ctypes.c_int * 1024)()
+L.dvcp_debug_fps_smid.argtypes = [ctypes.c_void_p]
+L.dvcp_debug_fps_smid(sm)
+ids = list(sm)[:16 * 8]
+print("SMs used by the 128 sampling CTAs:", len(set(ids)), "distinct; per cluster:", [sorted(ids[c * 8:c * 8 + 8]) for c in range(4)])
