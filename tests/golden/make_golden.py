@@ -105,6 +105,65 @@ def forward_case(name, kind, n_points, r, s, model_seed, rng_seed, pair_id=0, st
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def native_case(name="fwd_reference_native_n10000_g6", pair_id=5, model_seed=4, rng_seed=12, stride=16):
+    """The reference at its OWN operating point: all literals as shipped (npoint = 10000, radius 0.1,
+    nsample 256, r = 1.0, s = 0.4 -> 6^3 candidates, use_normal=True), no (r, s) shim. The clouds are
+    regenerated from (kind, pair_id, n_points) by the tests; big tensors are stored as a strided sample
+    plus an order-sensitive checksum."""
+    n_points = 10000
+    src, tgt, R, t = syn.make_batch("modelnet", [pair_id], n_points)
+    model = rs.make_model(True, n_points, seed=model_seed)
+    m = rs.load()
+    pu = m.pointnet2_utils
+    fps_log, ball_log = [], []
+    orig_fps, orig_ball = pu.farthest_point_sample, pu.query_ball_point
+
+    def fps(xyz, npoint):
+        out = orig_fps(xyz, npoint)
+        fps_log.append(out.clone())
+        return out
+
+    def ball(radius, nsample, xyz, new_xyz):
+        out = orig_ball(radius, nsample, xyz, new_xyz)
+        ball_log.append(out.clone())
+        return out
+
+    pu.farthest_point_sample, pu.query_ball_point = fps, ball
+    rec = {}
+    try:
+        torch.manual_seed(rng_seed)
+        kp, vcp = rs.forward(model, src, tgt, R, torch.zeros(1, 3), 1.0, 0.4, rec)
+    finally:
+        pu.farthest_point_sample, pu.query_ball_point = orig_fps, orig_ball
+    with rs.quiet():
+        x = kp.permute(0, 2, 1).double()
+        y = vcp.permute(0, 2, 1).double()
+        R2, t2, x1, y2 = m.deepVCP_loss.svd_optimization(x, y, R, t.view(1, 3, 1))
+    out = {
+        "kind": "modelnet", "pair_id": pair_id, "n_points": n_points, "r": 1.0, "s": 0.4, "stride": stride,
+        "R": npy(R), "t": npy(t),
+        "starts": np.array([int(fps_log[0][0, 0]), int(fps_log[1][0, 0]), int(fps_log[2][0, 0])]),
+        "src_fps": npy(fps_log[0]).astype(np.int16), "tgt_fps": npy(fps_log[2]).astype(np.int16),
+        "kp_fps": npy(fps_log[1]).astype(np.int16),
+        "src_ball_checksum": checksum(npy(ball_log[0])), "tgt_ball_checksum": checksum(npy(ball_log[2])),
+        "src_ball_s": npy(ball_log[0][:, ::250]).astype(np.int16),
+        "src_fe_feat_s": npy(rec["src_fe_feat"][:, ::stride]), "tgt_fe_feat_s": npy(rec["tgt_fe_feat"][:, ::stride]),
+        "topk_idx": npy(rec["topk_idx"]).astype(np.int32),
+        "src_keypts_full": npy(rec["src_keypts_full"]),
+        "picked_idx": npy(rec["picked_idx"]).astype(np.int16),
+        "centres": npy(rec["centres"]),
+        "candidates_s": npy(rec["candidates"][:, ::4]),
+        "src_dfe": npy(rec["src_dfe"]),
+        "tgt_dfe_s": npy(rec["tgt_dfe"].permute(0, 1, 3, 2)[:, :, ::stride]),
+        "vcp": npy(vcp), "src_keypts": npy(kp), "R2": npy(R2), "t2": npy(t2),
+    }
+    for k, v in model.state_dict().items():
+        out["sd/" + k] = npy(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def primitives_case():
     """Small calls of the L1 primitives and the standalone modules."""
     m = rs.load()
@@ -185,7 +244,11 @@ def primitives_case():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "native":
+        native_case()
+        sys.exit(0)
     primitives_case()
+    native_case()
     forward_case("fwd_modelnet_n1024_g5", "modelnet", 1024, 0.8, 0.4, model_seed=0, rng_seed=7)
     forward_case("fwd_modelnet_n512_g6", "modelnet", 512, 1.0, 0.4, model_seed=1, rng_seed=8, pair_id=3)
     forward_case("fwd_kitti_n2048_g7", "kitti", 2048, syn.grid_radius(7), 0.4, model_seed=2, rng_seed=9,

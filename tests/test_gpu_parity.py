@@ -698,3 +698,39 @@ def test_reference_native_shape_with_normals_vs_oracle(dv, synthetic):
     R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(1, 3, 1).to(DEV))
     R2r, t2r, _, _, _ = stages.pose_from_forward(ref["src_keypts"], ref["vcp"], R, t.view(1, 3, 1))
     assert rot_angle_deg(R2, R2r) < ROT_TOL_DEG and (t2.cpu() - t2r).abs().max() < TRANS_TOL
+
+
+def test_forward_vs_reference_record_at_native_operating_point(dv, synthetic):
+    """CUDA path against the record of the UNMODIFIED reference with all its literals as shipped
+    (tests/golden/make_golden.py:native_case: N = 10000 with normals, radius 0.1 / nsample 256,
+    r = 1.0, s = 0.4 -> 6^3 candidates). Indices bit-exact, features 1e-5, pose within the north-star bar."""
+    g = load_golden("fwd_reference_native_n10000_g6")
+    N = int(g["n_points"])
+    src, tgt, R, t = synthetic.make_batch(str(g["kind"]), [int(g["pair_id"])], N)
+    model = dv.DeepVCP(use_normal=True)                   # reference literals
+    model.load_state_dict(golden_state_dict(g))
+    model = model.to(DEV).eval()
+    starts = tuple(torch.tensor([int(v)]) for v in g["starts"])
+    ref_topk = T(g["topk_idx"]).long().view(1, -1)
+    model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True)
+    sc = model.last["scores"][0].cpu()
+    assert torch.allclose(sc[model.last["topk_idx"][0].cpu()], sc[ref_topk[0]], rtol=1e-6, atol=0)
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True,
+                    topk_override=ref_topk)
+    L = model.last
+    assert torch.equal(L["src_fps"].cpu().to(torch.int16), T(g["src_fps"]))
+    assert torch.equal(L["tgt_fps"].cpu().to(torch.int16), T(g["tgt_fps"]))
+    assert torch.equal(L["picked_idx"].cpu().to(torch.int16), T(g["picked_idx"]))
+    assert torch.equal(L["src_keypts_full"].cpu(), T(g["src_keypts_full"]))
+    s = int(g["stride"])
+    assert rel_err(L["src_fe_feat"][:, ::s], T(g["src_fe_feat_s"])) < 1e-5
+    assert rel_err(L["tgt_fe_feat"][:, ::s], T(g["tgt_fe_feat_s"])) < 1e-5
+    assert torch.allclose(L["centres"].cpu(), T(g["centres"]), rtol=0, atol=1e-12)
+    assert torch.allclose(L["candidates"].cpu().view(1, 64, -1, 3)[:, ::4], T(g["candidates_s"]), rtol=0, atol=4e-6)
+    assert rel_err(L["src_dfe"], T(g["src_dfe"]).squeeze(2)) < 1e-5
+    assert rel_err(L["tgt_dfe"][:, :, ::s], T(g["tgt_dfe_s"])) < 1e-5
+    assert torch.equal(kp.cpu(), T(g["src_keypts"]))
+    assert (vcp.cpu() - T(g["vcp"])).abs().max() < 2e-5
+    R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(1, 3, 1).to(DEV))
+    assert rot_angle_deg(R2, T(g["R2"])) < ROT_TOL_DEG
+    assert (t2.cpu() - T(g["t2"])).abs().max() < TRANS_TOL

@@ -167,3 +167,51 @@ def test_fe_ball_query_against_reference_record(name):
     new_xyz = stages.index_points(xyz, fps)
     idx = stages.query_ball_point(0.1, 256, xyz, new_xyz)
     assert torch.equal(idx.to(torch.int16), T(g["src_ball"]))
+
+
+def _checksum(a):
+    """tests/golden/make_golden.py:checksum restated (order-sensitive, wrap-around)."""
+    v = np.ascontiguousarray(a).astype(np.int64).reshape(-1)
+    w = (np.arange(v.size, dtype=np.int64) * np.int64(2654435761)) ^ np.int64(0x9E3779B97F4A7C15 - (1 << 64))
+    with np.errstate(over="ignore"):
+        return np.int64(np.sum((v + 1) * (w | 1), dtype=np.int64))
+
+
+def test_forward_at_the_reference_native_operating_point(synthetic):
+    """The reference with every literal as shipped (deepVCP.py:76-77, deep_feat_extraction.py:10:
+    npoint 10000, radius 0.1, nsample 256, r 1.0, s 0.4 -> 6^3 candidates, use_normal=True).
+    Big tensors of the record are strided samples plus checksums; the clouds are regenerated."""
+    g = load_golden("fwd_reference_native_n10000_g6")
+    sd = golden_state_dict(g)
+    N = int(g["n_points"])
+    src, tgt, R, t = synthetic.make_batch(str(g["kind"]), [int(g["pair_id"])], N)
+    assert torch.equal(R, T(g["R"])) and torch.equal(t, T(g["t"]))
+    st = g["starts"]
+    starts = (torch.tensor([st[0]]), torch.tensor([st[1]]), torch.tensor([st[2]]))
+    ref_topk = T(g["topk_idx"]).long().view(1, -1)
+    o = stages.deepvcp_forward(sd, src, tgt, R, float(g["r"]), float(g["s"]), starts, topk_override=ref_topk)
+    assert_topk_equivalent(o["scores"][0], stages.topk_indices(o["scores"], 64)[0], ref_topk[0])
+    assert torch.equal(o["src_fps"].to(torch.int16), T(g["src_fps"]))
+    assert torch.equal(o["tgt_fps"].to(torch.int16), T(g["tgt_fps"]))
+    assert torch.equal(o["kp_fps"].to(torch.int16), T(g["kp_fps"]))
+    assert torch.equal(o["picked_idx"].to(torch.int16), T(g["picked_idx"]))
+    assert torch.equal(o["centres"], T(g["centres"]))
+    assert torch.equal(o["src_keypts_full"], T(g["src_keypts_full"]))
+    assert torch.equal(o["candidates"].view(1, 64, -1, 3)[:, ::4], T(g["candidates_s"]))
+    # ball query of the FE layer (10000 x 256 indices per cloud): checksum + sample
+    for side, cloud in (("src", src), ("tgt", tgt)):
+        xyz = cloud[:, :3].permute(0, 2, 1).contiguous()
+        idx = stages.query_ball_point(0.1, 256, xyz, stages.index_points(xyz, o[side + "_fps"]))
+        assert _checksum(idx.numpy()) == g[side + "_ball_checksum"]
+        if side == "src":
+            assert torch.equal(idx[:, ::250].to(torch.int16), T(g["src_ball_s"]))
+    s = int(g["stride"])
+    assert torch.allclose(o["src_fe_feat"][:, ::s], T(g["src_fe_feat_s"]), atol=1e-6)
+    assert torch.allclose(o["tgt_fe_feat"][:, ::s], T(g["tgt_fe_feat_s"]), atol=1e-6)
+    assert torch.allclose(o["src_dfe"], T(g["src_dfe"]).squeeze(2), atol=1e-5)
+    assert torch.allclose(o["tgt_dfe"][:, :, ::s], T(g["tgt_dfe_s"]), atol=1e-5)
+    assert torch.allclose(o["vcp"], T(g["vcp"]), atol=1e-5)
+    assert torch.equal(o["src_keypts"], T(g["src_keypts"]))
+    R2, t2, _, _, _ = stages.pose_from_forward(o["src_keypts"], o["vcp"], R, t.view(1, 3, 1))
+    assert torch.allclose(R2, T(g["R2"]), atol=1e-5)
+    assert torch.allclose(t2, T(g["t2"]), atol=1e-4)
