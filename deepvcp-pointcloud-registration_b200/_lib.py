@@ -47,6 +47,9 @@ SIGNATURES = {
     "dvcp_fps_indexed": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, CloudIndex, c_i32, c_vp]),
     "dvcp_index_capacity": (c_i32, [c_i32]),
     "dvcp_build_index": (c_i32, [Cloud, c_i32, c_i32, CloudIndex, c_vp]),
+    "dvcp_index_capacity_any": (c_i32, [c_i32]),
+    "dvcp_build_index_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "dvcp_build_index_ws": (c_i32, [Cloud, c_i32, c_i32, CloudIndex, c_vp, c_i64, c_vp]),
     "dvcp_fps_plain": (c_i32, [Cloud, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_square_distance": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_ball_query": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp]),

@@ -173,15 +173,34 @@ __device__ __forceinline__ void knn_merge(unsigned long long &list, unsigned lon
     }
 }
 
-// Box of a "super-bucket": lane l owns the T Morton-consecutive buckets l*T .. l*T+T-1.
+// Key of a point for one query: (bits(d2), original index, slot in the sorted table) packed so that
+// unsigned 64-bit order is (d2, index) order. d2 >= +0, so its sign bit is free:
+//   caps <= 65536:  bits(d2) << 32 | index << 16 | slot          (16 + 16 bits)
+//   cap  = 131072:  bits(d2) << 33 | index << 16 | slot >> 1     (17 + 16 bits; the slot is one of
+//                   2h, 2h + 1 and is told apart by the index stored with the point)
+template <bool BIG>
+struct KnnKey {
+    static constexpr int DSH = BIG ? 33 : 32;
+    __device__ __forceinline__ static unsigned long long make(float d2, int id, int pos) {
+        return ((unsigned long long)__float_as_uint(d2) << DSH) | ((unsigned long long)(unsigned)id << 16) |
+               (unsigned)(BIG ? pos >> 1 : pos);
+    }
+    __device__ __forceinline__ static unsigned d2bits(unsigned long long k) { return (unsigned)(k >> DSH); }
+    __device__ __forceinline__ static unsigned id(unsigned long long k) {
+        return BIG ? ((unsigned)(k >> 16) & 0x1ffffu) : ((unsigned)(k & 0xffffffffu) >> 16);
+    }
+};
+
+// Two-level pruning. Level 1 "super-buckets" of TT = min(T, 32) Morton-consecutive buckets; lane l owns
+// the SB = max(T / 32, 1) super-buckets s * 32 + l (T = buckets / 32 = cap / 1024).
 struct Box6 {
     float nx, ny, nz, xx, xy, xz;   // min, max
 };
-__device__ __forceinline__ Box6 load_super_box(const float *box, int T, int lane) {
+__device__ __forceinline__ Box6 load_super_box(const float *box, int TT, int g) {
     Box6 s{INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    for (int t = 0; t < T; ++t) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8) + 1);
+    for (int t = 0; t < TT; ++t) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + t) * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + t) * 8) + 1);
         if (b1.z > 0.f) {
             s.nx = fminf(s.nx, b0.x); s.ny = fminf(s.ny, b0.y); s.nz = fminf(s.nz, b0.z);
             s.xx = fmaxf(s.xx, b0.w); s.xy = fmaxf(s.xy, b1.x); s.xz = fmaxf(s.xz, b1.y);
@@ -208,93 +227,104 @@ struct KnnCtx {
     int K;
 };
 
-// key of point at sorted slot `pos` for query (qx,qy,qz): bits(d2) << 32 | id << 16 | pos
+// key of the point at sorted slot `pos` for query (qx,qy,qz)
+template <bool BIG>
 __device__ __forceinline__ unsigned long long knn_point_key(const float4 *spt, int pos, float qx, float qy, float qz,
                                                             float &d2) {
     const float4 P = __ldg(spt + pos);   // unused slots hold +inf coordinates and id -1
     const int id = __float_as_int(P.w);
     d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
-    return id >= 0 ? (((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned)id << 16) | (unsigned)pos)
-                   : 0xffffffffffffffffull;
+    return id >= 0 ? KnnKey<BIG>::make(d2, id, pos) : 0xffffffffffffffffull;
 }
 
-// the K smallest of `cnt` keys in buf[], ascending across the lanes (lanes >= cnt of the last chunk hold INF)
-__device__ __forceinline__ unsigned long long knn_select_sorted(const unsigned long long *buf, int cnt, int lane) {
-    const unsigned long long INF = 0xffffffffffffffffull;
-    unsigned long long res = INF;
-    for (int g = 0; g < cnt; g += 32) {
-        unsigned long long k = g + lane < cnt ? buf[g + lane] : INF;
-        k = bitonic_sort32(k, lane);
-        if (g == 0) {
-            res = k;
-        } else {
-            const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
-            res = u64min(res, r);
-#pragma unroll
-            for (int j = 16; j > 0; j >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, res, j);
-                res = (lane & j) == 0 ? u64min(res, other) : u64max(res, other);
-            }
-        }
+// key of a point found for an earlier query (its key `old` tells where it is), re-evaluated for this query
+template <bool BIG>
+__device__ __forceinline__ unsigned long long knn_rekey(const float4 *spt, unsigned long long old, float qx, float qy,
+                                                        float qz, float &d2) {
+    if constexpr (!BIG) {
+        return knn_point_key<false>(spt, (int)(old & 0xffffu), qx, qy, qz, d2);
+    } else {
+        const int h = (int)(old & 0xffffu) * 2;
+        const float4 P0 = __ldg(spt + h), P1 = __ldg(spt + h + 1);
+        const bool first = __float_as_int(P0.w) == (int)KnnKey<true>::id(old);
+        const float4 P = first ? P0 : P1;
+        d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+        return KnnKey<true>::make(d2, __float_as_int(P.w), first ? h : h + 1);
     }
-    return res;
 }
 
 // One exact query by one warp. `list`: K points already known (the result of a nearby query; all-INF = none):
-// re-evaluated for this query they bound its K-th distance. sb: this lane's super-box. Returns the K nearest
+// re-evaluated for this query they bound its K-th distance. sb: this lane's super-boxes. Returns the K nearest
 // keys ascending across the lanes (lanes >= K hold INF).
-template <int T>
-__device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const Box6 &sb, float qx, float qy, float qz,
-                                                        unsigned long long list, int lane) {
+template <int T, bool BIG>
+__device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const Box6 (&sb)[(T + 31) / 32], float qx,
+                                                        float qy, float qz, unsigned long long list, int lane) {
+    constexpr int TT = T < 32 ? T : 32;
+    constexpr int SB = (T + 31) / 32;
+    using Key = KnnKey<BIG>;
     const unsigned long long INF = 0xffffffffffffffffull;
     const float *box = c.box;
     const float4 *spt = c.spt;
     unsigned long long *buf = c.buf;
     const int K = c.K;
-    auto point_key = [&](int pos, float qx_, float qy_, float qz_, float &d2) -> unsigned long long {
-        return knn_point_key(spt, pos, qx_, qy_, qz_, d2);
+    auto worst_d2 = [&](unsigned long long w, float none) -> float {
+        return w == INF ? none : __uint_as_float(Key::d2bits(w));
     };
-    const float lbs = box_lb(qx, qy, qz, sb.nx, sb.ny, sb.nz, sb.xx, sb.xy, sb.xz);
+    // lower bound of bucket `lane` of super-bucket g (lanes >= TT: +inf)
+    auto bucket_lb = [&](int g) -> float {
+        float l = INFINITY;
+        if (lane < TT) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + lane) * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + lane) * 8) + 1);
+            if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+        }
+        return l;
+    };
+    float lbs[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) lbs[s] = box_lb(qx, qy, qz, sb[s].nx, sb[s].ny, sb[s].nz, sb[s].xx, sb[s].xy, sb[s].xz);
     // ---- bound thr on the K-th squared distance: K known points, evaluated exactly ----
     float thr;
-    {
-        unsigned long long k0;
+    if (__any_sync(0xffffffffu, list != INF)) {
+        // previous neighbours re-evaluated for this query
         float d2 = 0.f;
-        if (__any_sync(0xffffffffu, list != INF)) {
-            // previous neighbours re-evaluated for this query
-            k0 = (lane < K && list != INF) ? point_key((int)(list & 0xffffu), qx, qy, qz, d2) : 0ull;
-            const unsigned mx = __reduce_max_sync(0xffffffffu, (unsigned)(k0 >> 32));
-            thr = __uint_as_float(mx);
-        } else {
-            thr = INFINITY;   // first query of a chain: best-first streaming search below
-        }
+        const unsigned long long k0 = (lane < K && list != INF) ? knn_rekey<BIG>(spt, list, qx, qy, qz, d2) : 0ull;
+        thr = __uint_as_float(__reduce_max_sync(0xffffffffu, Key::d2bits(k0)));
+    } else {
+        thr = INFINITY;   // first query of a chain: best-first streaming search below
     }
     unsigned long long res = INF;
     if (!(thr < INFINITY)) {
-        // ---- best-first over the bucket groups, streaming merge; exact for any start ----
+        // ---- best-first over the super-buckets, streaming merge; exact for any start ----
         unsigned long long worst = INF;
-        float rem = lbs;   // this lane's group lower bound; +inf once processed
+        float rem[SB];   // this lane's super-bucket lower bounds; +inf once processed
+#pragma unroll
+        for (int s = 0; s < SB; ++s) rem[s] = lbs[s];
         while (true) {
-            const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(rem));
-            const float now = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
-            if (mb == 0x7f800000u || !(__uint_as_float(mb) <= now)) break;
-            const int sl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(rem) == mb)) - 1;
-            if (lane == sl) rem = INFINITY;
-            float l = INFINITY;
-            if (lane < T) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
-                if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-            }
-            // the group's buckets in increasing order of their own bound
+            float rmin = rem[0];
+#pragma unroll
+            for (int s = 1; s < SB; ++s) rmin = fminf(rmin, rem[s]);
+            const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(rmin));
+            if (mb == 0x7f800000u || !(__uint_as_float(mb) <= worst_d2(worst, INFINITY))) break;
+            const int sl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(rmin) == mb)) - 1;
+            int ss = 0;
+#pragma unroll
+            for (int s = SB - 1; s >= 0; --s)
+                if (__float_as_uint(rem[s]) == mb) ss = s;
+            ss = __shfl_sync(0xffffffffu, ss, sl);
+#pragma unroll
+            for (int s = 0; s < SB; ++s)
+                if (lane == sl && s == ss) rem[s] = INFINITY;
+            const int g = ss * 32 + sl;
+            float l = bucket_lb(g);
+            // the super-bucket's buckets in increasing order of their own bound
             while (true) {
                 const unsigned lm = __reduce_min_sync(0xffffffffu, __float_as_uint(l));
-                const float now2 = worst == INF ? INFINITY : __uint_as_float((unsigned)(worst >> 32));
-                if (lm == 0x7f800000u || !(__uint_as_float(lm) <= now2)) break;
+                if (lm == 0x7f800000u || !(__uint_as_float(lm) <= worst_d2(worst, INFINITY))) break;
                 const int bl = __ffs(__ballot_sync(0xffffffffu, __float_as_uint(l) == lm)) - 1;
                 if (lane == bl) l = INFINITY;
                 float d2;
-                const unsigned long long key = point_key((sl * T + bl) * 32 + lane, qx, qy, qz, d2);
+                const unsigned long long key = knn_point_key<BIG>(spt, (g * TT + bl) * 32 + lane, qx, qy, qz, d2);
                 const unsigned m = __ballot_sync(0xffffffffu, key < worst);
                 if (m) knn_merge(res, worst, key, m, K, lane);
             }
@@ -302,31 +332,27 @@ __device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const B
     } else {
     // ---- collect every point with d2 <= thr from the buckets whose box allows it ----
     int cnt = 0;
-    unsigned sm = __ballot_sync(0xffffffffu, lbs <= thr);
-    while (sm) {
-        const int sl = __ffs(sm) - 1;
-        sm &= sm - 1;
-        float l = INFINITY;
-        if (lane < T) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(sl * T + lane) * 8) + 1);
-            if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-        }
-        unsigned bm = __ballot_sync(0xffffffffu, l <= thr);
-        while (bm) {
-            const int j = sl * T + __ffs(bm) - 1;
-            bm &= bm - 1;
-            const int pos = j * 32 + lane;
-            const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never within thr
-            const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
-            const bool qual = d2 <= thr;
-            const unsigned m = __ballot_sync(0xffffffffu, qual);
-            if (m) {
-                const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                if (qual && slot < KNI_BUF)
-                    buf[slot] = ((unsigned long long)__float_as_uint(d2) << 32) |
-                                ((unsigned)__float_as_int(P.w) << 16) | (unsigned)pos;
-                cnt += __popc(m);
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+        unsigned sm = __ballot_sync(0xffffffffu, lbs[s] <= thr);
+        while (sm) {
+            const int g = s * 32 + __ffs(sm) - 1;
+            sm &= sm - 1;
+            const float l = bucket_lb(g);
+            unsigned bm = __ballot_sync(0xffffffffu, l <= thr);
+            while (bm) {
+                const int j = g * TT + __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int pos = j * 32 + lane;
+                const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never within thr
+                const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+                const bool qual = d2 <= thr;
+                const unsigned m = __ballot_sync(0xffffffffu, qual);
+                if (m) {
+                    const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+                    if (qual && slot < KNI_BUF) buf[slot] = Key::make(d2, __float_as_int(P.w), pos);
+                    cnt += __popc(m);
+                }
             }
         }
     }
@@ -351,22 +377,25 @@ __device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const B
     } else {
         // too many qualifying points for the buffer (loose bound): streaming merge over the same buckets
         unsigned long long worst = INF;
-        unsigned sm2 = __ballot_sync(0xffffffffu, lbs <= thr);
-        while (sm2) {
-            const int sl = __ffs(sm2) - 1;
-            sm2 &= sm2 - 1;
-            for (int t = 0; t < T; ++t) {
-                const int j = sl * T + t;
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
-                if (!(b1.z > 0.f)) continue;
-                const float l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-                const float now = worst == INF ? thr : fminf(thr, __uint_as_float((unsigned)(worst >> 32)));
-                if (!(l <= now)) continue;
-                float d2;
-                const unsigned long long key = point_key(j * 32 + lane, qx, qy, qz, d2);
-                const unsigned m = __ballot_sync(0xffffffffu, key < worst && d2 <= thr);
-                if (m) knn_merge(res, worst, key, m, K, lane);
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+            unsigned sm2 = __ballot_sync(0xffffffffu, lbs[s] <= thr);
+            while (sm2) {
+                const int g = s * 32 + __ffs(sm2) - 1;
+                sm2 &= sm2 - 1;
+                for (int t = 0; t < TT; ++t) {
+                    const int j = g * TT + t;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
+                    if (!(b1.z > 0.f)) continue;
+                    const float l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
+                    const float now = fminf(thr, worst_d2(worst, thr));
+                    if (!(l <= now)) continue;
+                    float d2;
+                    const unsigned long long key = knn_point_key<BIG>(spt, j * 32 + lane, qx, qy, qz, d2);
+                    const unsigned m = __ballot_sync(0xffffffffu, key < worst && d2 <= thr);
+                    if (m) knn_merge(res, worst, key, m, K, lane);
+                }
             }
         }
     }
@@ -376,10 +405,12 @@ __device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const B
     return res;
 }
 
-template <int T>   // T = buckets / 32
+template <int T, bool BIG>   // T = buckets / 32
 __global__ void __launch_bounds__(KNI_WARPS * 32)
 knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, int64_t Q, int K, int chain,
                    int zline, float *__restrict__ dist, int64_t *__restrict__ idx64, int32_t *__restrict__ idx32) {
+    constexpr int TT = T < 32 ? T : 32;
+    constexpr int SB = (T + 31) / 32;
     __shared__ unsigned long long s_buf[KNI_WARPS][KNI_BUF];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long INF = 0xffffffffffffffffull;
@@ -389,7 +420,9 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     ctx.spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
     ctx.buf = s_buf[warp];
     ctx.K = K;
-    const Box6 sb = load_super_box(ctx.box, T, lane);
+    Box6 sb[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) sb[s] = load_super_box(ctx.box, TT, s * 32 + lane);
     const int64_t nchains = (Q + chain - 1) / chain;
     for (int64_t ch = (int64_t)blockIdx.x * KNI_WARPS + warp; ch < nchains; ch += (int64_t)gridDim.x * KNI_WARPS) {
         const int64_t q0 = ch * chain, q1 = min(q0 + chain, Q);
@@ -403,11 +436,11 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
             }
             const float *qp = query + ((int64_t)b * Q + q) * 3;
             const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-            const unsigned long long res = knn_query<T>(ctx, sb, qx, qy, qz, list, lane);
+            const unsigned long long res = knn_query<T, BIG>(ctx, sb, qx, qy, qz, list, lane);
             if (lane < K) {
                 const int64_t o = ((int64_t)b * Q + q) * K + lane;
-                dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(res >> 32)));
-                const unsigned id = ((unsigned)(res & 0xffffffffu)) >> 16;
+                dist[o] = __fsqrt_rn(__uint_as_float(KnnKey<BIG>::d2bits(res)));
+                const unsigned id = KnnKey<BIG>::id(res);
                 if (idx64) idx64[o] = id;
                 if (idx32) idx32[o] = (int32_t)id;
             }
@@ -416,7 +449,7 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     }
 }
 
-template <int T>
+template <int T, bool BIG = false>
 static int launch_knn_indexed(dvcp_cloud_index_t index, const float *query, int B, int64_t Q, int K, int chain,
                               int zline, float *dist, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
     const int64_t nchains = (Q + chain - 1) / chain;
@@ -424,7 +457,7 @@ static int launch_knn_indexed(dvcp_cloud_index_t index, const float *query, int 
     const int64_t cap = (int64_t)DVCP_NUM_SMS * 64 / (B < 64 ? B : 64) + 1;
     if (gx > cap) gx = cap;
     dim3 grid((unsigned)gx, B);
-    knn_indexed_kernel<T><<<grid, KNI_WARPS * 32, 0, st>>>(index, query, Q, K, chain, zline, dist, idx64, idx32);
+    knn_indexed_kernel<T, BIG><<<grid, KNI_WARPS * 32, 0, st>>>(index, query, Q, K, chain, zline, dist, idx64, idx32);
     DVCP_CHECK_LAUNCH();
     return 0;
 }
@@ -466,6 +499,9 @@ extern "C" int dvcp_knn_indexed(dvcp_cloud_index_t index, const float *query, in
         case 4: return launch_knn_indexed<4>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
         case 8: return launch_knn_indexed<8>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
         case 16: return launch_knn_indexed<16>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 32: return launch_knn_indexed<32>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 64: return launch_knn_indexed<64>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
+        case 128: return launch_knn_indexed<128, true>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
     }
     return DVCP_E_UNSUPPORTED;
 }

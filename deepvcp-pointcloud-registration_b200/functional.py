@@ -49,12 +49,13 @@ def draw_fps_start(B: int, N: int) -> torch.Tensor:
 
 # --------------------------------------------------------------------------- #
 class SpatialIndex:
-    """Device buffers of a cloud's spatial index (dvcp_cloud_index_t)."""
+    """Device buffers of a cloud's spatial index (dvcp_cloud_index_t). big=True admits clouds of up to
+    131072 points (multi-CTA build; consumed by the KNN only)."""
 
-    def __init__(self, B, N, device):
-        self.cap = lib().dvcp_index_capacity(N)
+    def __init__(self, B, N, device, big=False):
+        self.cap = lib().dvcp_index_capacity_any(N) if big else lib().dvcp_index_capacity(N)
         if self.cap == 0:
-            raise RuntimeError("clouds of %d points cannot be indexed (64..16384)" % N)
+            raise RuntimeError("clouds of %d points cannot be indexed (64..%d)" % (N, 131072 if big else 16384))
         self.sorted_pt = torch.empty(B, self.cap, 4, dtype=torch.float32, device=device)   # x, y, z, index bits
         self.bucket_box = torch.empty(B, self.cap // 32, 8, dtype=torch.float32, device=device)
         self.B = B
@@ -66,6 +67,10 @@ class SpatialIndex:
     @staticmethod
     def indexable(N, dtype=torch.float32):
         return USE_INDEX and dtype == torch.float32 and lib().dvcp_index_capacity(N) > 0
+
+    @staticmethod
+    def knn_indexable(N, dtype=torch.float32):
+        return USE_INDEX and dtype == torch.float32 and lib().dvcp_index_capacity_any(N) > 0
 
 
 def fps(xyz_cloud: Cloud, device, dtype, B, N, npoint, start, want64=True, want32=False, index=None):
@@ -104,10 +109,19 @@ def gather_rows(points, idx32):
     return out
 
 
-def build_index(xyz_cloud: Cloud, device, B, N):
-    index = SpatialIndex(B, N, device)
-    check(lib().dvcp_build_index(xyz_cloud, B, N, index.c(), stream_ptr(device)), "dvcp_build_index")
-    _count(1)
+def build_index(xyz_cloud: Cloud, device, B, N, big=False):
+    """Spatial index of B float32 clouds. big=True: any 64 <= N <= 131072 (above 16384 points the
+    index is built by several CTAs per cloud and serves the KNN only)."""
+    index = SpatialIndex(B, N, device, big=big)
+    if not big or index.cap <= 16384:
+        check(lib().dvcp_build_index(xyz_cloud, B, N, index.c(), stream_ptr(device)), "dvcp_build_index")
+        _count(1)
+        return index
+    nbytes = lib().dvcp_build_index_workspace_bytes(B, N)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    check(lib().dvcp_build_index_ws(xyz_cloud, B, N, index.c(), ptr(ws), nbytes, stream_ptr(device)),
+          "dvcp_build_index_ws")
+    _count(3 + int(math.log2(index.cap // 16384)))   # bbox, run sort, merges, publish
     return index
 
 

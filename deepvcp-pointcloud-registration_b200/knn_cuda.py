@@ -1,6 +1,7 @@
 """KNN -- stand-in for the third-party `knn_cuda.KNN` the reference imports
 (get_cat_feat_tgt.py:4,45,52; deepVCP_loss.py:3,70,72): same constructor and call
-convention, exact brute-force search on sm_100a."""
+convention, exact search on sm_100a: through the spatial index for clouds of
+64..131072 points and at least 256 queries, brute force otherwise; identical results."""
 import torch
 
 from . import functional as F_
@@ -25,8 +26,8 @@ class KNN:
             else:
                 B, _, N = ref.shape
                 rc, q = cloud_cm(ref), query.transpose(1, 2).contiguous()
-            if F_.SpatialIndex.indexable(N) and q.shape[1] >= 256:
-                index = F_.build_index(rc, ref.device, B, N)
+            if F_.SpatialIndex.knn_indexable(N) and q.shape[1] >= 256:
+                index = F_.build_index(rc, ref.device, B, N, big=True)
                 dist, idx, _ = F_.knn_indexed(index, 0, ref.device, B, N, q, self.k)
             else:
                 dist, idx, _ = F_.knn(rc, ref.device, B, N, q, self.k)

@@ -62,7 +62,7 @@ typedef struct {
     int in_ch, out_ch;
 } dvcp_mlp_layer_t;
 
-/* Spatial index of a cloud (64 <= N <= 16384): the points in Morton order, cut
+/* Spatial index of a cloud (64 <= N <= 16384; up to 131072 through dvcp_build_index_ws): the points in Morton order, cut
  * into buckets of 32 consecutive points with their bounding boxes. Built by
  * dvcp_build_index, or as a by-product of dvcp_fps (which sorts the cloud
  * anyway); consumed by the pruned ball-query / SA / KNN kernels. Pruning never
@@ -96,6 +96,17 @@ DVCP_API int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const 
 /* Capacity (slots) of the spatial index of an N-point cloud; 0 = N not indexable. */
 DVCP_API int dvcp_index_capacity(int N);
 DVCP_API int dvcp_build_index(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index_t index_out, dvcp_stream_t stream);
+
+/* The index of larger clouds (16384 < N <= 131072), built by several CTAs per cloud (csrc/index_big.cu:
+ * per-run block sorts + rank merges). dvcp_index_capacity_any covers 64 <= N <= 131072 (equal to
+ * dvcp_index_capacity up to 16384); dvcp_build_index_ws builds either kind and needs
+ * dvcp_build_index_workspace_bytes(B, N) bytes of workspace (0 up to 16384 points). Consumed by
+ * dvcp_knn_indexed (SURVEY 8(d) SWEEP: KNN at N = 32k..128k); the sampling and SA kernels take the
+ * single-CTA index only. */
+DVCP_API int dvcp_index_capacity_any(int N);
+DVCP_API int64_t dvcp_build_index_workspace_bytes(int B, int N);
+DVCP_API int dvcp_build_index_ws(dvcp_cloud_t xyz, int B, int N, dvcp_cloud_index_t index_out, void *workspace,
+                        int64_t workspace_bytes, dvcp_stream_t stream);
 
 /* Test hook: the plain O(N * npoint) kernel for float32 clouds (the spatially
  * pruned kernel dvcp_fps normally dispatches to must give identical indices). */

@@ -345,6 +345,75 @@ def test_spatial_index_is_a_permutation_with_tight_boxes(F):
             assert torch.equal(box[j, :3], p.min(dim=1)[0]) and torch.equal(box[j, 3:6], p.max(dim=1)[0])
 
 
+@pytest.mark.parametrize("n", [16385, 20000, 40000, 65536, 70000, 131072])
+def test_big_spatial_index_is_a_permutation_with_tight_boxes(F, synthetic, n):
+    """Multi-CTA index build (csrc/index_big.cu) for clouds above 16384 points."""
+    lib = importlib.import_module(PKG + "._lib")
+    pts = lattice_cloud(n, n, extent=40.0, step=0.125).to(DEV)       # duplicates and equal Morton codes
+    index = F.build_index(lib.cloud_pm(pts), pts.device, 1, n, big=True)
+    assert index.cap >= n and index.cap in (32768, 65536, 131072)
+    spt = index.sorted_pt[0].cpu()
+    sid = spt[:, 3].contiguous().view(torch.int32)
+    valid = sid >= 0
+    assert int(valid.sum()) == n and torch.equal(sid[valid].sort()[0], torch.arange(n, dtype=torch.int32))
+    assert bool(valid[:n].all())                           # unused slots sort behind every point
+    assert bool(torch.isinf(spt[~valid, :3]).all())
+    assert torch.equal(spt[valid, :3], pts[0].cpu()[sid[valid].long()])
+    box = index.bucket_box[0].cpu()
+    cnt = valid.view(-1, 32).sum(dim=1)
+    assert torch.equal(box[:, 6].long(), cnt)
+    used = cnt > 0
+    p = spt[:, :3].view(-1, 32, 3)
+    lo = torch.where(valid.view(-1, 32, 1), p, torch.full_like(p, float("inf"))).min(dim=1)[0]
+    hi = torch.where(valid.view(-1, 32, 1), p, torch.full_like(p, float("-inf"))).max(dim=1)[0]
+    assert torch.equal(box[used, :3], lo[used]) and torch.equal(box[used, 3:6], hi[used])
+    # Morton order: buckets are compact (ideal cubic cell of 32 points: edge 80 m * (32 / n)^(1/3))
+    diag = (hi[used] - lo[used]).norm(dim=1)
+    assert float(diag.median()) < 3.0 * 80.0 * (32.0 / n) ** (1.0 / 3.0)
+
+
+@pytest.mark.parametrize("n,kind", [(20000, "kitti"), (40000, "kitti"), (65536, "lattice"), (70000, "kitti"),
+                                     (131072, "kitti"), (131072, "lattice")])
+def test_knn_big_index_equals_brute_force_and_oracle(F, n, kind):
+    """KNN through the multi-CTA index (caps 32768 / 65536 / 131072, the last with the 17-bit key layout):
+    every query equal to the brute-force kernel, a sample equal to the oracle; voxelised clouds: exact ties."""
+    lib = importlib.import_module(PKG + "._lib")
+    g = torch.Generator().manual_seed(n)
+    if kind == "kitti":
+        rho = (torch.randn(n, generator=g) * 25.0).abs().clamp(max=80.0)
+        az = torch.rand(n, generator=g) * 6.2831853
+        z = torch.rand(n, generator=g) * 8.0 - 2.0
+        pts = (torch.round(torch.stack([rho * az.cos(), rho * az.sin(), z], 1) * 10.0) / 10.0).float().unsqueeze(0)
+    else:
+        pts = lattice_cloud(n, n + 1, extent=12.0, step=0.5)             # heavy duplicates: index tie-breaking
+    centres = pts[0, torch.randint(0, n, (12,), generator=g)].double().unsqueeze(0)
+    cand = F.candidates(centres.to(DEV), 1.2, 0.4, 7).view(1, -1, 3)      # 12 x 7^3 lattice queries
+    far = (torch.rand(1, 64, 3, generator=g) * 2 - 1) * 150.0             # and some far outside the cloud
+    qry = torch.cat([cand, far.to(DEV)], 1).contiguous()
+    pd = pts.to(DEV)
+    index = F.build_index(lib.cloud_pm(pd), pd.device, 1, n, big=True)
+    d, i, i32 = F.knn_indexed(index, 0, pd.device, 1, n, qry, 32, chain=49, zline=7, want32=True)
+    db, ib, _ = F.knn(lib.cloud_pm(pd), pd.device, 1, n, qry, 32)
+    assert torch.equal(i, ib) and torch.equal(d, db) and torch.equal(i32.long(), ib)
+    d1, i1, _ = F.knn_indexed(index, 0, pd.device, 1, n, qry, 5, chain=1)   # every query a cold start
+    assert torch.equal(i1, ib[..., :5]) and torch.equal(d1, db[..., :5])
+    pick = torch.arange(0, qry.shape[1], 23)
+    d_ref, i_ref = stages.knn(pts, qry[:, pick].cpu(), 32)
+    assert torch.equal(i[:, pick].cpu(), i_ref) and torch.equal(d[:, pick].cpu(), d_ref)
+
+
+def test_knn_module_uses_big_index_same_results(dv, F):
+    """knn_cuda.KNN stand-in above 16384 points (indexed path) == brute-force kernel."""
+    lib = importlib.import_module(PKG + "._lib")
+    n = 50000
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.round(torch.randn(2, n, 3, generator=g) * 200.0) / 10.0).to(DEV)
+    qry = (torch.round(torch.randn(2, 700, 3, generator=g) * 200.0) / 10.0).to(DEV)
+    d, i = dv.KNN(32, transpose_mode=True)(pts, qry)
+    db, ib, _ = F.knn(lib.cloud_pm(pts), pts.device, 2, n, qry, 32)
+    assert torch.equal(i, ib) and torch.equal(d, db)
+
+
 def test_knn_kitti_full_size_sampled_and_sorted(dv, F, synthetic):
     _, tgt, _, _ = synthetic.make_batch("kitti", [2], 16384)
     g = torch.Generator().manual_seed(4)
