@@ -13,8 +13,6 @@
 // queries and keeps each query's current K best as ONE key per lane, sorted
 // across the lanes. A step evaluates 32 points; lanes whose key beats the current
 // K-th are inserted with ballot + shuffle-up.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace dvcp {
@@ -451,347 +449,6 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     }
 }
 
-// ------------------------------------------------ indexed KNN, line pools -----
-// Queries that form a lattice (the candidate grid: runs of `zline` queries sharing x and y with ascending z,
-// `chain / zline` such lines per chain, neighbouring lines close together) let a warp traverse the index ONCE
-// per line instead of once per query:
-//   * the results of the previous line (kept as 32-bit (index, slot) words in shared memory), re-evaluated
-//     for the queries of this line, bound their K-th distances: thr_i for query i, T = max thr_i;
-//   * every point that can be within thr_i of some query of the line passes the test
-//         fma(dzm, dzm, fma(dy, dy, dx * dx)) <= T,   dzm = distance from the point's z to [z_first, z_last]
-//     (same rounded arithmetic as the point distances, monotone in |dz|, so no member is lost); buckets are
-//     pruned by the same expression on their boxes. The survivors form the line's pool in shared memory;
-//   * each query then collects the pool points with d2 <= thr_i and selects its K smallest keys.
-// The first line of a chain, lines that are not lattice lines, pools that overflow and queries with more
-// than KNI_BUF qualifying points go through knn_query (the per-query traversal above), seeded with the
-// neighbouring result. Same results as every other KNN kernel here: keys are totally ordered.
-constexpr int KNL_WARPS = 4;
-constexpr int KNL_POOL = 256;
-
-#ifdef DVCP_KNN_STATS   // development: pool statistics (tools/knn_stats.py)
-__device__ unsigned long long knl_stats[8];   // lines pooled, lines overflowed, sum npool, max npool, query fallbacks, sum cnt, first lines pooled, first lines overflowed
-#define KNL_STAT_ADD(i, v) do { if (lane == 0) atomicAdd(&knl_stats[i], (unsigned long long)(v)); } while (0)
-#define KNL_STAT_MAX(i, v) do { if (lane == 0) atomicMax(&knl_stats[i], (unsigned long long)(v)); } while (0)
-#else
-#define KNL_STAT_ADD(i, v)
-#define KNL_STAT_MAX(i, v)
-#endif
-
-// the K smallest of `cnt` keys in buf[], ascending across the lanes
-__device__ __forceinline__ unsigned long long knn_select_sorted(const unsigned long long *buf, int cnt, int lane) {
-    const unsigned long long INF = 0xffffffffffffffffull;
-    unsigned long long res = INF;
-    for (int g = 0; g < cnt; g += 32) {
-        unsigned long long k = g + lane < cnt ? buf[g + lane] : INF;
-        k = bitonic_sort32(k, lane);
-        if (g == 0) {
-            res = k;
-        } else {
-            const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
-            res = u64min(res, r);
-#pragma unroll
-            for (int j = 16; j > 0; j >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, res, j);
-                res = (lane & j) == 0 ? u64min(res, other) : u64max(res, other);
-            }
-        }
-    }
-    return res;
-}
-
-constexpr int KNL_SEGS = 4;   // a line's queries are bounded in up to 4 runs of consecutive queries
-
-template <int T>   // T = buckets / 32 <= 64 (16-bit index and slot fields)
-__global__ void __launch_bounds__(KNL_WARPS * 32)
-knn_lines_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, int64_t Q, int K, int chain,
-                 int zline, int lpt, float *__restrict__ dist, int64_t *__restrict__ idx64,
-                 int32_t *__restrict__ idx32) {
-    constexpr int TT = T < 32 ? T : 32;
-    constexpr int SB = (T + 31) / 32;
-    extern __shared__ __align__(16) unsigned char knl_smem[];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned long long INF = 0xffffffffffffffffull;
-    const int cap = index.cap;
-    const int per_warp = KNL_POOL * 16 + KNI_BUF * 8 + KNL_SEGS * 16 + ((zline * 32 * 2 + 15) & ~15);
-    unsigned char *mine = knl_smem + (size_t)warp * per_warp;
-    float4 *pool = reinterpret_cast<float4 *>(mine);
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(mine + KNL_POOL * 16);
-    float4 *segs = reinterpret_cast<float4 *>(mine + KNL_POOL * 16 + KNI_BUF * 8);   // (z first, z last, max thr, -)
-    unsigned short *lists = reinterpret_cast<unsigned short *>(mine + KNL_POOL * 16 + KNI_BUF * 8 + KNL_SEGS * 16);
-    KnnCtx ctx;
-    ctx.box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
-    ctx.spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
-    ctx.buf = buf;
-    ctx.K = K;
-    const float *box = ctx.box;
-    const float4 *spt = ctx.spt;
-    Box6 sb[SB];
-#pragma unroll
-    for (int s = 0; s < SB; ++s) sb[s] = load_super_box(ctx.box, TT, s * 32 + lane);
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    auto emit = [&](int64_t q, unsigned long long res) {
-        if (lane < K) {
-            const int64_t o = ((int64_t)b * Q + q) * K + lane;
-            dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(res >> 32)));
-            const unsigned id = ((unsigned)(res & 0xffffffffu)) >> 16;
-            if (idx64) idx64[o] = id;
-            if (idx32) idx32[o] = (int32_t)id;
-        }
-    };
-    // largest squared distance from (x, y, z) to the K points whose slots are in l[0..K-1]
-    auto bound_from = [&](const unsigned short *l, float x, float y, float z) -> float {
-        unsigned bits = 0u;
-        if (lane < K) {
-            const float4 P = __ldg(spt + l[lane]);
-            bits = __float_as_uint(sqdist_direct(P.x - x, P.y - y, P.z - z));
-        }
-        return __uint_as_float(__reduce_max_sync(0xffffffffu, bits));
-    };
-
-    // a task = up to `lpt` consecutive lines of one chain
-    const int lines_per_chain = (chain + zline - 1) / zline;
-    const int parts = (lines_per_chain + lpt - 1) / lpt;
-    const int64_t nchains = (Q + chain - 1) / chain;
-    const int64_t ntasks = nchains * parts;
-    for (int64_t task = (int64_t)blockIdx.x * KNL_WARPS + warp; task < ntasks; task += (int64_t)gridDim.x * KNL_WARPS) {
-        const int64_t ch = task / parts;
-        const int part = (int)(task - ch * parts);
-        const int64_t q0 = ch * chain, q1 = min(q0 + chain, Q);
-        const int nl_chain = (int)((q1 - q0 + zline - 1) / zline);
-        const int line_lo = part * lpt, line_hi = min(line_lo + lpt, nl_chain);
-        for (int line = line_lo; line < line_hi; ++line) {
-            const bool first = line == line_lo;
-            const int64_t lq0 = q0 + (int64_t)line * zline;
-            const int ln = (int)min((int64_t)zline, q1 - lq0);
-            // lane i holds query i of the line
-            float lx = 0.f, ly = 0.f, lz = 0.f;
-            if (lane < ln) {
-                const float *qp = query + ((int64_t)b * Q + lq0 + lane) * 3;
-                lx = __ldg(qp);
-                ly = __ldg(qp + 1);
-                lz = __ldg(qp + 2);
-            }
-            const float qx = __shfl_sync(0xffffffffu, lx, 0), qy = __shfl_sync(0xffffffffu, ly, 0);
-            const float lzp = __shfl_up_sync(0xffffffffu, lz, 1);
-            const bool lattice = __all_sync(0xffffffffu, lane >= ln || (lx == qx && ly == qy && (lane == 0 || lz >= lzp)));
-            const int mid = ln >> 1;
-            bool done = false;
-            if (lattice) {
-                // ---- bounds on every query's K-th distance: K known points re-evaluated exactly ----
-                float mythr = 0.f;
-                if (first) {
-                    // cold start: the middle query exactly (best-first search); its neighbours bound the whole line
-                    const float qz = __shfl_sync(0xffffffffu, lz, mid);
-                    const unsigned long long res = knn_query<T, false>(ctx, sb, qx, qy, qz, INF, lane);
-                    emit(lq0 + mid, res);
-                    lists[mid * 32 + lane] = (unsigned short)(res & 0xffffu);
-                    __syncwarp();
-                    for (int i = 0; i < ln; ++i) {
-                        const float t = bound_from(lists + mid * 32, qx, qy, __shfl_sync(0xffffffffu, lz, i));
-                        if (lane == i) mythr = t;
-                    }
-                } else {
-                    for (int i = 0; i < ln; ++i) {
-                        const float t = bound_from(lists + i * 32, qx, qy, __shfl_sync(0xffffffffu, lz, i));
-                        if (lane == i) mythr = t;
-                    }
-                }
-                // runs of consecutive queries: (first z, last z, largest bound)
-                const int seglen = (ln + KNL_SEGS - 1) / KNL_SEGS;
-                {
-                    float t = mythr;   // max over my run, by lanes of the same run
-                    for (int o = 1; o < seglen; ++o) {
-                        const float u = __shfl_down_sync(0xffffffffu, mythr, o);
-                        if (lane + o < ln && (lane + o) / seglen == lane / seglen) t = fmaxf(t, u);
-                    }
-                    const int last = min(lane + seglen - 1, ln - 1);
-                    const float zl = __shfl_sync(0xffffffffu, lz, last);
-                    if (lane < ln && lane % seglen == 0) segs[lane / seglen] = make_float4(lz, zl, t, 0.f);
-                    if (lane < KNL_SEGS && lane * seglen >= ln) segs[lane] = make_float4(0.f, 0.f, -1.f, 0.f);   // unused run
-                }
-                __syncwarp();
-                // a box (a point is a degenerate box) passes if it can be within the bound of some run; same
-                // rounded arithmetic as the point distances, monotone in every offset, so no member is lost
-                auto line_pass = [&](float nx, float ny, float nz, float xx, float xy, float xz) -> bool {
-                    const float ex = fmaxf(fmaxf(nx - qx, qx - xx), 0.f);
-                    const float ey = fmaxf(fmaxf(ny - qy, qy - xy), 0.f);
-                    const float hxy = __fmaf_rn(ey, ey, __fmul_rn(ex, ex));
-                    bool pass = false;
-#pragma unroll
-                    for (int s = 0; s < KNL_SEGS; ++s) {
-                        const float4 g = segs[s];
-                        const float ez = fmaxf(fmaxf(nz - g.y, g.x - xz), 0.f);
-                        pass |= __fmaf_rn(ez, ez, hxy) <= g.z;
-                    }
-                    return pass;
-                };
-                // ---- the line's pool ----
-                int npool = 0;
-#pragma unroll
-                for (int s = 0; s < SB; ++s) {
-                    unsigned sm = __ballot_sync(0xffffffffu,
-                                                line_pass(sb[s].nx, sb[s].ny, sb[s].nz, sb[s].xx, sb[s].xy, sb[s].xz));
-                    while (sm) {
-                        const int g = s * 32 + __ffs(sm) - 1;
-                        sm &= sm - 1;
-                        bool l = false;
-                        if (lane < TT) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + lane) * 8));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + lane) * 8) + 1);
-                            if (b1.z > 0.f) l = line_pass(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
-                        }
-                        unsigned bm = __ballot_sync(0xffffffffu, l);
-                        while (bm) {
-                            const int pos = (g * TT + __ffs(bm) - 1) * 32 + lane;
-                            bm &= bm - 1;
-                            const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never qualify
-                            const bool qual = line_pass(P.x, P.y, P.z, P.x, P.y, P.z);
-                            const unsigned m = __ballot_sync(0xffffffffu, qual);
-                            if (m) {
-                                const int slot = npool + __popc(m & lt_mask);
-                                if (qual && slot < KNL_POOL)
-                                    pool[slot] = make_float4(P.x, P.y, P.z,
-                                                             __uint_as_float(((unsigned)__float_as_int(P.w) << 16) | (unsigned)pos));
-                                npool += __popc(m);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                KNL_STAT_ADD(first ? (npool <= KNL_POOL ? 6 : 7) : (npool <= KNL_POOL ? 0 : 1), 1);
-                KNL_STAT_ADD(2, npool);
-                KNL_STAT_MAX(3, npool);
-                if (npool <= KNL_POOL) {
-                    // first line: from the middle outwards, each query also bounded by its finished neighbour
-                    const int nq = first ? ln - 1 : ln;
-                    for (int k = 0; k < nq; ++k) {
-                        int i = k, nb = -1;
-                        if (first) {
-                            if (k < mid) { i = mid - 1 - k; nb = i + 1; }
-                            else { i = k + 1; nb = i - 1; }
-                        }
-                        const float qz = __shfl_sync(0xffffffffu, lz, i);
-                        float thr = __shfl_sync(0xffffffffu, mythr, i);
-                        if (nb >= 0) thr = fminf(thr, bound_from(lists + nb * 32, qx, qy, qz));
-                        int cnt = 0;
-                        for (int g = 0; g < npool; g += 32) {
-                            bool qual = false;
-                            unsigned long long key = 0ull;
-                            if (g + lane < npool) {
-                                const float4 P = pool[g + lane];
-                                const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
-                                qual = d2 <= thr;
-                                key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(P.w);
-                            }
-                            const unsigned m = __ballot_sync(0xffffffffu, qual);
-                            const int slot = cnt + __popc(m & lt_mask);
-                            if (qual && slot < KNI_BUF) buf[slot] = key;
-                            cnt += __popc(m);
-                        }
-                        __syncwarp();
-                        unsigned long long res;
-                        KNL_STAT_ADD(5, cnt);
-                        if (cnt > KNI_BUF) KNL_STAT_ADD(4, 1);
-                        if (cnt <= KNI_BUF) {
-                            res = knn_select_sorted(buf, cnt, lane);
-                            if (lane >= K) res = INF;
-                        } else {
-                            const int from = nb >= 0 ? nb : i;
-                            res = knn_query<T, false>(ctx, sb, qx, qy, qz, (unsigned long long)lists[from * 32 + lane], lane);
-                        }
-                        __syncwarp();   // buf is reused by the next query
-                        emit(lq0 + i, res);
-                        lists[i * 32 + lane] = (unsigned short)(res & 0xffffu);
-                        __syncwarp();
-                    }
-                    done = true;
-                }
-            }
-            if (!done) {
-                // ---- per-query traversal along the line, each query seeded by a finished neighbour ----
-                // (a lattice first line has its middle query done already: walk outwards from it)
-                const bool from_mid = lattice && first;
-                unsigned long long list = from_mid ? (unsigned long long)lists[mid * 32 + lane]
-                                                   : (first ? INF : (unsigned long long)lists[lane]);
-                const int nq = from_mid ? ln - 1 : ln;
-                for (int k = 0; k < nq; ++k) {
-                    int i = k;
-                    if (from_mid) {
-                        i = k < mid ? mid - 1 - k : k + 1;
-                        if (k == mid) list = (unsigned long long)lists[mid * 32 + lane];   // turn round at the middle
-                    }
-                    const float x = __shfl_sync(0xffffffffu, lx, i), y = __shfl_sync(0xffffffffu, ly, i),
-                                z = __shfl_sync(0xffffffffu, lz, i);
-                    const unsigned long long res = knn_query<T, false>(ctx, sb, x, y, z, list, lane);
-                    emit(lq0 + i, res);
-                    lists[i * 32 + lane] = (unsigned short)(res & 0xffffu);
-                    list = res;
-                }
-                __syncwarp();
-            }
-        }
-    }
-}
-
-template <int T>
-static int launch_knn_lines(dvcp_cloud_index_t index, const float *query, int B, int64_t Q, int K, int chain,
-                            int zline, float *dist, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
-    const int smem = KNL_WARPS * (KNL_POOL * 16 + KNI_BUF * 8 + KNL_SEGS * 16 + ((zline * 32 * 2 + 15) & ~15));
-    auto k = knn_lines_kernel<T>;
-    DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // lines per task: few tasks leave warps idle, many tasks pay more cold starts (one exact query and a
-    // wider pool per task). Cost model in units of a warm line: cold start ~ 1.5 lines.
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, KNL_WARPS * 32, smem) != cudaSuccess || n < 1) n = 8;
-        ctas_per_sm = n;
-    }
-    const int64_t slots = (int64_t)DVCP_NUM_SMS * ctas_per_sm * KNL_WARPS;
-    const int lines_per_chain = (chain + zline - 1) / zline;
-    const int64_t nchains = ((Q + chain - 1) / chain) * B;
-    int lpt = lines_per_chain;
-    double best = 1e300;
-    for (int c = 2; c <= lines_per_chain; ++c) {
-        const int parts = (lines_per_chain + c - 1) / c;
-        const int64_t rounds = (nchains * parts + slots - 1) / slots;
-        const double cost = (double)rounds * (1.5 + c);
-        if (cost < best - 1e-9) { best = cost; lpt = c; }
-    }
-    const char *e = getenv("DVCP_KNN_LPT");
-    if (e && atoi(e) >= 1) lpt = atoi(e);
-    const int parts = (lines_per_chain + lpt - 1) / lpt;
-    const int64_t ntasks = ((Q + chain - 1) / chain) * parts;
-    int64_t gx = (ntasks + KNL_WARPS - 1) / KNL_WARPS;
-    const int64_t capx = (int64_t)DVCP_NUM_SMS * 64 / (B < 64 ? B : 64) + 1;
-    if (gx > capx) gx = capx;
-    k<<<dim3((unsigned)gx, B), KNL_WARPS * 32, smem, st>>>(index, query, Q, K, chain, zline, lpt, dist, idx64, idx32);
-    DVCP_CHECK_LAUNCH();
-    return 0;
-}
-
-#ifdef DVCP_KNN_STATS
-extern "C" __attribute__((visibility("default"))) int dvcp_knn_debug_stats(unsigned long long *out8_host, int reset) {
-    cudaDeviceSynchronize();
-    if (out8_host) cudaMemcpyFromSymbol(out8_host, dvcp::knl_stats, 8 * sizeof(unsigned long long));
-    if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        cudaMemcpyToSymbol(dvcp::knl_stats, z, sizeof(z));
-    }
-    return 0;
-}
-#endif
-
-// DVCP_KNN_LINES=0 keeps the per-query traversal for every query (same results; for timing comparisons).
-static bool knn_lines_enabled() {
-    static const bool v = [] {
-        const char *e = getenv("DVCP_KNN_LINES");
-        return !(e && e[0] == '0');
-    }();
-    return v;
-}
-
 template <int T, bool BIG = false>
 static int launch_knn_indexed(dvcp_cloud_index_t index, const float *query, int B, int64_t Q, int K, int chain,
                               int zline, float *dist, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
@@ -836,17 +493,6 @@ extern "C" int dvcp_knn_indexed(dvcp_cloud_index_t index, const float *query, in
     if (zline < 1 || zline > chain) zline = chain;
     if (K < 1 || K > 32 || K > N || B > 65535 || index.cap < N) return DVCP_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    if (chain >= 2 * zline && zline <= 32 && index.cap <= 65536 && knn_lines_enabled()) {
-        switch (index.cap / 1024) {
-            case 1: return launch_knn_lines<1>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-            case 2: return launch_knn_lines<2>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-            case 4: return launch_knn_lines<4>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-            case 8: return launch_knn_lines<8>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-            case 16: return launch_knn_lines<16>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-            case 32: return launch_knn_lines<32>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-            case 64: return launch_knn_lines<64>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
-        }
-    }
     switch (index.cap / 1024) {
         case 1: return launch_knn_indexed<1>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);
         case 2: return launch_knn_indexed<2>(index, query, B, Q, K, chain, zline, dist, idx64, idx32, st);

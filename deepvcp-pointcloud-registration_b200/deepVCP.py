@@ -173,12 +173,12 @@ class DeepVCP(nn.Module):
             mark("keypoint_candidates")
             C = G * G * G
             if index is not None:   # target clouds are batch items B..2B-1 of the index
-                kd, ki64, ki32 = F_.knn_indexed(index, B, dev, B, N, cand.view(B, K * C, 3), ns, chain=G * G, zline=G,
+                kd, ki64, ki32 = F_.knn_indexed(index, B, dev, B, N, cand.view(B, K * C, 3), ns, chain=G,
                                                 want64=keep_stages, want32=True)
             elif F_.SpatialIndex.knn_indexable(N):
                 # clouds above the sampling kernels' index capacity: multi-CTA index of the targets for the KNN
                 tindex = F_.build_index(cloud_cm(tgt), dev, B, N, big=True)
-                kd, ki64, ki32 = F_.knn_indexed(tindex, 0, dev, B, N, cand.view(B, K * C, 3), ns, chain=G * G, zline=G,
+                kd, ki64, ki32 = F_.knn_indexed(tindex, 0, dev, B, N, cand.view(B, K * C, 3), ns, chain=G,
                                                 want64=keep_stages, want32=True)
             else:
                 kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
