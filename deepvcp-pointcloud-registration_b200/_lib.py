@@ -61,8 +61,8 @@ SIGNATURES = {
                                   CloudIndex, c_vp, c_vp, c_vp]),
     "dvcp_weighting_scores": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_topk": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "dvcp_keypoint_stage": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_f32,
-                                    c_i32, DfeParams, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dvcp_keypoint_stage": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64,
+                                    c_f32, c_i32, DfeParams, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_grid_size": (c_i32, [c_f64, c_f64]),
     "dvcp_candidates": (c_i32, [c_vp, c_i64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "dvcp_knn": (c_i32, [Cloud, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
@@ -76,13 +76,19 @@ SIGNATURES = {
     "dvcp_dfe_dense": (c_i32, [c_vp, c_i32, c_i64, c_i32, DfeParams, c_vp, c_vp]),
     "dvcp_cpg_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "dvcp_cpg": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, CpgParams, c_vp, c_vp, c_vp, c_i64, c_vp]),
-    "dvcp_kabsch": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
-    "dvcp_kabsch_refine": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dvcp_kabsch": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dvcp_kabsch_refine": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp]),
 }
 
-QUIRK_KEYPOINT_VIEW = 1      # Q3: gather result re-read row-major (deepVCP.py:46)
-QUIRK_PER_FEATURE_WEIGHT = 2  # Q7: distance weight indexed by feature (get_cat_feat_tgt.py:65,92)
-QUIRKS_REFERENCE = QUIRK_KEYPOINT_VIEW | QUIRK_PER_FEATURE_WEIGHT
+# A set bit replicates the reference; a clear bit selects the semantics its code intends
+QUIRK_KEYPOINT_VIEW = 1         # Q3: gather result re-read row-major (deepVCP.py:46)
+QUIRK_PER_FEATURE_WEIGHT = 2    # Q7: distance weight indexed by feature (get_cat_feat_tgt.py:65,92)
+QUIRK_COST_VOLUME_RESHAPE = 4   # Q4: (feature, candidate) axes scrambled by the reshape (deepVCP.py:106, cpg.py:34)
+QUIRK_IGNORE_T_INIT = 8         # Q6: t_init never added (deepVCP.py:86-91)
+QUIRK_NO_REFLECTION_FIX = 16    # Q10: R = V U^T may have det = -1 (deepVCP_loss.py:36-40)
+QUIRKS_REFERENCE = 31
+QUIRKS_INTENDED = 0
 
 
 def lib_path() -> str:
@@ -101,7 +107,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.dvcp_abi_version() != 1:
+        if L.dvcp_abi_version() != 2:
             raise RuntimeError("libdvcp_b200.so ABI version mismatch")
         _LIB = L
     return _LIB

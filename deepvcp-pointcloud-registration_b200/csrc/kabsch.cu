@@ -6,8 +6,11 @@
 // covariance is reduced with shuffles, and the SVD is a closed-loop one-sided
 // Jacobi on the 3x3 matrix held in registers of every lane (no shared memory, no
 // library call). R = V U^T is the orthogonal polar factor of H^T; it does not
-// depend on the sign/order conventions of the SVD, and no reflection correction
-// is applied (quirk Q10: the reference builds Z but never uses it).
+// depend on the sign/order conventions of the SVD. Reference mode applies no
+// reflection correction (quirk Q10: the reference builds Z but never uses it);
+// with DVCP_QUIRK_NO_REFLECTION_FIX clear the term of the smallest singular value
+// is flipped when det(V U^T) < 0 (R = V diag(1, 1, -1) U^T). Optional
+// per-correspondence weights give the weighted Kabsch solve.
 #include "common.cuh"
 
 namespace dvcp {
@@ -19,7 +22,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // H (row-major 3x3) -> R = V U^T, where H = U S V^T.
-__device__ void polar_from_svd(const double (&H)[9], double (&R)[9]) {
+__device__ void polar_from_svd(const double (&H)[9], double (&R)[9], bool fix_reflection) {
     double A[3][3], V[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -105,23 +108,43 @@ __device__ void polar_from_svd(const double (&H)[9], double (&R)[9]) {
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             R[3 * i + j] = V[i][0] * U[j][0] + V[i][1] * U[j][1] + V[i][2] * U[j][2];
+    if (fix_reflection) {
+        const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
+                           R[2] * (R[3] * R[7] - R[4] * R[6]);
+        if (det < 0) {
+            int km = 0;
+            if (sig[1] < sig[km]) km = 1;
+            if (sig[2] < sig[km]) km = 2;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double vi = km == 0 ? V[i][0] : (km == 1 ? V[i][1] : V[i][2]);
+                    double uj = km == 0 ? U[j][0] : (km == 1 ? U[j][1] : U[j][2]);
+                    R[3 * i + j] -= 2.0 * vi * uj;
+                }
+        }
+    }
 }
 
-// Kabsch over the points whose `keep` predicate holds. load(c, i) returns
-// coordinate c of point i. Every lane returns the same R, t.
-template <typename LX, typename LY, typename KEEP>
-__device__ void kabsch_warp(int n, LX lx, LY ly, KEEP keep, double (&R)[9], double (&t)[3]) {
+// Kabsch over the points whose weight is non-zero (wt(i): 1 / 0 for the plain and
+// the inlier-masked solve, any non-negative weight for the weighted one). lx(c, i)
+// returns coordinate c of point i. Every lane returns the same R, t.
+template <typename LX, typename LY, typename WT>
+__device__ void kabsch_warp(int n, LX lx, LY ly, WT wt, bool fix_reflection, double (&R)[9], double (&t)[3]) {
     const int lane = lane_id();
     double sx[3] = {0, 0, 0}, sy[3] = {0, 0, 0}, cnt = 0;
-    for (int i = lane; i < n; i += 32)
-        if (keep(i)) {
-            cnt += 1.0;
+    for (int i = lane; i < n; i += 32) {
+        const double w = wt(i);
+        if (w != 0.0) {
+            cnt += w;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                sx[c] += lx(c, i);
-                sy[c] += ly(c, i);
+                sx[c] += w * lx(c, i);
+                sy[c] += w * ly(c, i);
             }
         }
+    }
     cnt = warp_sum_d(cnt);
     double mx[3], my[3];
 #pragma unroll
@@ -130,22 +153,24 @@ __device__ void kabsch_warp(int n, LX lx, LY ly, KEEP keep, double (&R)[9], doub
         my[c] = warp_sum_d(sy[c]) / cnt;
     }
     double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = lane; i < n; i += 32)
-        if (keep(i)) {
+    for (int i = lane; i < n; i += 32) {
+        const double w = wt(i);
+        if (w != 0.0) {
             double dx[3], dy[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 dx[c] = lx(c, i) - mx[c];
-                dy[c] = ly(c, i) - my[c];
+                dy[c] = w * (ly(c, i) - my[c]);
             }
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) H[3 * r + c] += dx[r] * dy[c];
         }
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) H[k] = warp_sum_d(H[k]);
-    polar_from_svd(H, R);
+    polar_from_svd(H, R, fix_reflection);
 #pragma unroll
     for (int r = 0; r < 3; ++r) t[r] = my[r] - (R[3 * r] * mx[0] + R[3 * r + 1] * mx[1] + R[3 * r + 2] * mx[2]);
 }
@@ -154,15 +179,15 @@ constexpr int KB_WARPS = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(KB_WARPS * 32)
-kabsch_kernel(const T *__restrict__ x, const T *__restrict__ y, int B, int n, double *__restrict__ Ro,
-              double *__restrict__ to) {
+kabsch_kernel(const T *__restrict__ x, const T *__restrict__ y, const double *__restrict__ wgt, int B, int n,
+              bool fix_reflection, double *__restrict__ Ro, double *__restrict__ to) {
     const int b = blockIdx.x * KB_WARPS + (threadIdx.x >> 5);
     if (b >= B) return;
     const T *xb = x + (int64_t)b * 3 * n, *yb = y + (int64_t)b * 3 * n;
     double R[9], t[3];
     kabsch_warp(
         n, [&](int c, int i) { return (double)xb[c * n + i]; }, [&](int c, int i) { return (double)yb[c * n + i]; },
-        [](int) { return true; }, R, t);
+        [&](int i) { return wgt ? wgt[(int64_t)b * n + i] : 1.0; }, fix_reflection, R, t);
     const int lane = lane_id();
     if (lane < 9) Ro[(int64_t)b * 9 + lane] = R[lane];
     if (lane < 3) to[(int64_t)b * 3 + lane] = t[lane];
@@ -172,7 +197,7 @@ constexpr int KR_MAXN = 1024;
 
 __global__ void __launch_bounds__(32)
 kabsch_refine_kernel(const double *__restrict__ x, const double *__restrict__ yp, const double *__restrict__ Rt,
-                     const double *__restrict__ tt, int n, int keepn, double *__restrict__ R2o,
+                     const double *__restrict__ tt, int n, int keepn, bool fix_reflection, double *__restrict__ R2o,
                      double *__restrict__ t2o, double *__restrict__ R1o, double *__restrict__ t1o) {
     __shared__ float s_ref[3][KR_MAXN];   // float32(y_pred1)
     __shared__ float s_d[KR_MAXN];        // 1-NN distance of y_true[i]
@@ -182,7 +207,7 @@ kabsch_refine_kernel(const double *__restrict__ x, const double *__restrict__ yp
     const double *Rg = Rt + (int64_t)b * 9, *tg = tt + (int64_t)b * 3;
     double R1[9], t1[3];
     auto lx = [&](int c, int i) { return xb[c * n + i]; };
-    kabsch_warp(n, lx, [&](int c, int i) { return yb[c * n + i]; }, [](int) { return true; }, R1, t1);
+    kabsch_warp(n, lx, [&](int c, int i) { return yb[c * n + i]; }, [](int) { return 1.0; }, fix_reflection, R1, t1);
     if (R1o && lane < 9) R1o[(int64_t)b * 9 + lane] = R1[lane];
     if (t1o && lane < 3) t1o[(int64_t)b * 3 + lane] = t1[lane];
     // y_pred1 = R1 x + t1 (float64), cast to float32 inside the KNN (knn_cuda casts)
@@ -217,7 +242,7 @@ kabsch_refine_kernel(const double *__restrict__ x, const double *__restrict__ yp
     double R2[9], t2[3];
     kabsch_warp(
         n, lx, [&](int c, int i) { return R1[3 * c] * lx(0, i) + R1[3 * c + 1] * lx(1, i) + R1[3 * c + 2] * lx(2, i) + t1[c]; },
-        [&](int i) { return s_keep[i] != 0; }, R2, t2);
+        [&](int i) { return s_keep[i] != 0 ? 1.0 : 0.0; }, fix_reflection, R2, t2);
     if (lane < 9) R2o[(int64_t)b * 9 + lane] = R2[lane];
     if (lane < 3) t2o[(int64_t)b * 3 + lane] = t2[lane];
 }
@@ -226,14 +251,15 @@ kabsch_refine_kernel(const double *__restrict__ x, const double *__restrict__ yp
 
 using namespace dvcp;
 
-extern "C" int dvcp_kabsch(const void *x, const void *y, int dtype, int B, int n, double *R, double *t,
-                           dvcp_stream_t stream) {
+extern "C" int dvcp_kabsch(const void *x, const void *y, int dtype, const double *weights, int B, int n, int quirks,
+                           double *R, double *t, dvcp_stream_t stream) {
     if (!x || !y || !R || !t || B <= 0 || n <= 0) return DVCP_E_ARG;
     const unsigned grid = (unsigned)((B + KB_WARPS - 1) / KB_WARPS);
+    const bool fix = !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX);
     if (dtype == 0)
-        kabsch_kernel<float><<<grid, KB_WARPS * 32, 0, (cudaStream_t)stream>>>((const float *)x, (const float *)y, B, n, R, t);
+        kabsch_kernel<float><<<grid, KB_WARPS * 32, 0, (cudaStream_t)stream>>>((const float *)x, (const float *)y, weights, B, n, fix, R, t);
     else if (dtype == 1)
-        kabsch_kernel<double><<<grid, KB_WARPS * 32, 0, (cudaStream_t)stream>>>((const double *)x, (const double *)y, B, n, R, t);
+        kabsch_kernel<double><<<grid, KB_WARPS * 32, 0, (cudaStream_t)stream>>>((const double *)x, (const double *)y, weights, B, n, fix, R, t);
     else
         return DVCP_E_ARG;
     DVCP_CHECK_LAUNCH();
@@ -241,12 +267,13 @@ extern "C" int dvcp_kabsch(const void *x, const void *y, int dtype, int B, int n
 }
 
 extern "C" int dvcp_kabsch_refine(const double *x, const double *y_pred, const double *R_true,
-                                  const double *t_true, int B, int n, int keep, double *R2, double *t2, double *R1,
-                                  double *t1, dvcp_stream_t stream) {
+                                  const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
+                                  double *R1, double *t1, dvcp_stream_t stream) {
     if (!x || !y_pred || !R_true || !t_true || !R2 || !t2 || B <= 0 || n <= 0 || keep <= 0 || keep > n)
         return DVCP_E_ARG;
     if (n > KR_MAXN) return DVCP_E_UNSUPPORTED;
-    kabsch_refine_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(x, y_pred, R_true, t_true, n, keep, R2, t2, R1, t1);
+    kabsch_refine_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(x, y_pred, R_true, t_true, n, keep,
+                                                             !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2, R1, t1);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

@@ -24,8 +24,8 @@ constexpr int KP_THREADS = 256;
 __global__ void __launch_bounds__(KP_THREADS)
 keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const int64_t *__restrict__ topk,
                       int Kp, const int64_t *__restrict__ kp_start, const float *__restrict__ src_feat, int S,
-                      const double *__restrict__ R_init, float radius2, int nsample, dvcp_dfe_params_t P,
-                      int ref_layout, float *__restrict__ keypts, int64_t *__restrict__ picked,
+                      const double *__restrict__ R_init, const double *__restrict__ t_init, int64_t t_bstride,
+                      float radius2, int nsample, dvcp_dfe_params_t P, int ref_layout, float *__restrict__ keypts, int64_t *__restrict__ picked,
                       float *__restrict__ src_cat, float *__restrict__ src_dfe, double *__restrict__ centres) {
     __shared__ __align__(16) float s_w[DFE_SMEM_FLOATS];
     __shared__ float s_kp[KP_MAX * KP_MAXC];
@@ -64,8 +64,11 @@ keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const 
             double *o = centres + ((int64_t)b * Kp + k) * 3;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
+            {
                 o[r] = __dadd_rn(__dadd_rn(__dmul_rn(R[3 * r], (double)x), __dmul_rn(R[3 * r + 1], (double)y)),
                                  __dmul_rn(R[3 * r + 2], (double)z));
+                if (t_init) o[r] = __dadd_rn(o[r], t_init[(int64_t)b * t_bstride + r]);   // intended mode only (Q6)
+            }
         }
     }
     __syncthreads();
@@ -173,7 +176,8 @@ using namespace dvcp;
 
 extern "C" int dvcp_keypoint_stage(const float *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
                                    const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
-                                   float radius2, int nsample, dvcp_dfe_params_t dfe, int quirks, float *keypts,
+                                   const double *t_init, int64_t t_bstride, float radius2, int nsample,
+                                   dvcp_dfe_params_t dfe, int quirks, float *keypts,
                                    int64_t *picked, float *src_cat, float *src_dfe, double *centres,
                                    dvcp_stream_t stream) {
     if (!src_pts || !topk || !kp_start || !src_feat || B <= 0 || N <= 0 || S <= 0) return DVCP_E_ARG;
@@ -181,7 +185,9 @@ extern "C" int dvcp_keypoint_stage(const float *src_pts, int C_in, int B, int N,
     if (!dfe.W1 || !dfe.b1 || !dfe.W2 || !dfe.b2 || !dfe.W3 || !dfe.b3) return DVCP_E_ARG;
     if (C_in < 3 || C_in > KP_MAXC || Kp < 1 || Kp > KP_MAX || nsample != 32 || Kp > S) return DVCP_E_UNSUPPORTED;
     keypoint_stage_kernel<<<B, KP_THREADS, 0, (cudaStream_t)stream>>>(src_pts, C_in, N, topk, Kp, kp_start, src_feat,
-                                                                    S, R_init, radius2, nsample, dfe, quirks & 1,
+                                                                    S, R_init,
+                                                                    (quirks & DVCP_QUIRK_IGNORE_T_INIT) ? nullptr : t_init,
+                                                                    t_bstride, radius2, nsample, dfe, quirks & 1,
                                                                     keypts, picked, src_cat, src_dfe, centres);
     DVCP_CHECK_LAUNCH();
     return 0;

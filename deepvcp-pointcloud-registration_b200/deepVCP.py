@@ -17,13 +17,14 @@ materialised):
 
 B > 1 means B independent pairs (the reference only runs B = 1).
 Reference-mode quirks are on by default and individually
-switchable through `quirks`.
+switchable through `quirks` (bits QUIRK_* of _lib.py; QUIRKS_INTENDED = 0 selects
+the semantics the reference's code intends for Q3, Q4, Q6, Q7 -- SURVEY 8f rank 2).
 """
 import torch
 import torch.nn as nn
 
 from . import functional as F_
-from ._lib import QUIRKS_REFERENCE, cloud_cm, cloud_pm, require_cuda
+from ._lib import QUIRK_COST_VOLUME_RESHAPE, QUIRKS_REFERENCE, cloud_cm, cloud_pm, require_cuda
 from .cpg import cpg
 from .deep_feat_embedding import feat_embedding_layer
 from .deep_feat_extraction import feat_extraction_layer
@@ -72,7 +73,7 @@ class DeepVCP(nn.Module):
         """src_pts, tgt_pts [B,C_in,N]; R_init [B,3,3] float64; t_init [1,3] (unused by
         the reference, quirk Q6) -> (src_keypts [B,K,3], tgt_vcp [B,K,3])."""
         fe = self.extract_features(src_pts, tgt_pts, starts)
-        return self.match(fe, R_init, keep_stages=keep_stages, topk_override=topk_override)
+        return self.match(fe, R_init, keep_stages=keep_stages, topk_override=topk_override, t_init=t_init)
 
     def _mark(self, name, dev):
         if self._events is not None:
@@ -147,7 +148,7 @@ class DeepVCP(nn.Module):
         return dict(src=src, tgt=tgt, both=both, index=index, fps2=fps2, feat2=feat2, starts=starts, B=B, N=N,
                     C_in=C_in, dev=dev)
 
-    def match(self, fe, R_init, keep_stages=False, topk_override=None):
+    def match(self, fe, R_init, keep_stages=False, topk_override=None, t_init=None):
         """Second half of forward(): key-point selection, candidates, KNN, embedding, CPG
         (deepVCP.py:33-110) on the state extract_features() returned."""
         src, tgt, index, fps2, feat2, starts = fe["src"], fe["tgt"], fe["index"], fe["fps2"], fe["feat2"], fe["starts"]
@@ -166,7 +167,7 @@ class DeepVCP(nn.Module):
             dfe = self.DFE.params()
             keypts, picked, cat, src_dfe, centres = F_.keypoint_stage(
                 src, topk, starts[1], sfeat, R, self.group_radius, ns, dfe, self.quirks,
-                want_cat=keep_stages, want_picked=keep_stages)
+                want_cat=keep_stages, want_picked=keep_stages, t_init=t_init)
             # candidates, KNN, target-side embedding
             G = F_.grid_size(self.r, self.s)
             cand = F_.candidates(centres, self.r, self.s, G)                 # [B,K,C,3]
@@ -195,7 +196,10 @@ class DeepVCP(nn.Module):
                                            self.quirks)
             mark("dfe")
             # corresponding point generation
-            vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.view(B * K, C * 32), 1,
+            # tgt_dfe is [candidate, feature] in memory: layout 1 applies the reference's permute + reshape
+            # (Q4); layout 0 reads it as it is, i.e. cost[c, f] = (src[f] - tgt[c, f])^2 (intended mode)
+            vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.view(B * K, C * 32),
+                                 1 if self.quirks & QUIRK_COST_VOLUME_RESHAPE else 0,
                                  cand.view(B * K, C, 3), G, self.cpg.params(), want_logits=keep_stages)
             mark("cpg")
         if keep_stages:

@@ -243,7 +243,7 @@ def topk(scores, K):
 
 
 def keypoint_stage(src_pts, topk_idx, kp_start, src_feat, R_init, radius, nsample, dfe, quirks,
-                   want_cat=False, want_picked=False):
+                   want_cat=False, want_picked=False, t_init=None):
     require_cuda(src_pts, topk_idx, src_feat, R_init)
     B, C_in, N = src_pts.shape
     Kp = topk_idx.shape[1]
@@ -253,13 +253,20 @@ def keypoint_stage(src_pts, topk_idx, kp_start, src_feat, R_init, radius, nsampl
     src_feat = _f32c(src_feat)
     R_init = R_init.to(torch.float64).contiguous()
     kp_start = _starts_to_device(kp_start, B, dev)
+    t_dev, t_stride = None, 0
+    if t_init is not None and not (quirks & _lib.QUIRK_IGNORE_T_INIT):
+        t_dev = torch.as_tensor(t_init).to(dev, torch.float64).reshape(-1, 3).contiguous()
+        if t_dev.shape[0] not in (1, B):
+            raise RuntimeError("t_init must be [1,3] or [B,3]")
+        t_stride = 3 if t_dev.shape[0] == B and B > 1 else 0
     keypts = torch.empty(B, Kp, C_in, dtype=torch.float32, device=dev)
     picked = torch.empty(B, Kp, nsample, dtype=torch.int64, device=dev) if want_picked else None
     cat = torch.empty(B, Kp, nsample, 35, dtype=torch.float32, device=dev) if want_cat else None
     sdfe = torch.empty(B, Kp, 32, dtype=torch.float32, device=dev)
     centres = torch.empty(B, Kp, 3, dtype=torch.float64, device=dev)
     code = lib().dvcp_keypoint_stage(ptr(src_pts), C_in, B, N, ptr(topk_idx.contiguous()), Kp, ptr(kp_start),
-                                     ptr(src_feat), S, ptr(R_init), radius2_f32(radius), nsample, dfe, quirks,
+                                     ptr(src_feat), S, ptr(R_init), ptr(t_dev), t_stride, radius2_f32(radius),
+                                     nsample, dfe, quirks,
                                      ptr(keypts), ptr(picked), ptr(cat), ptr(sdfe), ptr(centres), stream_ptr(dev))
     check(code, "dvcp_keypoint_stage")
     _count(1)
@@ -388,21 +395,24 @@ def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False):
     return vcp, logits
 
 
-def kabsch(x, y):
-    """x, y [B,3,n] float32/float64 -> R [B,3,3], t [B,3,1] float64."""
-    require_cuda(x, y)
+def kabsch(x, y, quirks=_lib.QUIRKS_REFERENCE, weights=None):
+    """x, y [B,3,n] float32/float64 -> R [B,3,3], t [B,3,1] float64. weights [B,n] (optional):
+    weighted solve; quirks without QUIRK_NO_REFLECTION_FIX: det R = +1."""
+    require_cuda(x, y, weights)
     if x.dtype != y.dtype or x.dtype not in (torch.float32, torch.float64):
         raise RuntimeError("kabsch: x and y must share a float32/float64 dtype")
     B, _, n = x.shape
     R = torch.empty(B, 3, 3, dtype=torch.float64, device=x.device)
     t = torch.empty(B, 3, 1, dtype=torch.float64, device=x.device)
-    check(lib().dvcp_kabsch(ptr(x.contiguous()), ptr(y.contiguous()), 0 if x.dtype == torch.float32 else 1, B, n,
-                            ptr(R), ptr(t), stream_ptr(x.device)), "dvcp_kabsch")
+    if weights is not None:
+        weights = weights.to(torch.float64).reshape(B, n).contiguous()
+    check(lib().dvcp_kabsch(ptr(x.contiguous()), ptr(y.contiguous()), 0 if x.dtype == torch.float32 else 1,
+                            ptr(weights), B, n, quirks, ptr(R), ptr(t), stream_ptr(x.device)), "dvcp_kabsch")
     _count(1)
     return R, t
 
 
-def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False):
+def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False, quirks=_lib.QUIRKS_REFERENCE):
     require_cuda(x, y_pred, R_true, t_true)
     B, _, n = x.shape
     dev = x.device
@@ -415,7 +425,7 @@ def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False)
     t2 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev)
     R1 = torch.empty(B, 3, 3, dtype=torch.float64, device=dev) if want_first else None
     t1 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev) if want_first else None
-    check(lib().dvcp_kabsch_refine(ptr(x), ptr(y_pred), ptr(R_true), ptr(t_true), B, n, keep, ptr(R2), ptr(t2),
+    check(lib().dvcp_kabsch_refine(ptr(x), ptr(y_pred), ptr(R_true), ptr(t_true), B, n, keep, quirks, ptr(R2), ptr(t2),
                                    ptr(R1), ptr(t1), stream_ptr(dev)), "dvcp_kabsch_refine")
     _count(1)
     return R2, t2, R1, t1

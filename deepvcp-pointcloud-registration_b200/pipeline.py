@@ -39,7 +39,7 @@ class StreamedRegistration:
         self.timing = False    # development: completion events carry timestamps
         self.trace = []
 
-    def submit(self, src, tgt, R_init, R_true, t_true, starts=None, host_out=None):
+    def submit(self, src, tgt, R_init, R_true, t_true, starts=None, host_out=None, t_init=None):
         """Enqueue one batch: src, tgt [B,C_in,N], R_init / R_true [B,3,3], t_true [B,3,1] (host or
         device tensors). host_out: optional pinned [B,12] float64 tensor the poses are copied into."""
         k = len(self.done)
@@ -66,8 +66,8 @@ class StreamedRegistration:
         ms = self.match_stream
         with torch.cuda.stream(ms):
             ms.wait_event(ev_fe)
-            kp, vcp = self.model.match(fe, Ri)
-            R2, t2 = pose_from_forward(kp, vcp, Rt, tt)
+            kp, vcp = self.model.match(fe, Ri, t_init=t_init)   # t_init is only read in intended mode (Q6)
+            R2, t2 = pose_from_forward(kp, vcp, Rt, tt, quirks=self.model.quirks)
             poses = pack_poses(R2, t2)
             if host_out is not None:
                 host_out.copy_(poses, non_blocking=True)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DVCP_ABI_VERSION 1
+#define DVCP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DVCP_API __attribute__((visibility("default")))
@@ -45,6 +45,16 @@ extern "C" {
 #define DVCP_E_ARG        (-1) /* null pointer / non-positive size            */
 #define DVCP_E_UNSUPPORTED (-2) /* size outside what the kernels are built for */
 #define DVCP_E_WORKSPACE  (-3) /* workspace too small                          */
+
+/* Reference-mode quirks. A set bit REPLICATES what the reference does; a clear bit
+ * selects the semantics its code intends. DVCP_QUIRKS_REFERENCE is the drop-in mode. */
+#define DVCP_QUIRK_KEYPOINT_VIEW       1  /* Q3  deepVCP.py:46        gather result re-read row-major as [K, C]        */
+#define DVCP_QUIRK_PER_FEATURE_WEIGHT  2  /* Q7  get_cat_feat_tgt.py:65,92  distance weight indexed by feature         */
+#define DVCP_QUIRK_COST_VOLUME_RESHAPE 4  /* Q4  deepVCP.py:106 + cpg.py:34 (feature, candidate) axes scrambled;
+                                             host-side: selects `layout` of dvcp_cpg                                  */
+#define DVCP_QUIRK_IGNORE_T_INIT       8  /* Q6  deepVCP.py:86-91     t_init never added to the transformed key-points */
+#define DVCP_QUIRK_NO_REFLECTION_FIX  16  /* Q10 deepVCP_loss.py:36-40 R = V U^T may have det = -1                     */
+#define DVCP_QUIRKS_REFERENCE         31
 
 typedef void *dvcp_stream_t;
 
@@ -169,8 +179,10 @@ DVCP_API int dvcp_topk(const float *scores, int B, int S, int K, int64_t *topk, 
 /* ---- a9..a11 + a15(src)  key-point stage            deepVCP.py:44-67,86-91,101
  * src_pts [B,C_in,N] channel-major float32; topk [B,Kp] int64; kp_start [B]
  * int64 (FPS start among the key-points, deepVCP.py:54 -> pointnet2_utils.py:75);
- * src_feat [B,S,32] (FPS order); R_init [B,3,3] float64; dfe = {W1[32,35],b1,
- * W2[32,32],b2,W3[32,32],b3}. quirks: bit 0 = reference key-point layout (Q3).
+ * src_feat [B,S,32] (FPS order); R_init [B,3,3] float64; t_init float64 (may be null), pair b reads
+ * t_init[b * t_bstride + 0..2] (t_bstride 0 = one translation for all pairs, like the reference's [1,3]);
+ * dfe = {W1[32,35],b1,W2[32,32],b2,W3[32,32],b3}. quirks: DVCP_QUIRK_KEYPOINT_VIEW (Q3),
+ * DVCP_QUIRK_IGNORE_T_INIT (Q6: centres = R_init kp, t_init unused; clear: + t_init).
  * Outputs (any may be null): keypts [B,Kp,C_in], picked [B,Kp,nsample] int64,
  * src_cat [B,Kp,nsample,35], src_dfe [B,Kp,32], centres [B,Kp,3] float64. */
 typedef struct {
@@ -178,7 +190,8 @@ typedef struct {
 } dvcp_dfe_params_t;
 DVCP_API int dvcp_keypoint_stage(const float *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
                         const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
-                        float radius2, int nsample, dvcp_dfe_params_t dfe, int quirks, float *keypts,
+                        const double *t_init, int64_t t_bstride, float radius2, int nsample,
+                        dvcp_dfe_params_t dfe, int quirks, float *keypts,
                         int64_t *picked, float *src_cat, float *src_dfe, double *centres,
                         dvcp_stream_t stream);
 
@@ -251,16 +264,18 @@ DVCP_API int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, co
 
 /* ---- a17 get_rigid_transform(x, y)                   deepVCP_loss.py:13-44
  * x, y [B,3,n] (dtype 0 float32 / 1 float64); R [B,3,3], t [B,3] float64.
- * R = V U^T without reflection correction (Q10). */
-DVCP_API int dvcp_kabsch(const void *x, const void *y, int dtype, int B, int n, double *R, double *t,
-                dvcp_stream_t stream);
+ * quirks & DVCP_QUIRK_NO_REFLECTION_FIX: R = V U^T as the reference computes it (Q10); clear: the
+ * reflection is corrected (det R = +1). weights [B,n] float64 (null = all 1): per-correspondence
+ * weights of the weighted solve (centroids and covariance weighted). */
+DVCP_API int dvcp_kabsch(const void *x, const void *y, int dtype, const double *weights, int B, int n, int quirks,
+                double *R, double *t, dvcp_stream_t stream);
 
 /* ---- a18 svd_optimization(x, y_pred, R_true, t_true)  deepVCP_loss.py:57-90
  * x, y_pred [B,3,n] float64; R_true [B,3,3], t_true [B,3] float64; keep =
  * int(0.8 n). Outputs R2 [B,3,3], t2 [B,3] float64; R1/t1 (first solve) may be
- * null. n <= 1024. */
+ * null. n <= 1024. quirks: DVCP_QUIRK_NO_REFLECTION_FIX as in dvcp_kabsch (both solves). */
 DVCP_API int dvcp_kabsch_refine(const double *x, const double *y_pred, const double *R_true,
-                       const double *t_true, int B, int n, int keep, double *R2, double *t2,
+                       const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
                        double *R1, double *t1, dvcp_stream_t stream);
 
 #ifdef __cplusplus

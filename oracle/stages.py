@@ -113,15 +113,16 @@ def topk_indices(scores, k=64):
 # --------------------------------------------------------------------------- #
 # key-point stage (deepVCP.py:44-67)
 # --------------------------------------------------------------------------- #
-def gather_keypoints(src_pts, topk_idx):
+def gather_keypoints(src_pts, topk_idx, view_quirk=True):
     """deepVCP.py:44-46 incl. the view-instead-of-permute layout,
-    with the channel count taken from the input (Q2). Per sample."""
+    with the channel count taken from the input (Q2). Per sample.
+    view_quirk=False: the permute the code intends (key-point k = column k)."""
     B, C, N = src_pts.shape
     K = topk_idx.shape[1]
     out = torch.empty(B, K, C, dtype=src_pts.dtype)
     for b in range(B):
         g = src_pts[b][:, topk_idx[b]]                     # [C, K]
-        out[b] = g.reshape(K, C)                           # row-major re-read
+        out[b] = g.reshape(K, C) if view_quirk else g.t()  # row-major re-read / proper permute
     return out
 
 
@@ -147,8 +148,9 @@ def knn(ref, query, k):
     return native.knn(ref, query, k)
 
 
-def cat_feat_tgt(cand, tgt_xyz, tgt_feat, dist, idx):
-    """get_cat_feat_tgt.py:53-96 incl. the per-FEATURE weight (Q7).
+def cat_feat_tgt(cand, tgt_xyz, tgt_feat, dist, idx, per_feature_weight=True):
+    """get_cat_feat_tgt.py:53-96 (SURVEY A.6) incl. the per-FEATURE weight (Q7;
+    per_feature_weight=False: the per-neighbour weight of the commented line :64).
     cand [B,M,C,3] f32, dist/idx [B,M*C,K]. float64 result [B,M,C,K,3+F]."""
     B, M, C, _ = cand.shape
     K = idx.shape[-1]
@@ -158,7 +160,7 @@ def cat_feat_tgt(cand, tgt_xyz, tgt_feat, dist, idx):
     feat = index_points(tgt_feat, idx).view(B, M, C, K, Fd)
     xyz = index_points(tgt_xyz, idx).view(B, M, C, K, 3)
     local = xyz - cand.unsqueeze(3)
-    wmap = w.view(B, M, C, 1, K)                                      # broadcast over neighbours
+    wmap = w.view(B, M, C, 1, K) if per_feature_weight else w.view(B, M, C, K, 1)
     return torch.cat([local, feat * wmap], dim=4)        # f32 local part promoted to f64
 
 
@@ -175,17 +177,18 @@ def feat_embedding(sd, X):
     return X.max(dim=-2)[0]
 
 
-def cpg(sd, src_dfe, tgt_dfe_cf, cand, G):
+def cpg(sd, src_dfe, tgt_dfe_cf, cand, G, reshape_quirk=True):
     """cpg.py:27-60.
 
     src_dfe [B,M,32]; tgt_dfe_cf [B,M,C,32] as the DFE produces it (candidate,
     feature). The reference permutes it to [B,M,32,C] (deepVCP.py:106) and then
     re-reads that logical order as (C,32) (cpg.py:34): T'[c',f'] =
-    tgt[(c'*32+f') % C, (c'*32+f') // C]  (SURVEY Q4).
+    tgt[(c'*32+f') % C, (c'*32+f') // C]  (SURVEY Q4). reshape_quirk=False: the cost
+    volume the code intends, cost[c, f] = (src[f] - tgt[c, f])^2.
     """
     B, M, C, Fd = tgt_dfe_cf.shape
     assert C == G * G * G
-    scr = tgt_dfe_cf.permute(0, 1, 3, 2).reshape(B, M, C, Fd)
+    scr = tgt_dfe_cf.permute(0, 1, 3, 2).reshape(B, M, C, Fd) if reshape_quirk else tgt_dfe_cf
     cost = (src_dfe.view(B, M, 1, Fd) - scr).square()
     x = cost.view(B * M, G, G, G, Fd).permute(0, 4, 1, 2, 3)
     x = F.conv3d(x, sd["cpg.conv1.weight"], sd["cpg.conv1.bias"], padding=1)
@@ -200,23 +203,36 @@ def cpg(sd, src_dfe, tgt_dfe_cf, cand, G):
 # --------------------------------------------------------------------------- #
 # pose solve (deepVCP_loss.py:13-90)
 # --------------------------------------------------------------------------- #
-def get_rigid_transform(x, y):
-    """deepVCP_loss.py:13-44: R = V U^T, no reflection fix (Q10)."""
-    cx = x.mean(dim=2, keepdim=True)
-    cy = y.mean(dim=2, keepdim=True)
-    H = (x - cx) @ (y - cy).transpose(1, 2)
+def get_rigid_transform(x, y, reflection_fix=False, weights=None):
+    """deepVCP_loss.py:13-44: R = V U^T, no reflection fix (Q10).
+    Beyond the reference: reflection_fix=True applies the Z = diag(1, 1, det)
+    the reference builds but never uses (:36-40); weights [B,n] gives the weighted solve."""
+    if weights is None:
+        cx = x.mean(dim=2, keepdim=True)
+        cy = y.mean(dim=2, keepdim=True)
+        H = (x - cx) @ (y - cy).transpose(1, 2)
+    else:
+        w = weights.to(x.dtype).unsqueeze(1)               # [B,1,n]
+        cx = (x * w).sum(dim=2, keepdim=True) / w.sum(dim=2, keepdim=True)
+        cy = (y * w).sum(dim=2, keepdim=True) / w.sum(dim=2, keepdim=True)
+        H = ((x - cx) * w) @ (y - cy).transpose(1, 2)
     U, S, Vh = torch.linalg.svd(H)
-    R = Vh.transpose(1, 2) @ U.transpose(1, 2)
+    V = Vh.transpose(1, 2)
+    R = V @ U.transpose(1, 2)
+    if reflection_fix:
+        Z = torch.diag_embed(torch.stack([torch.ones_like(S[:, 0]), torch.ones_like(S[:, 0]),
+                                          torch.sign(torch.linalg.det(R))], dim=1))
+        R = V @ Z @ U.transpose(1, 2)
     t = cy - R @ cx
     return R, t
 
 
-def svd_optimization(x, y_pred, R_true, t_true, inlier_ratio=0.8):
+def svd_optimization(x, y_pred, R_true, t_true, inlier_ratio=0.8, reflection_fix=False):
     """deepVCP_loss.py:57-90. x, y_pred [B,3,n] float64."""
     y_true = R_true @ x + t_true
     y_pred = y_pred.double()
     n = y_pred.shape[2]
-    R1, t1 = get_rigid_transform(x, y_pred)
+    R1, t1 = get_rigid_transform(x, y_pred, reflection_fix)
     y1 = R1 @ x + t1
     d, _ = native.knn(y1.transpose(1, 2).float().contiguous(),
                       y_true.transpose(1, 2).float().contiguous(), 1)   # [B,n,1]
@@ -230,7 +246,7 @@ def svd_optimization(x, y_pred, R_true, t_true, inlier_ratio=0.8):
     gi = inl.unsqueeze(1).expand(-1, 3, -1)
     y1i = torch.gather(y1, 2, gi)
     x1 = torch.gather(x, 2, gi)
-    R2, t2 = get_rigid_transform(x1, y1i)
+    R2, t2 = get_rigid_transform(x1, y1i, reflection_fix)
     return R2, t2, R1, t1, inl
 
 
@@ -241,9 +257,17 @@ def grid_size(r, s):
     return int(math.ceil((2 * r + s / 2) / s - 1e-9))
 
 
+QUIRK_KEYPOINT_VIEW, QUIRK_PER_FEATURE_WEIGHT, QUIRK_COST_VOLUME_RESHAPE, QUIRK_IGNORE_T_INIT, \
+    QUIRK_NO_REFLECTION_FIX = 1, 2, 4, 8, 16
+QUIRKS_REFERENCE = 31
+
+
 def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsample=32,
-                    fe_radius=0.1, fe_nsample=256, topk_override=None):
+                    fe_radius=0.1, fe_nsample=256, topk_override=None, quirks=QUIRKS_REFERENCE, t_init=None):
     """One call = B independent B=1 forwards.
+
+    quirks (default: all set = the reference as it runs): a clear bit selects the semantics the
+    reference's code intends -- nothing of the reference pins those.
 
     src_pts/tgt_pts [B,C_in,N]; R_init [B,3,3] float64; starts = (src_start[B],
     kp_start[B], tgt_start[B]) the three FPS start draws in the reference's order
@@ -255,7 +279,7 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
         sd, src_pts, starts[0], radius=fe_radius, nsample=fe_nsample)
     o["scores"] = weighting_scores(sd, o["src_fe_feat"])
     o["topk_idx"] = topk_indices(o["scores"], k_topk) if topk_override is None else topk_override
-    kp = gather_keypoints(src_pts, o["topk_idx"])                     # [B,64,C_in]
+    kp = gather_keypoints(src_pts, o["topk_idx"], bool(quirks & QUIRK_KEYPOINT_VIEW))   # [B,64,C_in]
     o["src_keypts_full"] = kp
     kp_xyz = kp[:, :, :3].contiguous()
     new_xyz, grouped, picked, kp_fps = sample_and_group(k_topk, 1, nsample, kp_xyz, None, starts[1])
@@ -266,6 +290,8 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
     o["tgt_fe_xyz"], o["tgt_fe_feat"], o["tgt_fps"] = feat_extraction(
         sd, tgt_pts, starts[2], radius=fe_radius, nsample=fe_nsample)
     centres = (R_init @ kp_xyz.transpose(1, 2).double()).transpose(1, 2).contiguous()  # Q6: no t
+    if t_init is not None and not (quirks & QUIRK_IGNORE_T_INIT):
+        centres = centres + t_init.double().reshape(-1, 1, 3)
     o["centres"] = centres
     G = grid_size(r, s)
     cand = voxelize(centres, r, s, G)
@@ -273,17 +299,18 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
     Q = cand.shape[1] * cand.shape[2]
     dist, idx = knn(tgt_xyz, cand.reshape(B, Q, 3), nsample)
     o["knn_dist"], o["knn_idx"] = dist, idx
-    tgt_cat = cat_feat_tgt(cand, tgt_xyz, o["tgt_fe_feat"], dist, idx)
+    tgt_cat = cat_feat_tgt(cand, tgt_xyz, o["tgt_fe_feat"], dist, idx, bool(quirks & QUIRK_PER_FEATURE_WEIGHT))
     o["src_dfe"] = feat_embedding(sd, o["src_cat"])                   # [B,64,32]
     o["tgt_dfe"] = feat_embedding(sd, tgt_cat)                        # [B,64,C,32]
     del tgt_cat
-    o["vcp"], o["logits"] = cpg(sd, o["src_dfe"], o["tgt_dfe"], cand, G)
+    o["vcp"], o["logits"] = cpg(sd, o["src_dfe"], o["tgt_dfe"], cand, G, bool(quirks & QUIRK_COST_VOLUME_RESHAPE))
     o["src_keypts"] = kp_xyz
     return o
 
 
-def pose_from_forward(src_keypts, vcp, R_true, t_true):
+def pose_from_forward(src_keypts, vcp, R_true, t_true, quirks=QUIRKS_REFERENCE):
     """train.py:110 -> deepVCP_loss.py:105-121 (pose only)."""
     x = src_keypts.permute(0, 2, 1).double()
     y = vcp.permute(0, 2, 1).double()
-    return svd_optimization(x, y, R_true.double(), t_true.double())
+    return svd_optimization(x, y, R_true.double(), t_true.double(),
+                            reflection_fix=not (quirks & QUIRK_NO_REFLECTION_FIX))

@@ -803,3 +803,66 @@ def test_forward_vs_reference_record_at_native_operating_point(dv, synthetic):
     R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(1, 3, 1).to(DEV))
     assert rot_angle_deg(R2, T(g["R2"])) < ROT_TOL_DEG
     assert (t2.cpu() - T(g["t2"])).abs().max() < TRANS_TOL
+
+
+# ---------------------------------------- intended-semantics mode ------
+@pytest.mark.parametrize("quirks", [0, 31 - 4, 31 - 8, 31 - 1, 31 - 2, 31 - 16, 4 + 16])
+def test_forward_with_quirk_switches_vs_oracle(dv, synthetic, quirks):
+    """Every quirk bit cleared on its own and all of them cleared ("intended" mode: proper key-point
+    permute, per-neighbour weights, un-scrambled cost volume, t_init applied, reflection fix): CUDA
+    path against the oracle with the same switches. Indices bit-exact, features 1e-5, pose north-star."""
+    N = 1024
+    src, tgt, R, t = synthetic.make_batch("modelnet", [31, 32], N)
+    torch.manual_seed(11)
+    model = dv.DeepVCP(use_normal=True, npoint=N, r=0.8, s=0.4, quirks=quirks).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    starts = (torch.tensor([5, 6]), torch.tensor([7, 8]), torch.tensor([9, 10]))
+    t_init = torch.tensor([[0.25, -0.5, 0.125], [-1.0, 0.0, 0.75]])
+    ref = stages.deepvcp_forward(sd, src, tgt, R, 0.8, 0.4, starts, quirks=quirks, t_init=t_init)
+    model = model.to(DEV)
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), t_init, starts=starts, keep_stages=True,
+                    topk_override=ref["topk_idx"])
+    L = model.last
+    assert torch.equal(L["src_keypts_full"].cpu(), ref["src_keypts_full"])
+    assert torch.equal(L["picked_idx"].cpu(), ref["picked_idx"])
+    assert torch.allclose(L["centres"].cpu(), ref["centres"], rtol=0, atol=1e-12)
+    if not (quirks & 8):
+        assert not torch.allclose(L["centres"].cpu(), (R @ ref["src_keypts"].transpose(1, 2).double()).transpose(1, 2))
+    assert torch.allclose(L["candidates"].cpu(), ref["candidates"], rtol=0, atol=4e-6)
+    if torch.equal(L["candidates"].cpu(), ref["candidates"]):
+        assert torch.equal(L["knn_idx"].cpu(), ref["knn_idx"])
+    assert rel_err(L["src_dfe"], ref["src_dfe"]) < 1e-5
+    assert rel_err(L["tgt_dfe"], ref["tgt_dfe"]) < 1e-5
+    assert rel_err(L["logits"], ref["logits"].view_as(L["logits"])) < 1e-4
+    assert (vcp.cpu() - ref["vcp"]).abs().max() < 5e-5
+    R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(2, 3, 1).to(DEV), quirks=quirks)
+    R2r, t2r, _, _, _ = stages.pose_from_forward(ref["src_keypts"], ref["vcp"], R, t.view(2, 3, 1), quirks=quirks)
+    assert rot_angle_deg(R2, R2r) < ROT_TOL_DEG and (t2.cpu() - t2r).abs().max() < TRANS_TOL
+    if not (quirks & 16):
+        assert (torch.det(R2.cpu()) > 0).all()
+
+
+def test_kabsch_reflection_fix_and_weights_vs_oracle(dv, F):
+    g = torch.Generator().manual_seed(17)
+    B, n = 512, 64
+    x = torch.randn(B, 3, n, generator=g, dtype=torch.float64)
+    Rg = torch.linalg.qr(torch.randn(B, 3, 3, generator=g, dtype=torch.float64))[0]
+    Rg = Rg * torch.sign(torch.det(Rg)).view(B, 1, 1)
+    Rg[1::2, :, 0] = -Rg[1::2, :, 0]                                                       # every other one improper
+    y = Rg @ x + torch.randn(B, 3, 1, generator=g, dtype=torch.float64) + 0.01 * torch.randn(B, 3, n, generator=g, dtype=torch.float64)
+    w = torch.rand(B, n, generator=g, dtype=torch.float64)
+    w[:, ::7] = 0.0
+    for quirks, fix in ((dv.QUIRKS_REFERENCE, False), (0, True)):
+        for weights in (None, w):
+            R, t = F.kabsch(x.to(DEV), y.to(DEV), quirks=quirks, weights=None if weights is None else weights.to(DEV))
+            Rr, tr = stages.get_rigid_transform(x, y, reflection_fix=fix, weights=weights)
+            assert rot_angle_deg(R, Rr) < ROT_TOL_DEG and (R.cpu() - Rr).abs().max() < 1e-9
+            assert (t.cpu() - tr).abs().max() < 1e-9
+            if fix:
+                assert torch.allclose(torch.det(R.cpu()), torch.ones(B, dtype=torch.float64), atol=1e-9)
+    Rq, _ = F.kabsch(x.to(DEV), y.to(DEV))
+    assert (torch.det(Rq.cpu()) < 0).any() and (torch.det(Rq.cpu()) > 0).any()          # reference mode keeps reflections
+    R2, t2, R1, t1 = F.kabsch_refine(x.to(DEV), y.to(DEV), Rg.to(DEV), torch.zeros(B, 3, 1, dtype=torch.float64).to(DEV),
+                                     want_first=True, quirks=0)
+    R2r, t2r, R1r, t1r, _ = stages.svd_optimization(x, y, Rg, torch.zeros(B, 3, 1, dtype=torch.float64), reflection_fix=True)
+    assert (R1.cpu() - R1r).abs().max() < 1e-9 and (R2.cpu() - R2r).abs().max() < 1e-8

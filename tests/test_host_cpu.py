@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(dv):
         assert hasattr(L, s), "missing export " + s
     lib = importlib.import_module(PKG + "._lib")
     assert sorted(lib.SIGNATURES) == syms          # the binding covers the whole header
-    assert dv.lib().dvcp_abi_version() == 1
+    assert dv.lib().dvcp_abi_version() == 2
     assert b"invalid argument" in dv.lib().dvcp_error_string(-1)
 
 

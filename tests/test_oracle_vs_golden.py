@@ -215,3 +215,44 @@ def test_forward_at_the_reference_native_operating_point(synthetic):
     R2, t2, _, _, _ = stages.pose_from_forward(o["src_keypts"], o["vcp"], R, t.view(1, 3, 1))
     assert torch.allclose(R2, T(g["R2"]), atol=1e-5)
     assert torch.allclose(t2, T(g["t2"]), atol=1e-4)
+
+
+# ---- "intended semantics" switches of the oracle: nothing of the reference pins
+# ---- these, so they are held to identities against the reference-mode functions pinned above
+def test_intended_mode_switches_reduce_to_reference_mode_identities(prim):
+    g = torch.Generator().manual_seed(3)
+    # Q3: proper permute
+    pts = torch.randn(2, 6, 50, generator=g)
+    idx = torch.randint(0, 50, (2, 8), generator=g)
+    kp = stages.gather_keypoints(pts, idx, view_quirk=False)
+    assert torch.equal(kp[1, 3], pts[1, :, idx[1, 3]])
+    assert torch.equal(stages.gather_keypoints(pts, idx)[0].reshape(-1), pts[0][:, idx[0]].reshape(-1))
+    # Q4: un-scrambled cost volume == reference mode fed with the inversely scrambled tensor
+    sd = golden_state_dict(prim, "cpg_sd/")
+    G, C = 5, 125
+    src, tgt, cand = torch.randn(1, 3, 32, generator=g), torch.randn(1, 3, C, 32, generator=g), torch.randn(1, 3, C, 3, generator=g)
+    pre = tgt.reshape(1, 3, 32, C).permute(0, 1, 3, 2).contiguous()      # permute + reshape of `pre` gives back `tgt`
+    a, _ = stages.cpg(sd, src, tgt, cand, G, reshape_quirk=False)
+    b, _ = stages.cpg(sd, src, pre, cand, G, reshape_quirk=True)
+    assert torch.equal(a, b)
+    # Q10 + weights
+    x = torch.randn(4, 3, 40, generator=g, dtype=torch.float64)
+    Rm = torch.linalg.qr(torch.randn(4, 3, 3, generator=g, dtype=torch.float64))[0]
+    Rm = Rm * torch.sign(torch.det(Rm)).view(4, 1, 1)
+    y = Rm @ x + 0.5
+    R0, t0 = stages.get_rigid_transform(x, y)
+    R1, t1 = stages.get_rigid_transform(x, y, reflection_fix=True)
+    assert torch.allclose(R0, R1, atol=1e-12) and torch.allclose(R1, Rm, atol=1e-10)     # proper input: no change
+    ym = y.clone()
+    ym[:, 0] = -ym[:, 0]                                                                 # mirrored target
+    Rq, _ = stages.get_rigid_transform(x, ym)
+    Rf, _ = stages.get_rigid_transform(x, ym, reflection_fix=True)
+    assert (torch.det(Rq) < 0).all() and torch.allclose(torch.det(Rf), torch.ones(4, dtype=torch.float64), atol=1e-10)
+    w = torch.ones(4, 40, dtype=torch.float64)
+    Rw, tw = stages.get_rigid_transform(x, y, weights=w * 0.37)
+    assert torch.allclose(Rw, R0, atol=1e-12) and torch.allclose(tw, t0, atol=1e-12)
+    w[:, 25:] = 0
+    yn = y + torch.cat([torch.zeros(4, 3, 25, dtype=torch.float64), torch.randn(4, 3, 15, generator=g, dtype=torch.float64)], 2)
+    Rs, ts = stages.get_rigid_transform(x, yn, weights=w)
+    Rsub, tsub = stages.get_rigid_transform(x[:, :, :25], yn[:, :, :25])
+    assert torch.allclose(Rs, Rsub, atol=1e-12) and torch.allclose(ts, tsub, atol=1e-12)
