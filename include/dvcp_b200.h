@@ -278,6 +278,16 @@ DVCP_API int dvcp_kabsch_refine(const double *x, const double *y_pred, const dou
                        const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
                        double *R1, double *t1, dvcp_stream_t stream);
 
+/* ---- data ingest   KITTIDataset.py:11-16,39-46,67-84
+ * raw: the B scans concatenated, [sum M_b, 4] float32 (x, y, z, reflectance; 16-byte aligned); scan b is
+ * rows scan_offset[b] .. scan_offset[b+1]-1 (scan_offset [B+1] int64, device). idx [B,N] int64: the rows
+ * `downsample` keeps, relative to the scan (null = rows 0..N-1). src [B,3,N] float32 (the model's layout);
+ * tgt [B,3,N] (may be null) = float32(R_b @ double(src) + t_b) with R [B,9], t [B,3] float64;
+ * reflectance [B,N] (may be null). A row index outside its scan yields NaN coordinates. */
+DVCP_API int dvcp_ingest_kitti(const float *raw, const int64_t *scan_offset, const int64_t *idx, const double *R,
+                      const double *t, int B, int N, float *src, float *tgt, float *reflectance,
+                      dvcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -866,3 +866,27 @@ def test_kabsch_reflection_fix_and_weights_vs_oracle(dv, F):
                                      want_first=True, quirks=0)
     R2r, t2r, R1r, t1r, _ = stages.svd_optimization(x, y, Rg, torch.zeros(B, 3, 1, dtype=torch.float64), reflection_fix=True)
     assert (R1.cpu() - R1r).abs().max() < 1e-9 and (R2.cpu() - R2r).abs().max() < 1e-8
+
+
+# ------------------------------------------------------------ data ingest ------
+def test_kitti_ingest_matches_the_reference_loader_arithmetic(dv, synthetic):
+    """KITTIDataset.py:11-16,44-46,67-84 restated with numpy (seeded np.random like the reference)."""
+    rs = np.random.RandomState(5)
+    scans = [rs.randn(m, 4).astype(np.float32) * 20 for m in (30000, 23456, 16500)]
+    N = 16384
+    idx = np.stack([dv.KITTIDataset.downsample_indices(s.shape[0], N, rs) for s in scans])
+    _, _, R, t = synthetic.make_batch("kitti", [0, 1, 2], 64)
+    src, tgt, refl = dv.KITTIDataset.ingest(scans, idx, R, t, want_reflectance=True)
+    for b, s in enumerate(scans):
+        pts = s[idx[b], :]                                   # downsample
+        sp = pts[:, :3].T                                    # 3 x N float32
+        assert np.array_equal(src[b].cpu().numpy(), sp)
+        assert np.array_equal(refl[b, 0].cpu().numpy(), pts[:, 3])
+        tg = (R[b].numpy() @ sp + t[b].numpy().reshape(3, 1)).astype(np.float32)      # float64 like numpy promotes
+        assert np.allclose(tgt[b].cpu().numpy(), tg, rtol=2e-7, atol=1e-6)
+    # the ingested pair goes straight into the model
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=2.0, s=0.4).to(DEV).eval()
+    kp, vcp = model(src[:1], tgt[:1], R[:1].to(DEV), torch.zeros(1, 3))
+    assert torch.isfinite(vcp).all()
+    with pytest.raises(IndexError):
+        dv.KITTIDataset.ingest(scans, np.full((3, 8), 29999), R, t)
