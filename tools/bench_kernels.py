@@ -73,6 +73,13 @@ def main():
         "knn": lambda: F_.knn(lib.cloud_cm(tgt), dev, B, N, cand, 32, want64=False, want32=True),
         "knn_indexed": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=G * G, zline=G, want64=False, want32=True),
         "knn_indexed_zline": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=G, want64=False, want32=True),
+        "knn_chain1": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=1, want64=False, want32=True),
+        "knn_chain2": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=2, want64=False, want32=True),
+        "knn_chain4": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=4, want64=False, want32=True),
+        "knn_2lines": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=2 * G, zline=G, want64=False, want32=True),
+        "knn_3lines": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=3 * G, zline=G, want64=False, want32=True),
+        "knn_4lines": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=4 * G, zline=G, want64=False, want32=True),
+        "knn_6lines": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=6 * G, zline=G, want64=False, want32=True),
         "knn_indexed_kp": lambda: F_.knn_indexed(index, B, dev, B, N, cand, 32, chain=G * G * G, zline=G, want64=False, want32=True),
         "dfe": lambda: F_.dfe_tgt_fused(cand, lib.cloud_cm(tgt), tfeat, kd, ki, B, N, model.DFE.params(),
                                         lib.QUIRKS_REFERENCE),
