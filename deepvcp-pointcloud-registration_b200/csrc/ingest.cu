@@ -37,9 +37,25 @@ ingest_kitti_kernel(const float4 *__restrict__ raw, const int64_t *__restrict__ 
     }
 }
 
+// point-major float4 copy (x, y, z, 0) of a cloud given in any layout: one 16-byte load per gathered
+// neighbour in the embedding kernel
+__global__ void __launch_bounds__(256)
+pack_xyz4_kernel(Cloud c, int N, float4 *__restrict__ out) {
+    const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) out[(int64_t)b * N + n] = make_float4(c.at(b, n, 0), c.at(b, n, 1), c.at(b, n, 2), 0.f);
+}
+
 }  // namespace dvcp
 
 using namespace dvcp;
+
+extern "C" int dvcp_pack_xyz4(dvcp_cloud_t xyz, int B, int N, float *out, dvcp_stream_t stream) {
+    if (!xyz.base || !out || B <= 0 || N <= 0) return DVCP_E_ARG;
+    if (B > 65535 || ((uintptr_t)out & 15)) return DVCP_E_UNSUPPORTED;
+    pack_xyz4_kernel<<<dim3((N + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(as_cloud(xyz), N, reinterpret_cast<float4 *>(out));
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int dvcp_ingest_kitti(const float *raw, const int64_t *scan_offset, const int64_t *idx, const double *R,
                                  const double *t, int B, int N, float *src, float *tgt, float *reflectance,

@@ -195,19 +195,22 @@ kabsch_kernel(const T *__restrict__ x, const T *__restrict__ y, const double *__
 
 constexpr int KR_MAXN = 1024;
 
+// x, yp: element (b, c, i) at base[b * 3 * n + c * cs + i * ps] -- the reference's [B,3,n] float64 arguments
+// (cs = n, ps = 1) or the forward's own [B,n,3] float32 outputs (cs = 1, ps = 3; cast like .double())
+template <typename T>
 __global__ void __launch_bounds__(32)
-kabsch_refine_kernel(const double *__restrict__ x, const double *__restrict__ yp, const double *__restrict__ Rt,
+kabsch_refine_kernel(const T *__restrict__ x, const T *__restrict__ yp, int cs, int ps, const double *__restrict__ Rt,
                      const double *__restrict__ tt, int n, int keepn, bool fix_reflection, double *__restrict__ R2o,
                      double *__restrict__ t2o, double *__restrict__ R1o, double *__restrict__ t1o) {
     __shared__ float s_ref[3][KR_MAXN];   // float32(y_pred1)
     __shared__ float s_d[KR_MAXN];        // 1-NN distance of y_true[i]
     __shared__ unsigned char s_keep[KR_MAXN];
     const int b = blockIdx.x, lane = lane_id();
-    const double *xb = x + (int64_t)b * 3 * n, *yb = yp + (int64_t)b * 3 * n;
+    const T *xb = x + (int64_t)b * 3 * n, *yb = yp + (int64_t)b * 3 * n;
     const double *Rg = Rt + (int64_t)b * 9, *tg = tt + (int64_t)b * 3;
     double R1[9], t1[3];
-    auto lx = [&](int c, int i) { return xb[c * n + i]; };
-    kabsch_warp(n, lx, [&](int c, int i) { return yb[c * n + i]; }, [](int) { return 1.0; }, fix_reflection, R1, t1);
+    auto lx = [&](int c, int i) { return (double)xb[c * cs + i * ps]; };
+    kabsch_warp(n, lx, [&](int c, int i) { return (double)yb[c * cs + i * ps]; }, [](int) { return 1.0; }, fix_reflection, R1, t1);
     if (R1o && lane < 9) R1o[(int64_t)b * 9 + lane] = R1[lane];
     if (t1o && lane < 3) t1o[(int64_t)b * 3 + lane] = t1[lane];
     // y_pred1 = R1 x + t1 (float64), cast to float32 inside the KNN (knn_cuda casts)
@@ -272,8 +275,21 @@ extern "C" int dvcp_kabsch_refine(const double *x, const double *y_pred, const d
     if (!x || !y_pred || !R_true || !t_true || !R2 || !t2 || B <= 0 || n <= 0 || keep <= 0 || keep > n)
         return DVCP_E_ARG;
     if (n > KR_MAXN) return DVCP_E_UNSUPPORTED;
-    kabsch_refine_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(x, y_pred, R_true, t_true, n, keep,
-                                                             !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2, R1, t1);
+    kabsch_refine_kernel<double><<<B, 32, 0, (cudaStream_t)stream>>>(x, y_pred, n, 1, R_true, t_true, n, keep,
+                                                                     !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2, R1, t1);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dvcp_pose_from_forward(const float *src_keypts, const float *tgt_vcp, const double *R_true,
+                                      const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
+                                      dvcp_stream_t stream) {
+    if (!src_keypts || !tgt_vcp || !R_true || !t_true || !R2 || !t2 || B <= 0 || n <= 0 || keep <= 0 || keep > n)
+        return DVCP_E_ARG;
+    if (n > KR_MAXN) return DVCP_E_UNSUPPORTED;
+    kabsch_refine_kernel<float><<<B, 32, 0, (cudaStream_t)stream>>>(src_keypts, tgt_vcp, 1, 3, R_true, t_true, n, keep,
+                                                                    !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2,
+                                                                    nullptr, nullptr);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

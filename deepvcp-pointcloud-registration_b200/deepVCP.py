@@ -188,7 +188,7 @@ class DeepVCP(nn.Module):
             if self.dfe_tensor_cores:
                 b_hi, b_lo = self.DFE.tc_operand()
                 # point-major float4 copy of the target xyz: one 16-byte load per gathered neighbour
-                tgt4 = torch.nn.functional.pad(tgt[:, :3].transpose(1, 2), (0, 1)).contiguous()
+                tgt4 = F_.pack_xyz4(cloud_cm(tgt), dev, B, N)
                 tgt_dfe = F_.dfe_tgt_tc(cand.view(B, K * C, 3), cloud_pm(tgt4), tfeat, kd, ki32, B, N, b_hi, b_lo,
                                         self.quirks)                           # [B,K*C,32]
             else:

@@ -26,7 +26,10 @@ def svd_optimization(x, y_pred, R_true, t_true, quirks=QUIRKS_REFERENCE):
 
 def pose_from_forward(src_keypts, tgt_vcp, R_true, t_true, quirks=QUIRKS_REFERENCE):
     """train.py:110 -> deepVCP_loss.py:105-107,121: permute to [B,3,N], double,
-    two-stage solve. Returns R [B,3,3], t [B,3,1] float64."""
+    two-stage solve -- done inside one kernel that reads the forward's float32
+    [B,N,3] outputs in place. Returns R [B,3,3], t [B,3,1] float64."""
+    if src_keypts.dtype == torch.float32 and tgt_vcp.dtype == torch.float32:
+        return F_.pose_from_forward(src_keypts, tgt_vcp, R_true, t_true, quirks=quirks)
     x = src_keypts.permute(0, 2, 1).double()
     y = tgt_vcp.permute(0, 2, 1).double()
     R2, t2, _, _ = F_.kabsch_refine(x, y, R_true, t_true, quirks=quirks)

@@ -354,6 +354,14 @@ def dfe_tc_operand(W1, b1, W2, b2, W3, b3, device):
     return img_hi.to(device), img_lo.to(device)
 
 
+def pack_xyz4(xyz_cloud: Cloud, device, B, N):
+    """[B,N,4] float32 (x, y, z, 0) copy of a cloud in any layout."""
+    out = torch.empty(B, N, 4, dtype=torch.float32, device=device)
+    check(lib().dvcp_pack_xyz4(xyz_cloud, B, N, ptr(out), stream_ptr(device)), "dvcp_pack_xyz4")
+    _count(1)
+    return out
+
+
 def dfe_tgt_tc(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, b_hi, b_lo, quirks):
     require_cuda(cand, tgt_feat, knn_dist, knn_idx32, b_hi, b_lo)
     Q = knn_dist.shape[1]
@@ -429,3 +437,22 @@ def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False,
                                    ptr(R1), ptr(t1), stream_ptr(dev)), "dvcp_kabsch_refine")
     _count(1)
     return R2, t2, R1, t1
+
+
+def pose_from_forward(src_keypts, tgt_vcp, R_true, t_true, inlier_ratio=0.8, quirks=_lib.QUIRKS_REFERENCE):
+    """svd_optimization on the forward's [B,n,3] float32 outputs, read in place (no permute / cast copies)."""
+    require_cuda(src_keypts, tgt_vcp, R_true, t_true)
+    B, n, _ = src_keypts.shape
+    dev = src_keypts.device
+    if src_keypts.dtype != torch.float32 or tgt_vcp.dtype != torch.float32:
+        raise RuntimeError("pose_from_forward: float32 key-points expected")
+    kp, vcp = src_keypts.contiguous(), tgt_vcp.contiguous()     # no-ops for the forward's outputs
+    Rt = R_true if R_true.dtype == torch.float64 and R_true.is_contiguous() else R_true.double().contiguous()
+    tt = t_true.reshape(B, 3, -1)[:, :, 0] if t_true.dim() == 3 else t_true.reshape(B, 3)
+    tt = tt if tt.dtype == torch.float64 and tt.is_contiguous() else tt.double().contiguous()
+    R2 = torch.empty(B, 3, 3, dtype=torch.float64, device=dev)
+    t2 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev)
+    check(lib().dvcp_pose_from_forward(ptr(kp), ptr(vcp), ptr(Rt), ptr(tt), B, n, int(n * inlier_ratio), quirks,
+                                       ptr(R2), ptr(t2), stream_ptr(dev)), "dvcp_pose_from_forward")
+    _count(1)
+    return R2, t2

@@ -278,6 +278,18 @@ DVCP_API int dvcp_kabsch_refine(const double *x, const double *y_pred, const dou
                        const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
                        double *R1, double *t1, dvcp_stream_t stream);
 
+/* train.py:110 -> deepVCP_loss.py:105-107,121: svd_optimization on the forward's own outputs. src_keypts,
+ * tgt_vcp [B,n,3] float32 (cast to float64 like .double(), read in place: no permute / cast copies);
+ * R_true [B,3,3], t_true [B,3] float64 -> R2 [B,3,3], t2 [B,3] float64. Same arithmetic as
+ * dvcp_kabsch_refine on the permuted float64 copies. */
+DVCP_API int dvcp_pose_from_forward(const float *src_keypts, const float *tgt_vcp, const double *R_true,
+                           const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
+                           dvcp_stream_t stream);
+
+/* Layout helper of the forward: out [B,N,4] float32 = (x, y, z, 0) per point of a cloud given in any layout
+ * (dvcp_dfe_tgt_tc gathers neighbours with one 16-byte load from it). */
+DVCP_API int dvcp_pack_xyz4(dvcp_cloud_t xyz, int B, int N, float *out, dvcp_stream_t stream);
+
 /* ---- data ingest   KITTIDataset.py:11-16,39-46,67-84
  * raw: the B scans concatenated, [sum M_b, 4] float32 (x, y, z, reflectance; 16-byte aligned); scan b is
  * rows scan_offset[b] .. scan_offset[b+1]-1 (scan_offset [B+1] int64, device). idx [B,N] int64: the rows

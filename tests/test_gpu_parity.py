@@ -890,3 +890,24 @@ def test_kitti_ingest_matches_the_reference_loader_arithmetic(dv, synthetic):
     assert torch.isfinite(vcp).all()
     with pytest.raises(IndexError):
         dv.KITTIDataset.ingest(scans, np.full((3, 8), 29999), R, t)
+
+
+def test_pose_from_forward_kernel_equals_refine_on_permuted_copies(dv, F):
+    """dvcp_pose_from_forward reads the forward's float32 [B,n,3] outputs in place; same arithmetic as
+    dvcp_kabsch_refine on the permuted float64 copies the reference makes (deepVCP_loss.py:105-107)."""
+    g = torch.Generator().manual_seed(23)
+    B, n = 37, 64
+    kp = torch.randn(B, n, 3, generator=g)
+    Rg = torch.linalg.qr(torch.randn(B, 3, 3, generator=g, dtype=torch.float64))[0]
+    tg = torch.randn(B, 3, 1, generator=g, dtype=torch.float64)
+    vcp = ((Rg @ kp.double().transpose(1, 2) + tg).transpose(1, 2) + 0.05 * torch.randn(B, n, 3, generator=g)).float()
+    for quirks in (dv.QUIRKS_REFERENCE, 0):
+        R2, t2 = dv.pose_from_forward(kp.to(DEV), vcp.to(DEV), Rg.to(DEV), tg.to(DEV), quirks=quirks)
+        Rr, tr, _, _ = F.kabsch_refine(kp.to(DEV).permute(0, 2, 1).double(), vcp.to(DEV).permute(0, 2, 1).double(),
+                                       Rg.to(DEV), tg.to(DEV), quirks=quirks)
+        assert torch.equal(R2, Rr) and torch.equal(t2, tr)
+    kp6 = torch.randn(B, n, 6, generator=g).to(DEV)                     # use_normal=True: a strided slice
+    R2, t2 = dv.pose_from_forward(kp6[:, :, :3], vcp.to(DEV), Rg.to(DEV), tg.to(DEV))
+    Rr, tr, _, _ = F.kabsch_refine(kp6[:, :, :3].permute(0, 2, 1).double(), vcp.to(DEV).permute(0, 2, 1).double(),
+                                   Rg.to(DEV), tg.to(DEV))
+    assert torch.equal(R2, Rr) and torch.equal(t2, tr)
