@@ -5,21 +5,26 @@
 // Linear layers have no activation between them (deep_feat_embedding.py:48-50), so
 // they are one affine map 35 -> 32; the host collapses them in float64
 // (Wc = W3 W2 W1, bc = W3 (W2 b1 + b2) + b3) and this kernel evaluates
-//     Y[128 x 32] = A[128 x 40] * Bm[40 x 32]
+//     Y^T[32 x 128] = Bm[32 x 40] * A^T[40 x 128]
 // per tile of 4 candidates x 32 neighbours, K = 32 weighted features + 3 local
 // coordinates + 1 (bias) + 4 zero columns, as a TF32 tensor-core GEMM with the
-// 3xTF32 split (A = Ah + Al, B = Bh + Bl; Ah*Bh + Al*Bh + Ah*Bl, FP32 accumulate
+// 3xTF32 split (A = Ah + Al, B = Bh + Bl; Bh*Ah + Bh*Al + Bl*Ah, FP32 accumulate
 // in TMEM), which keeps FP32-level accuracy (error ~2^-21 relative).
 //
-// Roles in a CTA (17 warps, one persistent CTA per SM, 4 A stages + 4 TMEM accumulators):
-//   warps 0-3   epilogue: tcgen05.ld of their 32 TMEM lanes (= one candidate's 32
-//               neighbours), butterfly max over the lanes (the max-pool over K), one
-//               coalesced 128-byte store;
-//   warps 4-15  producers, 3 groups of 4 (group g builds tiles g, g+3, ...): gather the
+// The WEIGHTS are the M-side operand (rows 32..127 of its 128-row image are zero) and the gathered
+// neighbour rows the N-side operand, so the accumulator is channel-major: TMEM lane = output channel,
+// column = neighbour. The max-pool over a candidate's 32 neighbours is then 31 FMNMX over the 32
+// registers one tcgen05.ld returns -- no shuffles (the row-major form needed a 63-shuffle butterfly per
+// warp and tile). The tensor pipe does 4x the useful work for it; it has the headroom (14 % busy before).
+//
+// Roles in a CTA (14 warps, one persistent CTA per SM, 4 operand stages + 4 TMEM accumulators of 128 columns):
+//   warp 0      epilogue: per candidate one tcgen05.ld of its 32 TMEM lanes (channels) x 32 columns
+//               (neighbours), max in registers, one coalesced 128-byte store;
+//   warps 1-12  producers, 3 groups of 4 (group g builds tiles g, g+3, ...): gather the
 //               neighbours' feature rows into registers (next tile's indices are already
 //               in flight), scale by the float64 distance weights carried as float pairs,
 //               split hi/lo, store into shared memory in the UMMA K-major core-matrix layout;
-//   warp 16     allocates TMEM, waits for A, issues the 15 tcgen05.mma of a tile from
+//   warp 13     allocates TMEM, waits for the operand, issues the 15 tcgen05.mma of a tile from
 //               one lane and commits to the mbarriers.
 // A is gathered (index-driven) and cannot be described by a TMA tensor map; the
 // operands reach the tensor core through shared-memory matrix descriptors.
@@ -27,20 +32,23 @@
 
 namespace dvcp {
 
+constexpr unsigned TC_M = 128;                   // UMMA M (32 channels used; M = 64 has another TMEM lane mapping and is no faster: measured)
 constexpr int TC_K = 40;                       // padded reduction length
 constexpr int TC_ROWS = 128;                   // rows per tile = 4 candidates x 32 neighbours
 constexpr int TC_A_SW_BYTES = TC_ROWS * 128;    // A plane, columns 0..31: 128-byte rows, SWIZZLE_128B (K-major)
 constexpr int TC_A_TAIL_BYTES = TC_ROWS * 32;   // A plane, columns 32..39: no-swizzle core matrices, K = 8
 constexpr int TC_A_BYTES = TC_A_SW_BYTES + TC_A_TAIL_BYTES;   // one A plane (hi or lo)
-constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one B plane
+constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one weight plane as the host lays it out (32 channels)
+constexpr int TC_BW_BYTES = 128 * TC_K * 4;     // the same plane as the 128-row M-side operand (rows 32..127 zero)
+constexpr int TC_ACC_COLS = 128;                // TMEM columns per accumulator (= rows of a tile)
 constexpr int TC_STAGES = 4;                   // shared-memory A stages == TMEM accumulators
-constexpr int TC_GROUPS = 3;                   // producer groups of 4 warps (one candidate per warp)
-constexpr int TC_EPI_WARPS = 4;                // warps 0-3: their TMEM lane quadrant = their warp index
+constexpr int TC_GROUPS = 4;                   // producer groups of 4 warps (one candidate per warp)
+constexpr int TC_EPI_WARPS = 1;                // warp 0 reads TMEM lanes 0..31 = the 32 output channels
 constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS - 1
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
 constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
 constexpr int TC_W_BYTES = TC_PROD_WARPS * 32 * 8;   // per producer warp: (hi, lo) distance weight of each feature
-constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_W_BYTES + 256 + 1024;   // + alignment slack
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + 1024;   // + alignment slack
 
 // byte offset of element (row r, column k) in the K-major, no-swizzle canonical layout:
 // 8x(16 B) core matrices; core (r/8, k/4) at ((r/8) * (K/4) + k/4) * 128 B.
@@ -70,8 +78,8 @@ __device__ __forceinline__ uint64_t make_desc_tail(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
            (1ull << 46);
 }
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 32
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128 (channels, 32 used), N = 128 (rows of the tile)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((TC_M >> 4) << 24);
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -111,16 +119,17 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
     unsigned char *sA = smem;                                      // [stage][hi sw | lo sw | hi tail | lo tail]
-    unsigned char *sB = smem + TC_STAGES * 2 * TC_A_BYTES;         // [hi|lo][TC_B_BYTES]
-    float2 *sW = reinterpret_cast<float2 *>(sB + 2 * TC_B_BYTES);  // [producer warp][32]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_B_BYTES + TC_W_BYTES);
+    unsigned char *sB = smem + TC_STAGES * 2 * TC_A_BYTES;         // [hi|lo][TC_BW_BYTES]
+    float2 *sW = reinterpret_cast<float2 *>(sB + 2 * TC_BW_BYTES);  // [producer warp][32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_BW_BYTES + TC_W_BYTES);
     uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 3 * TC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * TC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < TC_B_BYTES / 4; i += blockDim.x) {
-        reinterpret_cast<float *>(sB)[i] = Bhi[i];
-        reinterpret_cast<float *>(sB + TC_B_BYTES)[i] = Blo[i];
+    // rows 0..31 of the 128-row operand are the host's 32-row image (the layout is row-block major), the rest zero
+    for (int i = threadIdx.x; i < TC_BW_BYTES / 4; i += blockDim.x) {
+        reinterpret_cast<float *>(sB)[i] = i < TC_B_BYTES / 4 ? Bhi[i] : 0.f;
+        reinterpret_cast<float *>(sB + TC_BW_BYTES)[i] = i < TC_B_BYTES / 4 ? Blo[i] : 0.f;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -133,7 +142,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     }
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((unsigned)(32 * TC_STAGES))
+                     "r"((unsigned)(TC_ACC_COLS * TC_STAGES))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -149,7 +158,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
 
     if (warp == TC_MMA_WARP) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t a_base = smem_u32(sA), b_hi = smem_u32(sB), b_lo = smem_u32(sB + TC_B_BYTES);
+        const uint32_t a_base = smem_u32(sA), b_hi = smem_u32(sB), b_lo = smem_u32(sB + TC_BW_BYTES);
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
@@ -157,20 +166,21 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             mbar_wait(&tempty[s], ph ^ 1);      // accumulator s drained (tile i - TC_STAGES)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t d = tmem_base + (uint32_t)s * 32u;   // 32 FP32 columns per accumulator
+                const uint32_t d = tmem_base + (uint32_t)s * TC_ACC_COLS;   // 128 FP32 columns per accumulator
                 const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_SW_BYTES;
                 const uint32_t t_hi = a_hi + 2 * TC_A_SW_BYTES, t_lo = t_hi + TC_A_TAIL_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t ka = (uint32_t)ks * 32;          // 8 floats inside the 128-byte swizzled row
                     const uint32_t kb = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks of B per MMA (K = 8)
-                    umma_tf32(d, make_desc_sw128(a_hi + ka), make_desc(b_hi + kb), ks > 0);
-                    umma_tf32(d, make_desc_sw128(a_lo + ka), make_desc(b_hi + kb), 1u);
-                    umma_tf32(d, make_desc_sw128(a_hi + ka), make_desc(b_lo + kb), 1u);
+                    // M-side operand: the weights; N-side operand: the gathered rows
+                    umma_tf32(d, make_desc(b_hi + kb), make_desc_sw128(a_hi + ka), ks > 0);
+                    umma_tf32(d, make_desc(b_hi + kb), make_desc_sw128(a_lo + ka), 1u);
+                    umma_tf32(d, make_desc(b_lo + kb), make_desc_sw128(a_hi + ka), 1u);
                 }
-                umma_tf32(d, make_desc_tail(t_hi), make_desc(b_hi + 4 * 2 * 128), 1u);
-                umma_tf32(d, make_desc_tail(t_lo), make_desc(b_hi + 4 * 2 * 128), 1u);
-                umma_tf32(d, make_desc_tail(t_hi), make_desc(b_lo + 4 * 2 * 128), 1u);
+                umma_tf32(d, make_desc(b_hi + 4 * 2 * 128), make_desc_tail(t_hi), 1u);
+                umma_tf32(d, make_desc(b_hi + 4 * 2 * 128), make_desc_tail(t_lo), 1u);
+                umma_tf32(d, make_desc(b_lo + 4 * 2 * 128), make_desc_tail(t_hi), 1u);
                 umma_commit(&empty[s]);   // shared-memory stage may be rewritten
                 umma_commit(&tfull[s]);   // accumulator is complete
             }
@@ -178,43 +188,40 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         }
     } else if (warp < TC_EPI_WARPS) {
         // ------------------ epilogue: TMEM -> max over the 32 neighbours -> global ------------------
+        // lane = output channel; the 32 registers of one load are that channel's values for the 32 neighbours
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
-            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + warp;
+            const int64_t gq0 = (blockIdx.x + i * gridDim.x) * 4;
             mbar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)s * 32u;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float best[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (uint32_t)s * TC_ACC_COLS + (uint32_t)c * 32u;   // lanes 0..31
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float m = __uint_as_float(v[0]);
+#pragma unroll
+                for (int o = 1; o < 32; ++o) m = fmaxf(m, __uint_as_float(v[o]));
+                best[c] = m;
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[s]);
-            // max over the 32 neighbours (lanes): butterfly transpose-reduce, lane o ends with channel o
-            float y[32];
 #pragma unroll
-            for (int o = 0; o < 32; ++o) y[o] = __uint_as_float(v[o]);
-#pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) {
-                const bool up = (lane & st) != 0;
-#pragma unroll
-                for (int o = 0; o < st; ++o) {
-                    const float send = up ? y[o] : y[o + st];
-                    const float keep = up ? y[o + st] : y[o];
-                    y[o] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, st));
-                }
-            }
-            if (gq < total_cand) out[gq * 32 + lane] = y[0];
+            for (int c = 0; c < 4; ++c)
+                if (gq0 + c < total_cand) out[(gq0 + c) * 32 + lane] = best[c];
         }
     } else {
         // ---------------------- A producers: group g builds tiles g, g + TC_GROUPS, ... ----------------------
@@ -354,7 +361,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     __syncthreads();
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((unsigned)(32 * TC_STAGES))
+                     "r"((unsigned)(TC_ACC_COLS * TC_STAGES))
                      : "memory");
     }
 }
