@@ -134,3 +134,17 @@ def test_all_gather_poses_world2_gloo(tmp_path):
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_kitti_downsample_indices_follow_the_reference_draw(dv):
+    """KITTIDataset.py:11-16: np.random.choice(num_src, N, replace=False) when the scan is larger than N,
+    every row otherwise -- drawn on the same generator state, so a seeded run keeps the same points."""
+    import numpy as np
+    np.random.seed(7)
+    want = np.random.choice(30000, 10000, replace=False)
+    np.random.seed(7)
+    got = dv.KITTIDataset.downsample_indices(30000, 10000)
+    assert np.array_equal(got, want) and len(set(got.tolist())) == 10000
+    assert np.array_equal(dv.KITTIDataset.downsample_indices(500, 10000), np.arange(500))
+    with pytest.raises(RuntimeError):
+        dv.KITTIDataset.ingest([np.zeros((10, 4), np.float32)], None, device="cpu")
