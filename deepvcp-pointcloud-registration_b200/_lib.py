@@ -59,6 +59,7 @@ SIGNATURES = {
                               ctypes.POINTER(MlpLayer), c_i32, CloudIndex, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_sa_layer_all": (c_i32, [Cloud, Cloud, c_i32, c_vp, c_i32, c_i32, c_f32, c_i32, ctypes.POINTER(MlpLayer), c_i32,
                                   CloudIndex, c_vp, c_vp, c_vp]),
+    "dvcp_linear_rows": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_weighting_scores": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_topk": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_keypoint_stage": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64,

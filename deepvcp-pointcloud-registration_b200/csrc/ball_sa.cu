@@ -833,6 +833,33 @@ __global__ void index_points_i32_kernel(const float *__restrict__ pts, const int
     }
 }
 
+// ------------------------------------------------------ per-row Linear ------
+// y[row] = W x[row] + b, out <= 32 channels (lane = output channel), in <= 128. The fc that closes the
+// repaired three-layer feature extraction (deep_feat_extraction.py:15, never called by the reference).
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float *__restrict__ X, int64_t rows, int in, int out, const float *__restrict__ W,
+                   const float *__restrict__ bias, float *__restrict__ Y) {
+    extern __shared__ float lw[];   // [in][32]: W transposed, zero padded
+    for (int i = threadIdx.x; i < in * 32; i += blockDim.x) {
+        const int k = i >> 5, o = i & 31;
+        lw[i] = o < out ? __ldg(W + o * in + k) : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const float b = lane < out ? __ldg(bias + lane) : 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+        float xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = j * 32 + lane < in ? __ldg(X + r * in + j * 32 + lane) : 0.f;
+        float acc = b;
+        for (int k = 0; k < in; ++k) {
+            const float xk = __shfl_sync(0xffffffffu, xv[k >> 5], k & 31);
+            acc = fmaf(xk, lw[k * 32 + lane], acc);
+        }
+        if (lane < out) Y[r * out + lane] = acc;
+    }
+}
+
 // ---------------------------------------------------- weighting MLP ----------
 // One thread per point: 32 -> 16 (ReLU) -> 8 (ReLU) -> 1 (Softplus, beta 1,
 // threshold 20 as torch.nn.Softplus). Weights staged in shared memory.
@@ -1093,6 +1120,17 @@ extern "C" int dvcp_index_points_i32(const float *points, const int32_t *idx, in
     int64_t gx = (total + 255) / 256; if (gx > 148 * 16) gx = 148 * 16;
     dim3 grid((unsigned)gx, B);
     index_points_i32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, idx, N, C / 4, M, out);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dvcp_linear_rows(const float *X, int64_t rows, int in, int out, const float *W, const float *b,
+                                float *Y, dvcp_stream_t stream) {
+    if (!X || !W || !b || !Y || rows <= 0) return DVCP_E_ARG;
+    if (in < 1 || in > 128 || out < 1 || out > 32) return DVCP_E_UNSUPPORTED;
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > DVCP_NUM_SMS * 8) blocks = DVCP_NUM_SMS * 8;
+    linear_rows_kernel<<<(unsigned)blocks, 256, in * 32 * sizeof(float), (cudaStream_t)stream>>>(X, rows, in, out, W, b, Y);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

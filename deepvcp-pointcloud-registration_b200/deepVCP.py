@@ -33,10 +33,12 @@ from .weighting_layer import weighting_layer
 
 class DeepVCP(nn.Module):
     def __init__(self, use_normal, npoint=10000, fe_radius=0.1, fe_nsample=256, K_topk=64, nsample=32,
-                 r=1.0, s=0.4, group_radius=1, quirks=QUIRKS_REFERENCE):
+                 r=1.0, s=0.4, group_radius=1, quirks=QUIRKS_REFERENCE, chained_fe=False):
         super().__init__()
+        # chained_fe: the three-layer feature extraction the reference's file intends;
+        # default = what the reference can run (sa1 only)
         self.FE1 = feat_extraction_layer(use_normal=use_normal, npoint=npoint, radius=fe_radius,
-                                         nsample=fe_nsample)
+                                         nsample=fe_nsample, chained=chained_fe)
         self.WL = weighting_layer()
         self.DFE = feat_embedding_layer()
         self.cpg = cpg()
@@ -62,6 +64,11 @@ class DeepVCP(nn.Module):
     def draw_starts(self, B, N):
         """The three FPS start draws of one forward in the reference's order:
         FE(src) -> key-point grouping -> FE(tgt) (deepVCP.py:29,54,72)."""
+        if self.FE1.chained:   # one draw per set-abstraction layer
+            draw3 = lambda: torch.stack([F_.draw_fps_start(B, N) for _ in range(3)])
+            a = draw3()
+            k = F_.draw_fps_start(B, self.K_topk)
+            return (a, k, draw3())
         return (F_.draw_fps_start(B, N), F_.draw_fps_start(B, self.K_topk), F_.draw_fps_start(B, N))
 
     def stage_times_ms(self):
@@ -111,6 +118,16 @@ class DeepVCP(nn.Module):
             # feature extraction: source and target clouds go through each kernel in ONE
             # launch (2B independent clouds); features come out in FPS order
             both = torch.cat([src, tgt], dim=0)
+            if self.FE1.chained:
+                # three chained set-abstraction layers + fc through the module (one launch sequence for 2B clouds)
+                s0, s2 = torch.as_tensor(starts[0]), torch.as_tensor(starts[2])
+                st2 = torch.cat([s0.reshape(-1, B), s2.reshape(-1, B)], dim=1)      # [3, 2B] or [1, 2B]
+                _, feat2, fps2 = self.FE1(both, start=st2 if st2.shape[0] == 3 else st2[0], return_fps=True)
+                mark("fps")
+                mark("sa_layer")
+                index = F_.build_index(cloud_cm(both), dev, 2 * B, N) if F_.SpatialIndex.indexable(N) else None
+                return dict(src=src, tgt=tgt, both=both, index=index, fps2=fps2, feat2=feat2.contiguous(),
+                            starts=starts, B=B, N=N, C_in=C_in, dev=dev)
             st2 = torch.cat([torch.as_tensor(starts[0]).reshape(-1), torch.as_tensor(starts[2]).reshape(-1)])
             feat_cloud = cloud_cm(both[:, 3:, :]) if D else None
             if F_.SpatialIndex.indexable(N) and N > 2048 and 2 * S >= N:

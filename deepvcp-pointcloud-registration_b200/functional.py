@@ -221,6 +221,19 @@ def sa_layer_all(xyz_cloud, feats_cloud, D, identity_idx32, B, N, radius, nsampl
     return out
 
 
+def linear_rows(X, W, b):
+    """X [..., in] float32 -> [..., out] = X W^T + b (out <= 32, in <= 128)."""
+    require_cuda(X, W, b)
+    X = _f32c(X)
+    out_ch, in_ch = W.shape
+    rows = X.numel() // in_ch
+    Y = torch.empty(*X.shape[:-1], out_ch, dtype=torch.float32, device=X.device)
+    check(lib().dvcp_linear_rows(ptr(X), rows, in_ch, out_ch, ptr(_f32c(W.detach())), ptr(_f32c(b.detach())), ptr(Y),
+                                 stream_ptr(X.device)), "dvcp_linear_rows")
+    _count(1)
+    return Y
+
+
 def weighting_scores(X, W1, b1, W2, b2, W3, b3):
     require_cuda(X)
     B, S, _ = X.shape

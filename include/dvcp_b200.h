@@ -167,6 +167,12 @@ DVCP_API int dvcp_sa_layer_all(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, cons
                       dvcp_cloud_index_t index, unsigned char *overflow_ws, float *out_feat,
                       dvcp_stream_t stream);
 
+/* Linear layer over rows: Y [rows,out] = X [rows,in] W^T + b (W [out,in] row-major; in <= 128, out <= 32).
+ * deep_feat_extraction.py:15 (`fc`): only used by the repaired three-layer feature extraction
+ * (SURVEY 8f rank 1); the reference never calls it. */
+DVCP_API int dvcp_linear_rows(const float *X, int64_t rows, int in, int out, const float *W, const float *b, float *Y,
+                     dvcp_stream_t stream);
+
 /* ---- a8  weighting_layer.forward(X, K)              weighting_layer.py:26-33
  * X [B,S,32]; W1[16,32] b1 W2[8,16] b2 W3[1,8] b3; scores [B,S] (softplus
  * output, may be null if only indices are wanted -> then `scores` is still

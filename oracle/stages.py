@@ -77,16 +77,24 @@ def set_abstraction(sd, prefix, n_layers, xyz, points, npoint, radius, nsample, 
     return new_xyz, feats, fps_idx
 
 
-def feat_extraction(sd, pts, start, npoint=None, radius=0.1, nsample=256):
+def feat_extraction(sd, pts, start, npoint=None, radius=0.1, nsample=256, chained=False):
     """deep_feat_extraction.py:18-32, runnable semantics = sa1 only.
 
     pts [B,C_in,N] channel-major like the reference. Returns xyz [B,S,3],
     feats [B,S,32] in FPS order, fps_idx [B,S].
+    chained=True (beyond the reference): the three-layer stack the file intends --
+    sa1 -> sa2 (radius 0.2, 128 samples) -> sa3 (0.4, 64), xyz and features handed on, then fc (:10-15);
+    start is then [3,B], one FPS start per layer; fps_idx is the last layer's.
     """
     xyz = pts[:, :3, :].permute(0, 2, 1).contiguous()
     nrm = pts[:, 3:, :].permute(0, 2, 1).contiguous() if pts.shape[1] > 3 else None
     npoint = pts.shape[2] if npoint is None else npoint
-    return set_abstraction(sd, "FE1.sa1", 3, xyz, nrm, npoint, radius, nsample, start)
+    if not chained:
+        return set_abstraction(sd, "FE1.sa1", 3, xyz, nrm, npoint, radius, nsample, start)
+    x1, f1, _ = set_abstraction(sd, "FE1.sa1", 3, xyz, nrm, npoint, radius, nsample, start[0])
+    x2, f2, _ = set_abstraction(sd, "FE1.sa2", 2, x1, f1, npoint, 0.2, 128, start[1])
+    x3, f3, fps3 = set_abstraction(sd, "FE1.sa3", 2, x2, f2, npoint, 0.4, 64, start[2])
+    return x3, F.linear(f3, sd["FE1.fc.weight"], sd["FE1.fc.bias"]), fps3
 
 
 # --------------------------------------------------------------------------- #
@@ -263,7 +271,8 @@ QUIRKS_REFERENCE = 31
 
 
 def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsample=32,
-                    fe_radius=0.1, fe_nsample=256, topk_override=None, quirks=QUIRKS_REFERENCE, t_init=None):
+                    fe_radius=0.1, fe_nsample=256, topk_override=None, quirks=QUIRKS_REFERENCE, t_init=None,
+                    chained_fe=False):
     """One call = B independent B=1 forwards.
 
     quirks (default: all set = the reference as it runs): a clear bit selects the semantics the
@@ -276,7 +285,7 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
     B, C_in, N = src_pts.shape
     o = {}
     o["src_fe_xyz"], o["src_fe_feat"], o["src_fps"] = feat_extraction(
-        sd, src_pts, starts[0], radius=fe_radius, nsample=fe_nsample)
+        sd, src_pts, starts[0], radius=fe_radius, nsample=fe_nsample, chained=chained_fe)
     o["scores"] = weighting_scores(sd, o["src_fe_feat"])
     o["topk_idx"] = topk_indices(o["scores"], k_topk) if topk_override is None else topk_override
     kp = gather_keypoints(src_pts, o["topk_idx"], bool(quirks & QUIRK_KEYPOINT_VIEW))   # [B,64,C_in]
@@ -288,7 +297,7 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
     o["src_cat"] = cat_feat_src(kp, grouped, keyfeats)
     tgt_xyz = tgt_pts[:, :3, :].permute(0, 2, 1).contiguous()
     o["tgt_fe_xyz"], o["tgt_fe_feat"], o["tgt_fps"] = feat_extraction(
-        sd, tgt_pts, starts[2], radius=fe_radius, nsample=fe_nsample)
+        sd, tgt_pts, starts[2], radius=fe_radius, nsample=fe_nsample, chained=chained_fe)
     centres = (R_init @ kp_xyz.transpose(1, 2).double()).transpose(1, 2).contiguous()  # Q6: no t
     if t_init is not None and not (quirks & QUIRK_IGNORE_T_INIT):
         centres = centres + t_init.double().reshape(-1, 1, 3)

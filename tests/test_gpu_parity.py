@@ -911,3 +911,39 @@ def test_pose_from_forward_kernel_equals_refine_on_permuted_copies(dv, F):
     Rr, tr, _, _ = F.kabsch_refine(kp6[:, :, :3].permute(0, 2, 1).double(), vcp.to(DEV).permute(0, 2, 1).double(),
                                    Rg.to(DEV), tg.to(DEV))
     assert torch.equal(R2, Rr) and torch.equal(t2, tr)
+
+
+# ------------------------------------ repaired three-layer feature extraction ------
+def test_chained_feature_extraction_and_forward_vs_oracle(dv, F, synthetic):
+    """chained_fe=True: sa1 -> sa2 -> sa3 -> fc with xyz and features handed on (what
+    deep_feat_extraction.py:10-15,26-28 intends; the reference itself crashes there).
+    FPS indices of every layer bit-exact, features 1e-5, pose within the north-star bar."""
+    N = 512
+    src, tgt, R, t = synthetic.make_batch("modelnet", [41, 42], N)
+    torch.manual_seed(13)
+    model = dv.DeepVCP(use_normal=True, npoint=N, r=0.8, s=0.4, chained_fe=True).eval()
+    assert model.FE1.sa2.mlp_convs[0].in_channels == 35 and model.FE1.sa3.mlp_convs[0].in_channels == 67
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    starts = (torch.randint(0, N, (3, 2), generator=g), torch.tensor([7, 8]), torch.randint(0, N, (3, 2), generator=g))
+    ref = stages.deepvcp_forward(sd, src, tgt, R, 0.8, 0.4, starts, chained_fe=True)
+    model = model.to(DEV)
+    xyz3, feat3, fps3 = model.FE1(src.to(DEV), start=starts[0], return_fps=True)
+    assert torch.equal(fps3.cpu().long(), ref["src_fps"])
+    assert torch.equal(xyz3.cpu(), ref["src_fe_xyz"])
+    assert rel_err(feat3, ref["src_fe_feat"]) < 1e-5
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts, keep_stages=True,
+                    topk_override=ref["topk_idx"])
+    L = model.last
+    assert torch.equal(L["tgt_fps"].cpu().long(), ref["tgt_fps"])
+    assert rel_err(L["tgt_fe_feat"], ref["tgt_fe_feat"]) < 1e-5
+    assert torch.equal(kp.cpu(), ref["src_keypts"])
+    assert rel_err(L["tgt_dfe"], ref["tgt_dfe"]) < 1e-5
+    assert (vcp.cpu() - ref["vcp"]).abs().max() < 5e-5
+    R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.view(2, 3, 1).to(DEV))
+    R2r, t2r, _, _, _ = stages.pose_from_forward(ref["src_keypts"], ref["vcp"], R, t.view(2, 3, 1))
+    assert rot_angle_deg(R2, R2r) < ROT_TOL_DEG and (t2.cpu() - t2r).abs().max() < TRANS_TOL
+    # the seeded draw order: three per cloud, the key-point draw in between
+    torch.manual_seed(99)
+    a = model.draw_starts(2, N)
+    assert a[0].shape == (3, 2) and a[1].shape == (2,) and a[2].shape == (3, 2)
