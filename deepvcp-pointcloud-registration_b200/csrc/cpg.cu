@@ -206,11 +206,13 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
         const bool active = vl < nv;
         __syncthreads();   // weights staged / the previous round is finished with the shared volumes
         if (tid < 32 * nv) s_src[tid >> 5][tid & 31] = __ldg(src + (m0 + (tid >> 5)) * 32 + (tid & 31));
-        float acc[4][8];
+        // conv1 accumulators as float pairs: the packed FFMA2 of sm_100 (two IEEE FMAs per instruction, same
+        // results) halves the issue slots of the kernel's dominant instruction
+        float2 acc[4][4];
 #pragma unroll
         for (int v = 0; v < 4; ++v)
 #pragma unroll
-            for (int o = 0; o < 8; ++o) acc[v][o] = __ldg(p.b1 + ch * 8 + o);
+            for (int o = 0; o < 4; ++o) acc[v][o] = make_float2(__ldg(p.b1 + ch * 8 + 2 * o), __ldg(p.b1 + ch * 8 + 2 * o + 1));
 
         for (int half = 0; half < 2; ++half) {
             __syncthreads();   // s_src staged; the previous half's reads of the cost volumes are finished
@@ -263,12 +265,12 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
 #pragma unroll
                                 for (int o4 = 0; o4 < 2; ++o4) {
                                     const float4 w = w4[o4];
+                                    const float2 wa = make_float2(w.x, w.y), wb = make_float2(w.z, w.w);
 #pragma unroll
                                     for (int v = 0; v < 4; ++v) {
-                                        acc[v][4 * o4] = fmaf(w.x, in[v + dz], acc[v][4 * o4]);
-                                        acc[v][4 * o4 + 1] = fmaf(w.y, in[v + dz], acc[v][4 * o4 + 1]);
-                                        acc[v][4 * o4 + 2] = fmaf(w.z, in[v + dz], acc[v][4 * o4 + 2]);
-                                        acc[v][4 * o4 + 3] = fmaf(w.w, in[v + dz], acc[v][4 * o4 + 3]);
+                                        const float2 x2 = make_float2(in[v + dz], in[v + dz]);
+                                        acc[v][2 * o4] = __ffma2_rn(wa, x2, acc[v][2 * o4]);
+                                        acc[v][2 * o4 + 1] = __ffma2_rn(wb, x2, acc[v][2 * o4 + 1]);
                                     }
                                 }
                             }
@@ -284,17 +286,21 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
             for (int v = 0; v < 4; ++v)
                 if (z0 + v < G) {
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) A[(ch * 8 + o) * Cp + c0 + v] = acc[v][o];
+                    for (int o = 0; o < 4; ++o) {
+                        A[(ch * 8 + 2 * o) * Cp + c0 + v] = acc[v][o].x;
+                        A[(ch * 8 + 2 * o + 1) * Cp + c0 + v] = acc[v][o].y;
+                    }
                 }
         }
         __syncthreads();
         // ---- conv2 16 -> 4 ----
         if (active && ch == 0) {
-            float a2[4][4];
+            float2 a2[4][2];
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-#pragma unroll
-                for (int o = 0; o < 4; ++o) a2[v][o] = __ldg(p.b2 + o);
+            for (int v = 0; v < 4; ++v) {
+                a2[v][0] = make_float2(__ldg(p.b2), __ldg(p.b2 + 1));
+                a2[v][1] = make_float2(__ldg(p.b2 + 2), __ldg(p.b2 + 3));
+            }
             for (int dx = -1; dx <= 1; ++dx) {
                 const int xx = x + dx;
                 if (xx < 0 || xx >= G) continue;
@@ -316,10 +322,9 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
                             const float4 w = *reinterpret_cast<const float4 *>(W2 + ((tap0 + dz) * 16 + ci) * 4);
 #pragma unroll
                             for (int v = 0; v < 4; ++v) {
-                                a2[v][0] = fmaf(w.x, in[v + dz], a2[v][0]);
-                                a2[v][1] = fmaf(w.y, in[v + dz], a2[v][1]);
-                                a2[v][2] = fmaf(w.z, in[v + dz], a2[v][2]);
-                                a2[v][3] = fmaf(w.w, in[v + dz], a2[v][3]);
+                                const float2 x2 = make_float2(in[v + dz], in[v + dz]);
+                                a2[v][0] = __ffma2_rn(make_float2(w.x, w.y), x2, a2[v][0]);
+                                a2[v][1] = __ffma2_rn(make_float2(w.z, w.w), x2, a2[v][1]);
                             }
                         }
                     }
@@ -330,7 +335,10 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
             for (int v = 0; v < 4; ++v)
                 if (z0 + v < G) {
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) O2[o * Cp + c0 + v] = a2[v][o];
+                    for (int o = 0; o < 2; ++o) {
+                        O2[(2 * o) * Cp + c0 + v] = a2[v][o].x;
+                        O2[(2 * o + 1) * Cp + c0 + v] = a2[v][o].y;
+                    }
                 }
         }
         __syncthreads();
