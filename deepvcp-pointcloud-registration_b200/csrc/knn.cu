@@ -232,6 +232,8 @@ constexpr float KNI_LOOSE = 3.0f;   // measured: K8 unchanged for >= 3, ModelNet
 struct KnnCtx {
     const float *box;          // bucket boxes of the cloud
     const float4 *spt;         // points in Morton order
+    const float4 *spt_lane;    // spt + lane: slot `lane` of bucket j is spt_lane[j * 32] (one IMAD.WIDE per visit)
+    const float4 *box_lane;    // box of bucket (g * TT + lane): box_lane[g * TT * 2]
     unsigned long long *buf;   // this warp's KNI_BUF-entry scratch list in shared memory
     int K;
     float loose;               // a chained bound above loose * (previous K-th squared distance) is not used
@@ -284,8 +286,9 @@ __device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const B
     auto bucket_lb = [&](int g) -> float {
         float l = INFINITY;
         if (lane < TT) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + lane) * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(g * TT + lane) * 8) + 1);
+            const float4 *bp = c.box_lane + g * (TT * 2);
+            const float4 b0 = __ldg(bp);
+            const float4 b1 = __ldg(bp + 1);
             if (b1.z > 0.f) l = box_lb(qx, qy, qz, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y);
         }
         return l;
@@ -358,7 +361,7 @@ __device__ __forceinline__ unsigned long long knn_query(const KnnCtx &c, const B
                 const int j = g * TT + __ffs(bm) - 1;
                 bm &= bm - 1;
                 const int pos = j * 32 + lane;
-                const float4 P = __ldg(spt + pos);   // unused slots: +inf coordinates, never within thr
+                const float4 P = __ldg(c.spt_lane + j * 32);   // unused slots: +inf coordinates, never within thr
                 const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
                 const bool qual = d2 <= thr;
                 const unsigned m = __ballot_sync(0xffffffffu, qual);
@@ -433,6 +436,11 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     ctx.box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
     ctx.spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
     ctx.buf = s_buf[warp];
+    ctx.spt_lane = ctx.spt + lane;
+    ctx.box_lane = reinterpret_cast<const float4 *>(ctx.box) + lane * 2;
+    // keep the two bases in registers: rematerialised from the kernel parameters they cost five address
+    // instructions and a constant load per bucket visit instead of one IMAD.WIDE
+    asm volatile("" : "+l"(ctx.spt_lane), "+l"(ctx.box_lane));
     ctx.K = K;
     ctx.loose = loose;
     Box6 sb[SB];
