@@ -190,8 +190,12 @@ template <bool BIG>
 struct KnnKey {
     static constexpr int DSH = BIG ? 33 : 32;
     __device__ __forceinline__ static unsigned long long make(float d2, int id, int pos) {
+        if constexpr (!BIG) {   // the low word is 32-bit arithmetic (one IMAD), the distance bits are the high word as they are
+            const unsigned lo = ((unsigned)id << 16) | (unsigned)pos;
+            return ((unsigned long long)__float_as_uint(d2) << 32) | lo;
+        }
         return ((unsigned long long)__float_as_uint(d2) << DSH) | ((unsigned long long)(unsigned)id << 16) |
-               (unsigned)(BIG ? pos >> 1 : pos);
+               (unsigned)(pos >> 1);
     }
     __device__ __forceinline__ static unsigned d2bits(unsigned long long k) { return (unsigned)(k >> DSH); }
     __device__ __forceinline__ static unsigned id(unsigned long long k) {
