@@ -299,13 +299,17 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             const double wl = live ? dj / sum : 0.0;
             const float whi = (float)wl, wlo = (float)(wl - (double)whi);
-            float4 wq[2];   // per-feature mode: (hi, lo) of my 4 channels 4 * chunk .. 4 * chunk + 3
+            // per-feature mode: the weights of my 4 channels 4 * chunk .. 4 * chunk + 3, high parts and low parts as
+            // two float4 (pairs of adjacent channels feed the packed FMUL2 / FFMA2 below without moves)
+            float4 wqh = make_float4(0.f, 0.f, 0.f, 0.f), wql = wqh;
             if (per_feature_weight) {
+                float *wsh = reinterpret_cast<float *>(myw), *wsl = wsh + 32;
                 __syncwarp();
-                myw[lane] = make_float2(whi, wlo);
+                wsh[lane] = whi;
+                wsl[lane] = wlo;
                 __syncwarp();
-                wq[0] = *reinterpret_cast<const float4 *>(myw + chunk * 4);
-                wq[1] = *reinterpret_cast<const float4 *>(myw + chunk * 4 + 2);
+                wqh = *reinterpret_cast<const float4 *>(wsh + chunk * 4);
+                wql = *reinterpret_cast<const float4 *>(wsl + chunk * 4);
             }
             // my neighbour's local coordinates + bias column
             const float4 loc = live ? make_float4(px - cx, py - cy, pz - cz, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,25 +319,29 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int row = 4 * g + rsub, trow = cw * 32 + row;
-                const float fe[4] = {f[g].x, f[g].y, f[g].z, f[g].w};
-                float wh[4], wlw[4];
+                float2 h01, h23, l01, l23;   // weight pairs
                 if (per_feature_weight) {
-                    wh[0] = wq[0].x; wlw[0] = wq[0].y; wh[1] = wq[0].z; wlw[1] = wq[0].w;
-                    wh[2] = wq[1].x; wlw[2] = wq[1].y; wh[3] = wq[1].z; wlw[3] = wq[1].w;
+                    h01 = make_float2(wqh.x, wqh.y); h23 = make_float2(wqh.z, wqh.w);
+                    l01 = make_float2(wql.x, wql.y); l23 = make_float2(wql.z, wql.w);
                 } else {
                     const float rhi = __shfl_sync(0xffffffffu, whi, row), rlo = __shfl_sync(0xffffffffu, wlo, row);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { wh[e] = rhi; wlw[e] = rlo; }
+                    h01 = h23 = make_float2(rhi, rhi);
+                    l01 = l23 = make_float2(rlo, rlo);
                 }
+                // v = fma(f, w_hi, f * w_lo); hi = v truncated to TF32 (exact); lo = v - hi (exact) -- two channels per
+                // packed instruction (FMUL2 / FFMA2 of sm_100: the same IEEE operations, half the issue slots)
+                const float2 f01 = make_float2(f[g].x, f[g].y), f23 = make_float2(f[g].z, f[g].w);
+                const float2 v01 = __ffma2_rn(f01, h01, __fmul2_rn(f01, l01));
+                const float2 v23 = __ffma2_rn(f23, h23, __fmul2_rn(f23, l23));
                 float4 hv, lv;
-                float *hp = &hv.x, *lp = &lv.x;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float v = fmaf(fe[e], wh[e], fe[e] * wlw[e]);
-                    const float t = __uint_as_float(__float_as_uint(v) & 0xffffe000u);   // exact TF32
-                    hp[e] = t;
-                    lp[e] = v - t;
-                }
+                hv.x = __uint_as_float(__float_as_uint(v01.x) & 0xffffe000u);
+                hv.y = __uint_as_float(__float_as_uint(v01.y) & 0xffffe000u);
+                hv.z = __uint_as_float(__float_as_uint(v23.x) & 0xffffe000u);
+                hv.w = __uint_as_float(__float_as_uint(v23.y) & 0xffffe000u);
+                const float2 m1 = make_float2(-1.f, -1.f);
+                const float2 d01 = __ffma2_rn(make_float2(hv.x, hv.y), m1, v01);   // v - hi, exact
+                const float2 d23 = __ffma2_rn(make_float2(hv.z, hv.w), m1, v23);
+                lv = make_float4(d01.x, d01.y, d23.x, d23.y);
                 const int off = trow * 128 + ((chunk ^ (trow & 7)) << 4);   // SWIZZLE_128B
                 *reinterpret_cast<float4 *>(ahi + off) = hv;
                 *reinterpret_cast<float4 *>(alo + off) = lv;
