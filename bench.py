@@ -132,6 +132,82 @@ def make_inputs(dv, rank, B):
     return dv.synthetic.make_batch(w["kind"], ids, w["n_points"])
 
 
+def time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, steps, barrier=None):
+    """K steps through the streamed API, CUDA events on the current stream around them. Returns ms."""
+    cur = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if barrier is not None:
+        barrier()
+    e0.record(cur)
+    for i in range(steps):
+        s_i, t_i = rot[i % len(rot)]
+        pipe.submit(s_i, t_i, d_R, d_R, d_t, starts=starts)
+    for st in pipe.streams:
+        cur.wait_stream(st)
+    e1.record(cur)
+    poses = pipe.collect()[-1]
+    if barrier is not None:
+        barrier()
+    return e0.elapsed_time(e1), poses
+
+
+def extra_config(torch, dv, dev, kind, B, N, G, use_normal, steps, depth):
+    """One of the other BASELINE.json configurations, measured in the same run with the same method
+    (streamed API, device time, rotating input copies larger than L2 together with the intermediates)."""
+    r = dv.synthetic.grid_radius(G)
+    src, tgt, R, t = dv.synthetic.make_batch(kind, list(range(B)), N)
+    torch.manual_seed(0)
+    model = dv.DeepVCP(use_normal=use_normal, npoint=N, r=r, s=0.4).to(dev).eval()
+    g = torch.Generator().manual_seed(7)
+    starts = (torch.randint(0, N, (B,), generator=g), torch.randint(0, 64, (B,), generator=g),
+              torch.randint(0, N, (B,), generator=g))
+    d_src, d_tgt, d_R, d_t = src.to(dev), tgt.to(dev), R.to(dev), t.view(B, 3, 1).to(dev)
+    n_rot = max(2, int(160e6 // (d_src.numel() * 8)) + 1)
+    rot = [(d_src.clone(), d_tgt.clone()) for _ in range(min(n_rot, 64))]
+    pipe = dv.StreamedRegistration(model, depth=depth)
+    time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, 3 * depth + 2)      # warm-up: pipeline + allocator pools
+    ms, _ = time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, steps)
+    return {"pairs_per_gpu": B, "n_points": N, "grid": "%d^3" % G, "steps": steps,
+            "ms_per_step": round(ms / steps, 4), "pairs_per_s": round(B * steps / (ms * 1e-3), 1)}
+
+
+def parity_check(torch, dv, dev, model, sd, src, tgt, R, t, starts):
+    """Pair 0 of the timed workload through the CUDA path and through the CPU oracle with the SAME
+    state_dict and FPS starts (key-point choice teacher-forced: torch.topk's tie order is unspecified).
+    Returns the oracle's wall time too (it doubles as the cpu_baseline sample)."""
+    from oracle import stages
+    w = WORKLOAD
+    st = tuple(x[:1] for x in starts)
+    t0 = time.perf_counter()
+    ref = stages.deepvcp_forward(sd, src[:1], tgt[:1], R[:1], w["r"], w["s"], st)
+    R2r, t2r, _, _, _ = stages.pose_from_forward(ref["src_keypts"], ref["vcp"], R[:1], t[:1].view(1, 3, 1))
+    cpu_s = time.perf_counter() - t0
+    kp, vcp = model(src[:1].to(dev), tgt[:1].to(dev), R[:1].to(dev), torch.zeros(1, 3), starts=st, keep_stages=True,
+                    topk_override=ref["topk_idx"])
+    L = model.last
+    R2, t2 = dv.pose_from_forward(kp, vcp, R[:1].to(dev), t[:1].view(1, 3, 1).to(dev))
+    d = R2.cpu() @ R2r.transpose(-1, -2)
+    sk = 0.5 * torch.stack([d[..., 2, 1] - d[..., 1, 2], d[..., 0, 2] - d[..., 2, 0], d[..., 1, 0] - d[..., 0, 1]], -1).norm(dim=-1)
+    c = ((d.diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2).clamp(-1, 1)
+    cand_same = bool(torch.equal(L["candidates"].cpu(), ref["candidates"]))
+    out = {
+        "pair": 0, "against": "oracle/stages.py (CPU port pinned to the reference's records), same weights and FPS starts",
+        "fps_idx_equal": bool(torch.equal(L["src_fps"].cpu().long(), ref["src_fps"]) and
+                              torch.equal(L["tgt_fps"].cpu().long(), ref["tgt_fps"])),
+        "keypoints_equal": bool(torch.equal(kp.cpu(), ref["src_keypts"])),
+        "candidates_equal": cand_same,
+        "knn_idx_equal": bool(torch.equal(L["knn_idx"].cpu(), ref["knn_idx"])),
+        "knn_dist_equal": bool(torch.equal(L["knn_dist"].cpu(), ref["knn_dist"])),
+        "tgt_dfe_max_rel": float((L["tgt_dfe"].cpu() - ref["tgt_dfe"]).abs().max() / ref["tgt_dfe"].abs().max()),
+        "vcp_max_abs": float((vcp.cpu() - ref["vcp"]).abs().max()),
+        "rot_deg": float(torch.rad2deg(torch.atan2(sk, c)).max()),
+        "trans_m": float((t2.cpu() - t2r).abs().max()),
+    }
+    out["ok"] = bool(out["fps_idx_equal"] and out["keypoints_equal"] and out["knn_idx_equal"] and
+                     out["vcp_max_abs"] < 5e-5 and out["rot_deg"] < 1e-3 and out["trans_m"] < 1e-4)
+    return out, cpu_s
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -152,7 +228,9 @@ def run_ours(args):
     Q = w["keypoints"] * G ** 3
     src, tgt, R, t = make_inputs(dv, rank, B)
     torch.manual_seed(0)
-    model = dv.DeepVCP(use_normal=False, npoint=N, r=w["r"], s=w["s"]).to(dev).eval()
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=w["r"], s=w["s"]).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev)
     g = torch.Generator().manual_seed(1000 + rank)
     starts = (torch.randint(0, N, (B,), generator=g), torch.randint(0, 64, (B,), generator=g),
               torch.randint(0, N, (B,), generator=g))
@@ -213,25 +291,19 @@ def run_ours(args):
         sampler.wait_first()
         sampler.mark()
     launches0 = F_.LAUNCHES
-    barrier()
-    cur = torch.cuda.current_stream(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pipe.timing = os.environ.get("DVCP_BENCH_TRACE") == "1"
     pipe.trace = []
-    e0.record(cur)
-    for i in range(args.steps):
-        s_i, t_i = rot[i % len(rot)]                                       # inputs never L2-resident (see rot)
-        pipe.submit(s_i, t_i, d_R, d_R, d_t, starts=starts)
-    for st in pipe.streams:
-        cur.wait_stream(st)
-    e1.record(cur)
-    poses = pipe.collect()[-1]
-    barrier()
+    ms_total, poses = time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, args.steps, barrier)
     if pipe.timing:
-        sys.stderr.write("trace (ms since start): " + " ".join("fe%.1f/m%.1f" % (e0.elapsed_time(a), e0.elapsed_time(b)) for a, b in pipe.trace) + "\n")
+        sys.stderr.write("trace: " + " ".join("fe%d/m%d" % (i, i) for i, _ in enumerate(pipe.trace)) + "\n")
         pipe.timing = False
     launches = F_.LAUNCHES - launches0
-    ms_total = e0.elapsed_time(e1)
+    # ---- sustained pass: the same loop for >= args.sustain seconds of device time (clocks settle) ----
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain * 1e3 / (ms_total / args.steps)) + 1)
+        ms_sus, _ = time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, n_sus, barrier)
+        sustained = (n_sus, ms_sus)
 
     # ---- e2e leg: pinned host buffers in, poses back in pinned host memory, wall clock ----
     h_poses = [torch.empty(B, 12, dtype=torch.float64).pin_memory() for _ in range(args.steps)]
@@ -251,10 +323,10 @@ def run_ours(args):
     # multi-GPU: the one collective of the path, then max over ranks
     all_poses = dv.sharding.all_gather_poses(poses, B * world)
     assert all_poses.shape == (B * world, 12)
-    tm = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms_total, e2e_s * 1e3, sustained[1] if sustained else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(tm[0]), float(tm[1])
+    ms_total, e2e_ms, ms_sus = float(tm[0]), float(tm[1]), float(tm[2])
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -309,8 +381,24 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_pose.numel() * 8},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if sustained:
+            out["sustained"] = {"value": round(pairs * sustained[0] / (ms_sus * 1e-3), 3), "unit": "pairs/s",
+                                "steps": sustained[0], "seconds": round(ms_sus * 1e-3, 3)}
+        if world == 1 and not args.no_extra:
+            # the other BASELINE.json configurations in the same run (configs[1] and one rank's share of configs[3])
+            out["extra_configs"] = {
+                "M64": extra_config(torch, dv, dev, "modelnet", 64, 1024, 5, True, 20, args.depth),
+                "K256_per_gpu_32": extra_config(torch, dv, dev, "kitti", 32, 16384, 11, False, 5, args.depth),
+            }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_port_baseline(steps=3, warmup=1)
+            torch.set_num_threads(os.cpu_count() or 1)
+            pc, cpu_s = parity_check(torch, dv, dev, model, sd, src, tgt, R, t, starts)
+            out["parity_check"] = pc
+            # the same pair, weights and starts as the parity check (whose oracle pass was the warm-up)
+            base = cpu_port_baseline(steps=2, warmup=0, state=(sd, src[:1], tgt[:1], R[:1], t[:1],
+                                                                tuple(x[:1] for x in starts)))
+            base["parity_pair_s"] = round(cpu_s, 3)
+            out["cpu_baseline"] = base
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -338,11 +426,11 @@ def cpu_port_state():
     return sd, src, tgt, R, t, starts
 
 
-def cpu_port_baseline(steps, warmup):
+def cpu_port_baseline(steps, warmup, state=None):
     """The oracle port of the reference's CPU path on ONE pair of the workload."""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    state = cpu_port_state()
+    state = cpu_port_state() if state is None else state
     for _ in range(warmup):
         cpu_port_once(state)
     t0 = time.perf_counter()
@@ -377,9 +465,6 @@ def run_reference(args):
 
 
 def main():
-    # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -387,6 +472,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (1 = one at a time)")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the extra sustained timed pass (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs (M64, K256 share) measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -77,6 +77,7 @@ SIGNATURES = {
     "dvcp_dfe_dense": (c_i32, [c_vp, c_i32, c_i64, c_i32, DfeParams, c_vp, c_vp]),
     "dvcp_cpg_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "dvcp_cpg": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, CpgParams, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "dvcp_cpg_path": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, CpgParams, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "dvcp_pose_from_forward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_pack_xyz4": (c_i32, [Cloud, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_ingest_kitti": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),

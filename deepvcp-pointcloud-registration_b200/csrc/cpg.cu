@@ -417,16 +417,18 @@ extern "C" int64_t dvcp_cpg_workspace_bytes(int64_t M, int G) {
     return M * (int64_t)G * G * G * (32 + 16 + 4 + 1) * (int64_t)sizeof(float);
 }
 
-extern "C" int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
-                        int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
-                        int64_t workspace_bytes, dvcp_stream_t stream) {
+extern "C" int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
+                             int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
+                             int64_t workspace_bytes, int path, dvcp_stream_t stream) {
     if (!src_dfe || !tgt_dfe || !cand || !vcp || !workspace || M <= 0 || G <= 0) return DVCP_E_ARG;
     if (!p.w1 || !p.b1 || !p.w2 || !p.b2 || !p.w3 || !p.b3 || (layout != 0 && layout != 1)) return DVCP_E_ARG;
     if (M > 65535 || G > 64) return DVCP_E_UNSUPPORTED;
     if (workspace_bytes < dvcp_cpg_workspace_bytes(M, G)) return DVCP_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int C = G * G * G;
-    if (G <= CF_MAXG) {
+    if (path < DVCP_CPG_AUTO || path > DVCP_CPG_LAYERED) return DVCP_E_ARG;
+    if (path == DVCP_CPG_FUSED && G > CF_MAXG) return DVCP_E_UNSUPPORTED;
+    if (G <= CF_MAXG && path != DVCP_CPG_LAYERED) {
         const int Cp = (C + 3) & ~3;
         const int items = G * G * ((G + 3) / 4);
         int VPC = CF_ITEMS / items;          // volumes per CTA round: all 384 item threads busy on small grids
@@ -466,4 +468,11 @@ extern "C" int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, 
     DVCP_CHECK_LAUNCH();
     if (logits) DVCP_CUDA(cudaMemcpyAsync(logits, v3, M * (int64_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+extern "C" int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
+                        int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
+                        int64_t workspace_bytes, dvcp_stream_t stream) {
+    return dvcp_cpg_path(src_dfe, tgt_dfe, layout, cand, M, G, p, vcp, logits, workspace, workspace_bytes,
+                         DVCP_CPG_AUTO, stream);
 }

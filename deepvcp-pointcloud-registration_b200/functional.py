@@ -400,8 +400,12 @@ def dfe_dense(X, dfe):
     return out
 
 
-def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False):
-    """src_dfe [M,32]; tgt_dfe [M,32*C] flat (layout 0: logical [32,C]; 1: [C,32]); cand [M,C,3]."""
+CPG_AUTO, CPG_FUSED, CPG_LAYERED = 0, 1, 2
+
+
+def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False, path=CPG_AUTO):
+    """src_dfe [M,32]; tgt_dfe [M,32*C] flat (layout 0: logical [32,C]; 1: [C,32]); cand [M,C,3].
+    path: kernel family (CPG_AUTO = the library's choice; tests force the others)."""
     require_cuda(src_dfe, tgt_dfe, cand)
     M = src_dfe.shape[0]
     C = G * G * G
@@ -410,9 +414,9 @@ def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     vcp = torch.empty(M, 3, dtype=torch.float32, device=dev)
     logits = torch.empty(M, C, dtype=torch.float32, device=dev) if want_logits else None
-    check(lib().dvcp_cpg(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params, ptr(vcp),
-                         ptr(logits), ptr(ws), nbytes, stream_ptr(dev)), "dvcp_cpg")
-    _count(1 if G <= 11 else 5)   # fused kernel up to 11^3, else cost + 3 convs + softmax
+    check(lib().dvcp_cpg_path(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params,
+                              ptr(vcp), ptr(logits), ptr(ws), nbytes, path, stream_ptr(dev)), "dvcp_cpg")
+    _count(1 if G <= 11 and path != CPG_LAYERED else 5)   # fused kernel up to 11^3, else cost + 3 convs + softmax
     return vcp, logits
 
 

@@ -267,6 +267,15 @@ DVCP_API int64_t dvcp_cpg_workspace_bytes(int64_t M, int G);
 DVCP_API int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
              int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
              int64_t workspace_bytes, dvcp_stream_t stream);
+/* Same, with the kernel family chosen by the caller (parity tests compare the families with each other
+ * and with the oracle at every grid size): AUTO = what dvcp_cpg picks; FUSED = whole chain in one kernel
+ * with the volume in shared memory (G <= 11); LAYERED = one kernel per layer through the workspace. */
+#define DVCP_CPG_AUTO    0
+#define DVCP_CPG_FUSED   1
+#define DVCP_CPG_LAYERED 2
+DVCP_API int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
+             int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
+             int64_t workspace_bytes, int path, dvcp_stream_t stream);
 
 /* ---- a17 get_rigid_transform(x, y)                   deepVCP_loss.py:13-44
  * x, y [B,3,n] (dtype 0 float32 / 1 float64); R [B,3,3], t [B,3] float64.
