@@ -47,6 +47,10 @@ class DeepVCP(nn.Module):
         self.quirks = quirks
         self.last = None   # stage tensors of the most recent forward (for tests / inspection)
         self.dfe_tensor_cores = True    # tcgen05 embedding (collapsed affine map, 3xTF32); False = FP32 CUDA-core kernel
+        # KNN through per-key-point shared-memory pools (knn_pool.cu, dvcp_knn_groups): exact, but measured SLOWER
+        # than the index walk per query on B200 (K8: 3.8 ms against 1.65 ms) -- kept as an option
+        self.knn_pools_min_n = 0
+        self.knn_pools = False
         self.profile = False   # record a CUDA event after every stage (bench.py reads them)
         self._events = None
 
@@ -190,7 +194,11 @@ class DeepVCP(nn.Module):
             cand = F_.candidates(centres, self.r, self.s, G)                 # [B,K,C,3]
             mark("keypoint_candidates")
             C = G * G * G
-            if index is not None:   # target clouds are batch items B..2B-1 of the index
+            if index is not None and self.knn_pools and N >= self.knn_pools_min_n:
+                # one CTA per key-point: the target points around its candidate lattice are pooled in shared memory
+                kd, ki64, ki32 = F_.knn_groups(index, B, dev, B, N, cand.view(B, K * C, 3), ns, group=C, zline=G,
+                                               cell=self.s, want64=keep_stages, want32=True)
+            elif index is not None:   # target clouds are batch items B..2B-1 of the index
                 kd, ki64, ki32 = F_.knn_indexed(index, B, dev, B, N, cand.view(B, K * C, 3), ns, chain=G,
                                                 want64=keep_stages, want32=True)
             elif F_.SpatialIndex.knn_indexable(N):

@@ -333,6 +333,24 @@ def knn_indexed(index, lo, device, B, N, query, K, chain=1, zline=0, want64=True
     return dist, i64, i32
 
 
+def knn_groups(index, lo, device, B, N, query, K, group, zline, cell, pool_cap=0, want64=True, want32=False,
+               stats=None):
+    """KNN of query groups (one candidate lattice per key-point) through per-group shared-memory pools;
+    index: SpatialIndex whose batch items lo..lo+B-1 are the reference clouds. Exact for any queries."""
+    require_cuda(query)
+    query = _f32c(query)
+    Q = query.shape[1]
+    dist = torch.empty(B, Q, K, dtype=torch.float32, device=device)
+    i64 = torch.empty(B, Q, K, dtype=torch.int64, device=device) if want64 else None
+    i32 = torch.empty(B, Q, K, dtype=torch.int32, device=device) if want32 else None
+    nbytes = lib().dvcp_knn_groups_workspace_bytes(B, Q)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    check(lib().dvcp_knn_groups(index.c(lo), ptr(query), B, N, Q, K, group, zline, float(cell), pool_cap, ptr(dist),
+                                ptr(i64), ptr(i32), ptr(stats), ptr(ws), nbytes, stream_ptr(device)), "dvcp_knn_groups")
+    _count(2)   # pool kernel + the deferred index searches
+    return dist, i64, i32
+
+
 def dfe_tgt_fused(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, dfe, quirks):
     require_cuda(cand, tgt_feat, knn_dist, knn_idx32)
     Q = knn_dist.shape[1]

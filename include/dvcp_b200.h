@@ -225,6 +225,22 @@ DVCP_API int dvcp_knn_indexed(dvcp_cloud_index_t ref_index, const float *query, 
                      int chain, int zline, float *dist, int64_t *idx64, int32_t *idx32,
                      dvcp_stream_t stream);
 
+/* Same contract for GROUPS of nearby queries: queries [g * group, (g + 1) * group) of every batch item form
+ * one group (the G^3 candidate lattice of one key-point: group = G^3, zline = G, cell = the lattice step s
+ * of voxelize.py). One CTA per group copies the target points around the group's bounding box from the
+ * index into shared memory, answers the queries there, and certifies every answer (an uncertified query
+ * goes through the index search of dvcp_knn_indexed). Exact for ANY queries; results are bit-identical to
+ * dvcp_knn. pool_cap: shared-memory pool capacity in points (0 = default; 64..8192). Clouds of up to
+ * 65536 points. stats (nullable): 8 device counters ADDED to, for profiling -- queries certified by the pool,
+ * uncertified, list overflows, cold starts, queries of groups without a pool, pool points, points admitted
+ * by the bound, points scanned. workspace: dvcp_knn_groups_workspace_bytes(B, Q) bytes (the list of queries
+ * the pools could not certify; a second kernel answers them through the index, one warp per query). */
+DVCP_API int64_t dvcp_knn_groups_workspace_bytes(int B, int64_t Q);
+DVCP_API int dvcp_knn_groups(dvcp_cloud_index_t index, const float *query, int B, int N, int64_t Q, int K,
+                    int group, int zline, float cell, int pool_cap, float *dist, int64_t *idx64,
+                    int32_t *idx32, uint64_t *stats, void *workspace, int64_t workspace_bytes,
+                    dvcp_stream_t stream);
+
 /* ---- a14+a15 Get_Cat_Feat_Tgt + feat_embedding_layer(src=False), fused
  *          get_cat_feat_tgt.py:53-96, deep_feat_embedding.py:46-60
  * cand [B,Q,3]; tgt_xyz cloud [B,N,3]; tgt_feat [B,N,32]; knn_dist [B,Q,32];

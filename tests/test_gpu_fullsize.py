@@ -220,3 +220,74 @@ def test_cpg_module_at_benchmark_grid_vs_oracle(dv):
     out = net(src.to(DEV), tgt_cf.to(DEV).permute(0, 1, 3, 2), cand.to(DEV), 2.0, 0.4)
     ref, _ = stages.cpg(sd, src.view(B, N, 32), tgt_cf, cand, G)
     assert (out.cpu() - ref).abs().max() < 5e-5
+
+
+# ------------------------------------------------------------------ pooled KNN (knn_pool.cu) ------
+def _knn_groups_case(F, lib, cloud_pm, cand, group, zline, cell, pool_caps, K=32):
+    """dvcp_knn_groups against the brute-force kernel on every query, for several pool capacities (a tiny
+    pool leaves most queries uncertified: the index-search fallback and the list-overflow path run)."""
+    B, N, _ = cloud_pm.shape
+    d0, i0, _ = F.knn(lib.cloud_pm(cloud_pm), cloud_pm.device, B, N, cand, K)
+    index = F.build_index(lib.cloud_pm(cloud_pm), cloud_pm.device, B, N, big=N > 16384)
+    out = {}
+    for cap in pool_caps:
+        stats = torch.zeros(8, dtype=torch.int64, device=cloud_pm.device)
+        d, i, _ = F.knn_groups(index, 0, cloud_pm.device, B, N, cand, K, group, zline, cell, pool_cap=cap, stats=stats)
+        assert torch.equal(i, i0), "pool capacity %d: indices differ from the brute-force kernel" % cap
+        assert torch.equal(d, d0), "pool capacity %d: distances differ" % cap
+        st = stats.cpu().tolist()
+        assert st[0] + st[1] + st[4] == B * cand.shape[1]
+        out[cap] = st
+    return d0, i0, out
+
+
+def test_knn_groups_k8_all_queries_equal_brute_force_and_oracle(dv, F):
+    """K8 shape: 64 key-points x 11^3 candidates against 16384 target points, B = 2; every one of the
+    170 368 queries equals the brute-force kernel, a sample equals the oracle; pool capacities from tiny
+    (fallback for almost everything) to the maximum."""
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    lib = importlib.import_module(PKG + "._lib")
+    src, tgt, R, _ = synthetic.make_batch("kitti", [3, 4], 16384)
+    g = torch.Generator().manual_seed(9)
+    pick = torch.stack([torch.randperm(16384, generator=g)[:64] for _ in range(2)])
+    kp = torch.stack([src[b, :, pick[b]].t() for b in range(2)]).double()            # [2,64,3] points of the source
+    centres = (R @ kp.transpose(1, 2)).transpose(1, 2).contiguous()
+    cand = F.candidates(centres.to(DEV), 2.0, 0.4).view(2, -1, 3)
+    tpm = tgt.permute(0, 2, 1).contiguous().to(DEV)
+    d0, i0, st = _knn_groups_case(F, lib, tpm, cand, 1331, 11, 0.4, [0, 64, 512, 8192])
+    assert st[8192][0] > 0.9 * 2 * 85184, "large pool: most queries should be certified by the pool: %s" % st[8192]
+    assert st[64][1] + st[64][4] > 0, "a 64-point pool must leave queries to the index search"
+    sel = torch.randperm(cand.shape[1], generator=g)[:1000]
+    d_ref, i_ref = stages.knn(tpm.cpu(), cand[:, sel].cpu(), 32)
+    assert torch.equal(i0[:, sel].cpu(), i_ref) and torch.equal(d0[:, sel].cpu(), d_ref)
+
+
+@pytest.mark.parametrize("n,G,cell,K", [(1024, 5, 0.4, 32), (2048, 7, 0.4, 32), (5000, 6, 0.4, 5), (300, 3, 0.4, 1),
+                                        (40000, 11, 0.4, 32), (65536, 5, 0.4, 32)])
+def test_knn_groups_shapes_vs_brute_force(F, n, G, cell, K):
+    """ModelNet-shaped unit-ball clouds (pool = whole cloud), odd sizes, small K, clouds above the
+    single-CTA index (multi-CTA index build) -- all queries against the brute-force kernel."""
+    lib = importlib.import_module(PKG + "._lib")
+    g = torch.Generator().manual_seed(n + G)
+    if n <= 5000:
+        d = torch.randn(2, n, 3, generator=g)
+        cloud = d / d.norm(dim=-1, keepdim=True) * torch.rand(2, n, 1, generator=g) ** (1 / 3)
+    else:
+        cloud = (torch.rand(2, n, 3, generator=g) * 2 - 1) * torch.tensor([40.0, 40.0, 3.0])
+        cloud = torch.round(cloud * 10) / 10          # 0.1 m lattice: exact distance ties
+    centres = cloud[:, torch.randperm(n, generator=g)[:16]].double() + 0.05
+    r = (G - 1) * cell / 2
+    cand = F.candidates(centres.to(DEV), r, cell, G).view(2, -1, 3)
+    _knn_groups_case(F, lib, cloud.to(DEV), cand, G ** 3, G, cell, [0, 256], K=K)
+
+
+def test_knn_groups_arbitrary_queries_and_ragged_last_group(F):
+    """Queries that are NOT a lattice (random, far outside the cloud, duplicated), a group size that does
+    not divide Q, lattice-snapped target with heavy ties: exactness does not depend on the query layout."""
+    lib = importlib.import_module(PKG + "._lib")
+    g = torch.Generator().manual_seed(77)
+    cloud = torch.round((torch.rand(1, 9000, 3, generator=g) * 2 - 1) * 6 / 0.25) * 0.25
+    q = torch.cat([(torch.rand(1, 700, 3, generator=g) * 2 - 1) * 7,
+                   torch.round((torch.rand(1, 300, 3, generator=g) * 2 - 1) * 6 / 0.25) * 0.25,     # on the lattice: ties
+                   torch.full((1, 13, 3), 50.0), torch.zeros(1, 10, 3)], dim=1)
+    _knn_groups_case(F, lib, cloud.to(DEV), q.to(DEV), 100, 7, 0.3, [0, 64, 2048])
