@@ -76,7 +76,8 @@ SIGNATURES = {
                                    c_vp]),
     "dvcp_dfe_tc_b_floats": (c_i32, []),
     "dvcp_dfe_tc_b_offset": (c_i32, [c_i32, c_i32]),
-    "dvcp_dfe_tgt_tc": (c_i32, [c_vp, Cloud, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "dvcp_dfe_tgt_tc": (c_i32, [c_vp, Cloud, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dvcp_cpg_tc_image_bytes": (c_i64, []),
     "dvcp_dfe_dense": (c_i32, [c_vp, c_i32, c_i64, c_i32, DfeParams, c_vp, c_vp]),
     "dvcp_cpg_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "dvcp_cpg": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_i32, CpgParams, c_vp, c_vp, c_vp, c_i64, c_vp]),

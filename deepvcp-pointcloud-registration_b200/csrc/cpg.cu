@@ -410,11 +410,19 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
 
 }  // namespace dvcp
 
+namespace dvcp {
+int cpg_tc_launch(const float *src_dfe, const float *tgt_dfe, const float *cand, int64_t M, int G, dvcp_cpg_params_t p,
+                  float *vcp, float *logits, float *image, cudaStream_t st);   // cpg_tc.cu
+}
+extern "C" int64_t dvcp_cpg_tc_image_bytes(void);
+
 using namespace dvcp;
 
 extern "C" int64_t dvcp_cpg_workspace_bytes(int64_t M, int G) {
     if (M <= 0 || G <= 0) return 0;
-    return M * (int64_t)G * G * G * (32 + 16 + 4 + 1) * (int64_t)sizeof(float);
+    const int64_t layered = M * (int64_t)G * G * G * (32 + 16 + 4 + 1) * (int64_t)sizeof(float);
+    const int64_t tc = dvcp_cpg_tc_image_bytes();   // the tensor-core kernel's split weight image
+    return layered > tc ? layered : tc;
 }
 
 extern "C" int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
@@ -426,8 +434,11 @@ extern "C" int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int lay
     if (workspace_bytes < dvcp_cpg_workspace_bytes(M, G)) return DVCP_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int C = G * G * G;
-    if (path < DVCP_CPG_AUTO || path > DVCP_CPG_LAYERED) return DVCP_E_ARG;
+    if (path < DVCP_CPG_AUTO || path > DVCP_CPG_TC) return DVCP_E_ARG;
     if (path == DVCP_CPG_FUSED && G > CF_MAXG) return DVCP_E_UNSUPPORTED;
+    if (path == DVCP_CPG_TC && (G > CF_MAXG || G < 2 || layout != 0)) return DVCP_E_UNSUPPORTED;
+    if (path == DVCP_CPG_TC || (path == DVCP_CPG_AUTO && layout == 0 && G >= 2 && G <= CF_MAXG))
+        return cpg_tc_launch(src_dfe, tgt_dfe, cand, M, G, p, vcp, logits, (float *)workspace, st);
     if (G <= CF_MAXG && path != DVCP_CPG_LAYERED) {
         const int Cp = (C + 3) & ~3;
         const int items = G * G * ((G + 3) / 4);

@@ -1,0 +1,384 @@
+// Corresponding-point generation with conv1 on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Reference: cpg.py:27-60. conv1 (Conv3d 32 -> 16, 3x3x3, zero padding) is 88 % of the
+// layer's arithmetic; here it is an IMPLICIT GEMM
+//     D[voxel, cout] = sum over (tap, cin) of  V[voxel + shift(tap), cin] * W1[cout, cin, tap]
+// with M = voxels, N = 16, K = 27 taps x 32 channels, evaluated as tcgen05.mma kind::tf32 with the 3xTF32
+// split (V = Vh + Vl, W = Wh + Wl; Vh*Wh + Vl*Wh + Vh*Wl, FP32 accumulate in TMEM: FP32-level accuracy).
+//
+// The cost volume V of one key-point lives in shared memory as a ZERO-PADDED volume (G+2)^3 in the
+// K-major no-swizzle operand layout with the rows laid out contiguously:
+//     element (row r, channel k) of a channel octet at  plane(k / 4) + r * 16 B + (k % 4) * 4 B
+// (core matrices of 8 rows x 16 B follow each other every 128 B = SBO, the two K halves of an MMA are one
+// plane = LBO apart). A row is a voxel of the padded volume in linear order, so the rows a tap needs are
+// the SAME rows shifted by a constant: the A descriptor of tap (dx, dy, dz) is the base descriptor plus
+// ((dx * Gp + dy) * Gp + dz) rows, zero padding comes from the halo rows, and no im2col copy exists.
+// M tiles of 128 consecutive padded rows cover the interior (15 tiles for G = 11; the results of halo
+// rows are ignored). Eight input channels (one MMA K step) are resident at a time: 4 passes per volume,
+// 27 taps x 15 tiles x 3 MMAs each, all accumulating into the same 15 x 16 TMEM columns.
+//
+// conv2 / conv3 / softmax / weighted sum follow in the same CTA on the CUDA cores (they are 12 % of the
+// arithmetic) with the volume in shared memory, as in cpg_fused_kernel (cpg.cu).
+//
+// The target embedding is read as flat[c' * 32 + f'] (the LOGICAL [32, C] order, `layout` 0 of dvcp_cpg):
+// 32 contiguous floats per voxel. DeepVCP.match has the embedding kernel write that order directly.
+#include "common.cuh"
+
+namespace dvcp {
+
+constexpr int CT_THREADS = 512;
+constexpr int CT_MAXG = 11;
+constexpr int CT_TMEM_COLS = 256;
+constexpr int CT_B_FLOATS_Q = 27 * 2 * 2 * 16 * 4;   // per channel octet: [tap][hi|lo][k half][cout][4]
+constexpr int CT_B_FLOATS = 4 * CT_B_FLOATS_Q;
+
+__device__ __forceinline__ uint32_t ct_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: LBO = distance of the two 16-byte K halves, SBO = distance of 8-row groups
+__device__ __forceinline__ uint64_t ct_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 16
+constexpr uint32_t CT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void ct_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(CT_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void ct_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "CT_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CT_WAIT_DONE;\n\t"
+        "bra CT_WAIT_LOOP;\n\t"
+        "CT_WAIT_DONE:\n\t}" ::"r"(ct_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ bool ct_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// conv1 weights [16][32][27] -> the N-side operand image, split hi / lo:
+//   image[q][tap][h][kh][n][e] = part_h( w1[n][8 q + 4 kh + e][tap] )
+__global__ void cpg_tc_prepare_kernel(const float *__restrict__ w1, float *__restrict__ image) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= CT_B_FLOATS) return;
+    const int e = i & 3, n = (i >> 2) & 15, kh = (i >> 6) & 1, h = (i >> 7) & 1, tap = (i >> 8) % 27, q = (i >> 8) / 27;
+    const float w = __ldg(w1 + (n * 32 + 8 * q + 4 * kh + e) * 27 + tap);
+    const float hi = ct_hi(w);
+    image[i] = h == 0 ? hi : w - hi;
+}
+
+__device__ __forceinline__ float ct_block_sum(float v, float *red, int tid) {
+#pragma unroll
+    for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < CT_THREADS / 32; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, const float *__restrict__ cand, int64_t M,
+              int G, int R, const float *__restrict__ bimage, dvcp_cpg_params_t p, float *__restrict__ vcp,
+              float *__restrict__ logits_out) {
+    extern __shared__ __align__(128) unsigned char ct_smem[];
+    __shared__ float red[CT_THREADS / 32];
+    __shared__ __align__(16) float s_src[32];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Gp = G + 2, Gp2 = Gp * Gp, C = G * G * G, Cp = (C + 3) & ~3;
+    const int m_lo = Gp2 + Gp + 1;                             // first interior row of the padded volume
+    const int ntiles = ((G - 1) * m_lo + 1 + 127) >> 7;        // M tiles of 128 padded rows over the interior span
+    const int nissue = ntiles < CT_THREADS / 32 ? ntiles : CT_THREADS / 32;   // warps that issue MMAs (one commit each)
+    // shared memory: A planes [hi k0 | hi k1 | lo k0 | lo k1][R rows][16 B]; B image of the current octet; W2; W3
+    float4 *sA = reinterpret_cast<float4 *>(ct_smem);
+    float *sB = reinterpret_cast<float *>(ct_smem + (size_t)4 * R * 16);
+    float *W2 = sB + CT_B_FLOATS_Q;    // [27][16][4]
+    float *W3 = W2 + 27 * 16 * 4;      // [27][4] (padded to 112)
+    // after conv1 the A region is dead and holds conv1 out [16][Cp], conv2 out [4][Cp], logits [Cp]
+    float *A1 = reinterpret_cast<float *>(ct_smem), *O2 = A1 + 16 * Cp, *LG = O2 + 4 * Cp;
+
+    for (int i = tid; i < 27 * 16 * 4; i += CT_THREADS) {
+        const int co = i & 3, ci = (i >> 2) & 15, tap = i >> 6;
+        W2[i] = __ldg(p.w2 + (co * 16 + ci) * 27 + tap);
+    }
+    for (int i = tid; i < 27 * 4; i += CT_THREADS) W3[i] = __ldg(p.w3 + (i & 3) * 27 + (i >> 2));
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ct_smem_u32(&s_bar)), "r"((unsigned)nissue));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ct_smem_u32(&s_tmem)),
+                     "r"((unsigned)CT_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+    const uint32_t a_base = ct_smem_u32(sA), b_base = ct_smem_u32(sB);
+    const uint32_t plane = (uint32_t)R * 16u;   // bytes of one A plane = LBO of the A operand
+    const float b3 = __ldg(p.b3);
+    unsigned phase = 0;
+
+    for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
+        const float *t = tgt + m * 32 * (int64_t)C;
+        __syncthreads();   // the previous volume is finished with the shared volumes
+        // zero the A planes (halo rows must read as zero; the conv stages of the previous volume overwrote them)
+        for (int i = tid; i < 4 * R; i += CT_THREADS) sA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 32) s_src[tid] = __ldg(src + m * 32 + tid);
+        __syncthreads();
+        for (int q = 0; q < 4; ++q) {
+            // ---- weights of this channel octet (pre-split image, 27 KB) ----
+            const float4 *bi = reinterpret_cast<const float4 *>(bimage + (size_t)q * CT_B_FLOATS_Q);
+            for (int i = tid; i < CT_B_FLOATS_Q / 4; i += CT_THREADS) reinterpret_cast<float4 *>(sB)[i] = __ldg(bi + i);
+            // ---- cost volume of channels 8q .. 8q+7: cost[c', f'] = (src[f'] - flat[c' * 32 + f'])^2 ----
+            const float4 s0 = *reinterpret_cast<const float4 *>(s_src + 8 * q), s1 = *reinterpret_cast<const float4 *>(s_src + 8 * q + 4);
+            for (int c = tid; c < C; c += CT_THREADS) {
+                const float4 t0 = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q));
+                const float4 t1 = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q + 4));
+                const int z = c % G, y = (c / G) % G, x = c / (G * G);
+                const int r = ((x + 1) * Gp + (y + 1)) * Gp + (z + 1);
+                float4 v0, v1, h0, h1;
+                v0.x = (s0.x - t0.x) * (s0.x - t0.x); v0.y = (s0.y - t0.y) * (s0.y - t0.y);
+                v0.z = (s0.z - t0.z) * (s0.z - t0.z); v0.w = (s0.w - t0.w) * (s0.w - t0.w);
+                v1.x = (s1.x - t1.x) * (s1.x - t1.x); v1.y = (s1.y - t1.y) * (s1.y - t1.y);
+                v1.z = (s1.z - t1.z) * (s1.z - t1.z); v1.w = (s1.w - t1.w) * (s1.w - t1.w);
+                h0 = make_float4(ct_hi(v0.x), ct_hi(v0.y), ct_hi(v0.z), ct_hi(v0.w));
+                h1 = make_float4(ct_hi(v1.x), ct_hi(v1.y), ct_hi(v1.z), ct_hi(v1.w));
+                sA[r] = h0;
+                sA[R + r] = h1;
+                sA[2 * R + r] = make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w);
+                sA[3 * R + r] = make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w);
+            }
+            // operands were written with ordinary stores: make them visible to the tensor core's (async) proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            // ---- MMA issue: warp w owns the accumulator tiles w, w + 16, ... (independent accumulators, so the
+            //      issue work -- one thread can only feed the tensor core every few cycles -- is spread over the
+            //      warps); the loop is warp-uniform so the descriptors live in uniform registers, one elected
+            //      lane issues ----
+            if (warp < nissue) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool leader = ct_elect_one();
+                for (int tile = warp; tile < ntiles; tile += CT_THREADS / 32) {
+                    const uint32_t d = tmem_base + (uint32_t)tile * 16u;
+                    const uint32_t row0 = (uint32_t)(m_lo + tile * 128);
+                    const uint64_t a0 = ct_desc(a_base + row0 * 16u, plane, 128u);
+                    const uint64_t w0 = ct_desc(b_base, 256u, 128u);
+#pragma unroll
+                    for (int tap = 0; tap < 27; ++tap) {
+                        const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
+                        // the address field counts 16-byte units = rows: a tap shifts the descriptor by a constant
+                        const uint64_t a_hi = a0 + (uint64_t)(int64_t)(dx * Gp2 + dy * Gp + dz);
+                        const uint64_t a_lo = a_hi + (uint64_t)(2u * (plane >> 4));
+                        const uint64_t w_hi = w0 + (uint64_t)(tap * 64), w_lo = w_hi + 32u;   // 1024 B per tap, lo at + 512 B
+                        if (leader) {
+                            ct_mma(d, a_hi, w_hi, (q | tap) != 0);
+                            ct_mma(d, a_lo, w_hi, 1u);
+                            ct_mma(d, a_hi, w_lo, 1u);
+                        }
+                    }
+                }
+                if (leader)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ct_smem_u32(&s_bar))
+                                 : "memory");
+                __syncwarp();
+            }
+            // everybody waits for the MMAs of this octet: the operands are rewritten next
+            ct_mbar_wait(&s_bar, phase);
+            phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        __syncthreads();   // every thread has passed the wait: the A region may be reused
+        // ---- conv1 accumulators: TMEM -> + bias -> shared [16][Cp] ----
+        {
+            const int lq = warp & 3;   // a warp reads the TMEM lanes 32 (warp % 4) .. + 31
+            for (int tile = warp >> 2; tile < ntiles; tile += CT_THREADS / 128) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)tile * 16u;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int r = m_lo + tile * 128 + lq * 32 + lane;
+                const int zp = r % Gp, yp = (r / Gp) % Gp, xp = r / Gp2;
+                if (xp >= 1 && xp <= G && yp >= 1 && yp <= G && zp >= 1 && zp <= G) {
+                    const int c = ((xp - 1) * G + (yp - 1)) * G + (zp - 1);
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) A1[o * Cp + c] = __uint_as_float(v[o]) + __ldg(p.b1 + o);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        __syncthreads();
+        // ---- conv2 16 -> 4: thread = (line (x, y), group of 4 z), packed FFMA2 ----
+        {
+            const int NG = (G + 3) >> 2, items = G * G * NG;
+            if (tid < items) {
+                const int line = tid / NG, zg = tid - line * NG;
+                const int x = line / G, y = line - x * G, z0 = zg * 4;
+                float2 a2[4][2];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    a2[v][0] = make_float2(__ldg(p.b2), __ldg(p.b2 + 1));
+                    a2[v][1] = make_float2(__ldg(p.b2 + 2), __ldg(p.b2 + 3));
+                }
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = x + dx;
+                    if (xx < 0 || xx >= G) continue;
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int yy = y + dy;
+                        if (yy < 0 || yy >= G) continue;
+                        const int tap0 = ((dx + 1) * 3 + (dy + 1)) * 3;
+                        const float *col = A1 + (xx * G + yy) * G + z0 - 1;
+#pragma unroll 4
+                        for (int ci = 0; ci < 16; ++ci) {
+                            float in[6];
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) {
+                                const int z = z0 - 1 + k;
+                                in[k] = (z >= 0 && z < G) ? col[ci * Cp + k] : 0.f;
+                            }
+#pragma unroll
+                            for (int dz = 0; dz < 3; ++dz) {
+                                const float4 w = *reinterpret_cast<const float4 *>(W2 + ((tap0 + dz) * 16 + ci) * 4);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) {
+                                    const float2 x2 = make_float2(in[v + dz], in[v + dz]);
+                                    a2[v][0] = __ffma2_rn(make_float2(w.x, w.y), x2, a2[v][0]);
+                                    a2[v][1] = __ffma2_rn(make_float2(w.z, w.w), x2, a2[v][1]);
+                                }
+                            }
+                        }
+                    }
+                }
+                const int c0 = (x * G + y) * G + z0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (z0 + v < G) {
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) {
+                            O2[(2 * o) * Cp + c0 + v] = a2[v][o].x;
+                            O2[(2 * o + 1) * Cp + c0 + v] = a2[v][o].y;
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+        // ---- conv3 4 -> 1: thread per voxel ----
+        for (int c = tid; c < C; c += CT_THREADS) {
+            const int iz = c % G, iy = (c / G) % G, ix = c / (G * G);
+            float a3 = b3;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = ix + dx;
+                if (xx < 0 || xx >= G) continue;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = iy + dy;
+                    if (yy < 0 || yy >= G) continue;
+#pragma unroll
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        const int zz = iz + dz;
+                        if (zz < 0 || zz >= G) continue;
+                        const int tap = ((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1);
+                        const float4 w = *reinterpret_cast<const float4 *>(W3 + tap * 4);
+                        const int cc = (xx * G + yy) * G + zz;
+                        a3 = fmaf(w.x, O2[cc], a3);
+                        a3 = fmaf(w.y, O2[Cp + cc], a3);
+                        a3 = fmaf(w.z, O2[2 * Cp + cc], a3);
+                        a3 = fmaf(w.w, O2[3 * Cp + cc], a3);
+                    }
+                }
+            }
+            LG[c] = a3;
+            if (logits_out) logits_out[m * C + c] = a3;
+        }
+        __syncthreads();
+        // ---- softmax over the C voxels + weighted candidate sum ----
+        {
+            float mx = -INFINITY;
+            for (int c = tid; c < C; c += CT_THREADS) mx = fmaxf(mx, LG[c]);
+#pragma unroll
+            for (int s = 16; s; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+            __syncthreads();
+            if (lane == 0) red[warp] = mx;
+            __syncthreads();
+            mx = red[0];
+#pragma unroll
+            for (int w = 1; w < CT_THREADS / 32; ++w) mx = fmaxf(mx, red[w]);
+            float zp = 0.f;
+            for (int c = tid; c < C; c += CT_THREADS) zp += expf(LG[c] - mx);
+            const float Z = ct_block_sum(zp, red, tid);
+            const float *cp = cand + m * C * 3;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = tid; c < C; c += CT_THREADS) {
+                const float w = expf(LG[c] - mx) / Z;
+                a[0] = fmaf(w, __ldg(cp + 3 * c), a[0]);
+                a[1] = fmaf(w, __ldg(cp + 3 * c + 1), a[1]);
+                a[2] = fmaf(w, __ldg(cp + 3 * c + 2), a[2]);
+                a[3] += w;
+            }
+            const float sx = ct_block_sum(a[0], red, tid), sy = ct_block_sum(a[1], red, tid),
+                        sz = ct_block_sum(a[2], red, tid), sw = ct_block_sum(a[3], red, tid);
+            if (tid == 0) {
+                vcp[m * 3] = sx / sw;
+                vcp[m * 3 + 1] = sy / sw;
+                vcp[m * 3 + 2] = sz / sw;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)CT_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// rows of one A plane: the last tile's last row plus the largest tap shift, rounded up to 8
+static inline int ct_rows(int G) {
+    const int Gp = G + 2, m_lo = Gp * Gp + Gp + 1;
+    const int ntiles = ((G - 1) * m_lo + 1 + 127) / 128;
+    return ((m_lo + ntiles * 128 + m_lo) + 7) & ~7;
+}
+
+int cpg_tc_launch(const float *src_dfe, const float *tgt_dfe, const float *cand, int64_t M, int G, dvcp_cpg_params_t p,
+                  float *vcp, float *logits, float *image, cudaStream_t st) {
+    if (G < 2 || G > CT_MAXG) return DVCP_E_UNSUPPORTED;
+    cpg_tc_prepare_kernel<<<(CT_B_FLOATS + 255) / 256, 256, 0, st>>>(p.w1, image);
+    DVCP_CHECK_LAUNCH();
+    const int R = ct_rows(G);
+    const int smem = 4 * R * 16 + (CT_B_FLOATS_Q + 27 * 16 * 4 + 112) * (int)sizeof(float);
+    DVCP_CUDA(cudaFuncSetAttribute(cpg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int64_t grid = M < DVCP_NUM_SMS ? M : DVCP_NUM_SMS;
+    cpg_tc_kernel<<<(unsigned)grid, CT_THREADS, smem, st>>>(src_dfe, tgt_dfe, cand, M, G, R, image, p, vcp, logits);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace dvcp
+
+extern "C" int64_t dvcp_cpg_tc_image_bytes(void) { return (int64_t)dvcp::CT_B_FLOATS * (int64_t)sizeof(float); }

@@ -48,7 +48,14 @@ constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS -
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
 constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
 constexpr int TC_W_BYTES = TC_PROD_WARPS * 32 * 8;   // per producer warp: (hi, lo) distance weight of each feature
-constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + 1024;   // + alignment slack
+constexpr int TC_RUN = 8;                      // a CTA takes its tiles in runs of 8 consecutive tiles = 32 consecutive candidates
+constexpr int TC_T_BYTES = 32 * 33 * 4;        // epilogue transposition tile (feature-major output)
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + TC_T_BYTES + 1024;   // + alignment slack
+
+// first candidate of this CTA's i-th tile: runs of TC_RUN consecutive tiles, the runs dealt round-robin to the CTAs
+__device__ __forceinline__ int64_t tc_tile_cand(int64_t i) {
+    return (((i / TC_RUN) * gridDim.x + blockIdx.x) * TC_RUN + (i % TC_RUN)) * 4;
+}
 
 // byte offset of element (row r, column k) in the K-major, no-swizzle canonical layout:
 // 8x(16 B) core matrices; core (r/8, k/4) at ((r/8) * (K/4) + k/4) * 128 B.
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__restrict__ tfeat,
                   const float *__restrict__ kdist, const int32_t *__restrict__ kidx, int N, int64_t total_cand,
                   int64_t Q, const float *__restrict__ Bhi, const float *__restrict__ Blo, int per_feature_weight,
-                  float *__restrict__ out) {
+                  int fm_C, float *__restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
     unsigned char *sA = smem;                                      // [stage][hi sw | lo sw | hi tail | lo tail]
@@ -124,6 +131,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + 2 * TC_BW_BYTES + TC_W_BYTES);
     uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 3 * TC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * TC_STAGES);
+    float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [32][33]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // rows 0..31 of the 128-row operand are the host's 32-row image (the layout is row-block major), the rest zero
@@ -154,7 +162,9 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     const uint32_t tmem_base = *tmem_slot;
 
     const int64_t ntiles = (total_cand + 3) / 4;
-    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t nruns = (ntiles + TC_RUN - 1) / TC_RUN;
+    // (the tiles of a last, partial run beyond ntiles are dead: every role skips candidates >= total_cand)
+    const int64_t my_tiles = blockIdx.x < nruns ? (nruns - blockIdx.x + gridDim.x - 1) / gridDim.x * TC_RUN : 0;
 
     if (warp == TC_MMA_WARP) {
         // ------------------------------ MMA issuer ------------------------------
@@ -192,7 +202,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
-            const int64_t gq0 = (blockIdx.x + i * gridDim.x) * 4;
+            const int64_t gq0 = tc_tile_cand(i);
             mbar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float best[4];
@@ -219,9 +229,30 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[s]);
+            if (fm_C == 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (gq0 + c < total_cand) out[(gq0 + c) * 32 + lane] = best[c];
+                for (int c = 0; c < 4; ++c)
+                    if (gq0 + c < total_cand) out[(gq0 + c) * 32 + lane] = best[c];
+            } else {
+                // feature-major inside every block of fm_C candidates (one key-point): the logical [32, C] order
+                // cpg.py:34 re-reads (quirk Q4), so that the CPG kernel finds a voxel's 32 values contiguous.
+                // The 8 tiles of a run are 32 consecutive candidates: transposed through shared memory, every
+                // store instruction then writes one feature of 32 consecutive candidates (coalesced).
+                const int col = (int)(i % TC_RUN) * 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sT[lane * 33 + col + c] = best[c];
+                if (i % TC_RUN == TC_RUN - 1) {
+                    __syncwarp();
+                    const int64_t gq = gq0 - (TC_RUN - 1) * 4 + lane;   // lane = candidate of the run
+                    if (gq < total_cand) {
+                        const int64_t kp = gq / fm_C;
+                        float *o = out + kp * 32 * fm_C + (gq - kp * fm_C);
+#pragma unroll 8
+                        for (int f = 0; f < 32; ++f) o[(int64_t)f * fm_C] = sT[f * 33 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
         }
     } else {
         // ---------------------- A producers: group g builds tiles g, g + TC_GROUPS, ... ----------------------
@@ -249,7 +280,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         int id_n = 0;
         float dj_n = 0.f;
         if (i < my_tiles) {
-            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + cw;
+            const int64_t gq = tc_tile_cand(i) + cw;
             if (gq < total_cand) {
                 id_n = __ldg(kidx + gq * 32 + lane);
                 dj_n = __ldg(kdist + gq * 32 + lane);
@@ -258,13 +289,13 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         for (; i < my_tiles; i += TC_GROUPS) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
-            const int64_t gq = (blockIdx.x + i * gridDim.x) * 4 + cw;   // this warp's candidate
+            const int64_t gq = tc_tile_cand(i) + cw;   // this warp's candidate
             const bool live = gq < total_cand;
             const int id = id_n;
             const float djf = dj_n;
             {
                 const int64_t i2 = i + TC_GROUPS;
-                const int64_t gq2 = (blockIdx.x + i2 * gridDim.x) * 4 + cw;
+                const int64_t gq2 = tc_tile_cand(i2) + cw;
                 if (i2 < my_tiles && gq2 < total_cand) {
                     id_n = __ldg(kidx + gq2 * 32 + lane);
                     dj_n = __ldg(kdist + gq2 * 32 + lane);
@@ -388,9 +419,9 @@ extern "C" int dvcp_dfe_tc_b_offset(int n, int k) {
 
 extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const float *tgt_feat, const float *knn_dist,
                                const int32_t *knn_idx, int B, int N, int64_t Q, const float *b_hi,
-                               const float *b_lo, int quirks, float *out, dvcp_stream_t stream) {
+                               const float *b_lo, int quirks, int feature_major_c, float *out, dvcp_stream_t stream) {
     if (!cand || !tgt_xyz.base || !tgt_feat || !knn_dist || !knn_idx || !b_hi || !b_lo || !out || B <= 0 || N <= 0 ||
-        Q <= 0)
+        Q <= 0 || feature_major_c < 0 || (feature_major_c > 0 && Q % feature_major_c != 0))
         return DVCP_E_ARG;
     const int64_t total = (int64_t)B * Q;
     const int64_t ntiles = (total + 3) / 4;
@@ -399,7 +430,7 @@ extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const fl
     if (grid > ntiles) grid = ntiles;
     // one cloud stride for the whole batch: tgt_xyz is addressed with b = candidate / Q
     dfe_tgt_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
-        cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, (quirks >> 1) & 1, out);
+        cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, (quirks >> 1) & 1, feature_major_c, out);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

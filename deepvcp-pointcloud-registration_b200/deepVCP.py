@@ -210,26 +210,34 @@ class DeepVCP(nn.Module):
                 kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
                                         want32=True)
             mark("knn")
+            reshape_quirk = bool(self.quirks & QUIRK_COST_VOLUME_RESHAPE)
+            fm = False   # tgt_dfe held feature-major per key-point ([B,K,32,C])?
             if self.dfe_tensor_cores:
                 b_hi, b_lo = self.DFE.tc_operand()
                 # point-major float4 copy of the target xyz: one 16-byte load per gathered neighbour
                 tgt4 = F_.pack_xyz4(cloud_cm(tgt), dev, B, N)
+                # Reference mode: cpg.py:34 re-reads the LOGICAL [32, C] order of the permuted tensor (Q4); the
+                # embedding kernel writes exactly that order, so CPG finds a voxel's 32 values contiguous
+                # (layout 0) and its tensor-core kernel applies. Intended mode wants [C, 32] as it is: also layout 0.
+                fm = reshape_quirk
                 tgt_dfe = F_.dfe_tgt_tc(cand.view(B, K * C, 3), cloud_pm(tgt4), tfeat, kd, ki32, B, N, b_hi, b_lo,
-                                        self.quirks)                           # [B,K*C,32]
+                                        self.quirks, feature_major_c=C if fm else 0)   # [B,K*C,32] or [B,K,32,C]
             else:
                 tgt_dfe = F_.dfe_tgt_fused(cand.view(B, K * C, 3), cloud_cm(tgt), tfeat, kd, ki32, B, N, dfe,
                                            self.quirks)
             mark("dfe")
-            # corresponding point generation
-            # tgt_dfe is [candidate, feature] in memory: layout 1 applies the reference's permute + reshape
-            # (Q4); layout 0 reads it as it is, i.e. cost[c, f] = (src[f] - tgt[c, f])^2 (intended mode)
-            vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.view(B * K, C * 32),
-                                 1 if self.quirks & QUIRK_COST_VOLUME_RESHAPE else 0,
+            # corresponding point generation. layout 0: the flat tensor IS the logical [32, C] order the reference
+            # reshapes (or, in intended mode, cost[c, f] = (src[f] - tgt[c, f])^2 read as it lies); layout 1: the
+            # flat tensor is [C, 32] and the kernel applies the reference's permute + reshape itself
+            vcp, logits = F_.cpg(src_dfe.view(B * K, 32), tgt_dfe.reshape(B * K, C * 32),
+                                 1 if (reshape_quirk and not fm) else 0,
                                  cand.view(B * K, C, 3), G, self.cpg.params(), want_logits=keep_stages)
+            if fm:
+                tgt_dfe = tgt_dfe.permute(0, 1, 3, 2)        # logical [B,K,C,32] view for inspection
             mark("cpg")
         if keep_stages:
             self.last = dict(src_fps=sfps, tgt_fps=tfps, src_fe_feat=sfeat, tgt_fe_feat=tfeat, scores=scores,
                              topk_idx=topk, src_keypts_full=keypts, picked_idx=picked, src_cat=cat,
                              src_dfe=src_dfe, centres=centres, candidates=cand, knn_dist=kd, knn_idx=ki64,
-                             tgt_dfe=tgt_dfe.view(B, K, C, 32), logits=logits, vcp=vcp.view(B, K, 3))
+                             tgt_dfe=tgt_dfe.reshape(B, K, C, 32), logits=logits, vcp=vcp.view(B, K, 3))
         return keypts[:, :, :3], vcp.view(B, K, 3)

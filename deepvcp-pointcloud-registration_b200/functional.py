@@ -393,12 +393,15 @@ def pack_xyz4(xyz_cloud: Cloud, device, B, N):
     return out
 
 
-def dfe_tgt_tc(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, b_hi, b_lo, quirks):
+def dfe_tgt_tc(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, b_hi, b_lo, quirks, feature_major_c=0):
+    """-> [B,Q,32]; feature_major_c = C > 0: [B,Q/C,32,C] (every key-point's block feature-major)."""
     require_cuda(cand, tgt_feat, knn_dist, knn_idx32, b_hi, b_lo)
     Q = knn_dist.shape[1]
-    out = torch.empty(B, Q, 32, dtype=torch.float32, device=cand.device)
+    out = (torch.empty(B, Q, 32, dtype=torch.float32, device=cand.device) if feature_major_c == 0 else
+           torch.empty(B, Q // feature_major_c, 32, feature_major_c, dtype=torch.float32, device=cand.device))
     check(lib().dvcp_dfe_tgt_tc(ptr(_f32c(cand)), tgt_cloud, ptr(_f32c(tgt_feat)), ptr(knn_dist), ptr(knn_idx32), B, N,
-                                Q, ptr(b_hi), ptr(b_lo), quirks, ptr(out), stream_ptr(cand.device)), "dvcp_dfe_tgt_tc")
+                                Q, ptr(b_hi), ptr(b_lo), quirks, feature_major_c, ptr(out), stream_ptr(cand.device)),
+          "dvcp_dfe_tgt_tc")
     _count(1)
     return out
 
@@ -418,7 +421,7 @@ def dfe_dense(X, dfe):
     return out
 
 
-CPG_AUTO, CPG_FUSED, CPG_LAYERED = 0, 1, 2
+CPG_AUTO, CPG_FUSED, CPG_LAYERED, CPG_TC = 0, 1, 2, 3
 
 
 def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False, path=CPG_AUTO):
@@ -434,7 +437,8 @@ def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False, path=CPG_A
     logits = torch.empty(M, C, dtype=torch.float32, device=dev) if want_logits else None
     check(lib().dvcp_cpg_path(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params,
                               ptr(vcp), ptr(logits), ptr(ws), nbytes, path, stream_ptr(dev)), "dvcp_cpg")
-    _count(1 if G <= 11 and path != CPG_LAYERED else 5)   # fused kernel up to 11^3, else cost + 3 convs + softmax
+    tc = path == CPG_TC or (path == CPG_AUTO and layout == 0 and 2 <= G <= 11)
+    _count(2 if tc else (1 if G <= 11 and path != CPG_LAYERED else 5))   # TC: weight image + kernel; fused: 1; layered: 5
     return vcp, logits
 
 

@@ -256,12 +256,16 @@ DVCP_API int dvcp_dfe_tgt_fused(const float *cand, dvcp_cloud_t tgt_xyz, const f
  *     Bm[n][k] = Wc[n][3 + k] (k < 32), Wc[n][k - 32] (32 <= k < 35), bc[n] (k = 35), 0
  * stored at float offset dvcp_dfe_tc_b_offset(n, k) (UMMA K-major core-matrix
  * layout), dvcp_dfe_tc_b_floats() floats each. Same inputs / output as the fused
- * entry point; results agree with it to FP32 round-off of the collapsed map. */
+ * entry point; results agree with it to FP32 round-off of the collapsed map.
+ * feature_major_c: 0 = out [B,Q,32] (candidate, feature); C > 0 (Q % C == 0) = every block of C candidates
+ * (one key-point) is written feature-major, out [B,Q/C,32,C] -- the logical [32,C] order of deepVCP.py:106
+ * that dvcp_cpg reads with layout 0. */
 DVCP_API int dvcp_dfe_tc_b_floats(void);
 DVCP_API int dvcp_dfe_tc_b_offset(int n, int k);
 DVCP_API int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const float *tgt_feat, const float *knn_dist,
                     const int32_t *knn_idx, int B, int N, int64_t Q, const float *b_hi, const float *b_lo,
-                    int quirks, float *out, dvcp_stream_t stream);
+                    int quirks, int feature_major_c, float *out, dvcp_stream_t stream);
+DVCP_API int64_t dvcp_cpg_tc_image_bytes(void);
 
 /* ---- a15 feat_embedding_layer.forward on a materialised input
  *          deep_feat_embedding.py:23-61
@@ -284,11 +288,12 @@ DVCP_API int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, co
              int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
              int64_t workspace_bytes, dvcp_stream_t stream);
 /* Same, with the kernel family chosen by the caller (parity tests compare the families with each other
- * and with the oracle at every grid size): AUTO = what dvcp_cpg picks; FUSED = whole chain in one kernel
+ * and with the oracle at every grid size): AUTO = what dvcp_cpg picks (TC for layout 0 up to 11^3); FUSED = whole chain in one kernel
  * with the volume in shared memory (G <= 11); LAYERED = one kernel per layer through the workspace. */
 #define DVCP_CPG_AUTO    0
 #define DVCP_CPG_FUSED   1
 #define DVCP_CPG_LAYERED 2
+#define DVCP_CPG_TC      3   /* conv1 as an implicit GEMM on tcgen05 (3xTF32, TMEM); layout 0, 2 <= G <= 11 */
 DVCP_API int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
              int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
              int64_t workspace_bytes, int path, dvcp_stream_t stream);
