@@ -15,7 +15,7 @@
 // ((dx * Gp + dy) * Gp + dz) rows, zero padding comes from the halo rows, and no im2col copy exists.
 // M tiles of 128 consecutive padded rows cover the interior (15 tiles for G = 11; the results of halo
 // rows are ignored). Eight input channels (one MMA K step) are resident at a time: 4 passes per volume,
-// 27 taps x 15 tiles x 3 MMAs each, all accumulating into the same 15 x 16 TMEM columns.
+// 27 taps x 15 tiles x 2 MMAs each (Vh [Wh | Wl], N = 32; Vl Wh, N = 16), accumulating into 15 x 32 TMEM columns.
 //
 // conv2 / conv3 / softmax / weighted sum follow in the same CTA on the CUDA cores (they are 12 % of the
 // arithmetic) with the volume in shared memory, as in cpg_fused_kernel (cpg.cu).
@@ -28,8 +28,8 @@ namespace dvcp {
 
 constexpr int CT_THREADS = 512;
 constexpr int CT_MAXG = 11;
-constexpr int CT_TMEM_COLS = 256;
-constexpr int CT_B_FLOATS_Q = 27 * 2 * 2 * 16 * 4;   // per channel octet: [tap][hi|lo][k half][cout][4]
+constexpr int CT_TMEM_COLS = 512;
+constexpr int CT_B_FLOATS_Q = 27 * 2 * 32 * 4;   // per channel octet: [tap][k half][hi cout 0..15 | lo cout 0..15][4]
 constexpr int CT_B_FLOATS = 4 * CT_B_FLOATS_Q;
 
 __device__ __forceinline__ uint32_t ct_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -38,15 +38,16 @@ __device__ __forceinline__ uint32_t ct_smem_u32(const void *p) { return (uint32_
 __device__ __forceinline__ uint64_t ct_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 16
-constexpr uint32_t CT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = 16 / 32
+constexpr uint32_t CT_IDESC16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t CT_IDESC32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void ct_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void ct_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(CT_IDESC), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void ct_mbar_wait(uint64_t *bar, unsigned parity) {
@@ -71,12 +72,14 @@ __device__ __forceinline__ bool ct_elect_one() {
 }
 __device__ __forceinline__ float ct_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
-// conv1 weights [16][32][27] -> the N-side operand image, split hi / lo:
-//   image[q][tap][h][kh][n][e] = part_h( w1[n][8 q + 4 kh + e][tap] )
+// conv1 weights [16][32][27] -> the N-side operand image, split hi / lo; the 32 rows of a tap are
+// [hi of cout 0..15 | lo of cout 0..15], so ONE MMA forms Vh * [Wh | Wl] (the operand Vh is fetched from shared
+// memory once for both terms: the MMAs of this kernel are bound by their operand reads, N being only 16):
+//   image[q][tap][kh][h * 16 + n][e] = part_h( w1[n][8 q + 4 kh + e][tap] )
 __global__ void cpg_tc_prepare_kernel(const float *__restrict__ w1, float *__restrict__ image) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= CT_B_FLOATS) return;
-    const int e = i & 3, n = (i >> 2) & 15, kh = (i >> 6) & 1, h = (i >> 7) & 1, tap = (i >> 8) % 27, q = (i >> 8) / 27;
+    const int e = i & 3, n = (i >> 2) & 15, h = (i >> 6) & 1, kh = (i >> 7) & 1, tap = (i >> 8) % 27, q = (i >> 8) / 27;
     const float w = __ldg(w1 + (n * 32 + 8 * q + 4 * kh + e) * 27 + tap);
     const float hi = ct_hi(w);
     image[i] = h == 0 ? hi : w - hi;
@@ -182,21 +185,20 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const bool leader = ct_elect_one();
                 for (int tile = warp; tile < ntiles; tile += CT_THREADS / 32) {
-                    const uint32_t d = tmem_base + (uint32_t)tile * 16u;
+                    const uint32_t d = tmem_base + (uint32_t)tile * 32u;   // columns 0..15: Vh Wh + Vl Wh, 16..31: Vh Wl
                     const uint32_t row0 = (uint32_t)(m_lo + tile * 128);
                     const uint64_t a0 = ct_desc(a_base + row0 * 16u, plane, 128u);
-                    const uint64_t w0 = ct_desc(b_base, 256u, 128u);
+                    const uint64_t w0 = ct_desc(b_base, 512u, 128u);
 #pragma unroll
                     for (int tap = 0; tap < 27; ++tap) {
                         const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
                         // the address field counts 16-byte units = rows: a tap shifts the descriptor by a constant
                         const uint64_t a_hi = a0 + (uint64_t)(int64_t)(dx * Gp2 + dy * Gp + dz);
                         const uint64_t a_lo = a_hi + (uint64_t)(2u * (plane >> 4));
-                        const uint64_t w_hi = w0 + (uint64_t)(tap * 64), w_lo = w_hi + 32u;   // 1024 B per tap, lo at + 512 B
+                        const uint64_t w = w0 + (uint64_t)(tap * 64);   // 1024 B per tap
                         if (leader) {
-                            ct_mma(d, a_hi, w_hi, (q | tap) != 0);
-                            ct_mma(d, a_lo, w_hi, 1u);
-                            ct_mma(d, a_hi, w_lo, 1u);
+                            ct_mma(d, a_hi, w, CT_IDESC32, (q | tap) != 0);   // Vh * [Wh | Wl]
+                            ct_mma(d, a_lo, w, CT_IDESC16, 1u);               // Vl * Wh (the first 16 rows)
                         }
                     }
                 }
@@ -215,13 +217,17 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         {
             const int lq = warp & 3;   // a warp reads the TMEM lanes 32 (warp % 4) .. + 31
             for (int tile = warp >> 2; tile < ntiles; tile += CT_THREADS / 128) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)tile * 16u;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)tile * 32u;
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int r = m_lo + tile * 128 + lq * 32 + lane;
@@ -229,7 +235,8 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                 if (xp >= 1 && xp <= G && yp >= 1 && yp <= G && zp >= 1 && zp <= G) {
                     const int c = ((xp - 1) * G + (yp - 1)) * G + (zp - 1);
 #pragma unroll
-                    for (int o = 0; o < 16; ++o) A1[o * Cp + c] = __uint_as_float(v[o]) + __ldg(p.b1 + o);
+                    for (int o = 0; o < 16; ++o)
+                        A1[o * Cp + c] = (__uint_as_float(v[o]) + __uint_as_float(v[16 + o])) + __ldg(p.b1 + o);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
