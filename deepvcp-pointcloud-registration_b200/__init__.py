@@ -16,7 +16,7 @@ from .cpg import cpg                                                   # noqa: F
 from .deep_feat_embedding import feat_embedding_layer                  # noqa: F401
 from .deep_feat_extraction import feat_extraction_layer                # noqa: F401
 from .deepVCP import DeepVCP                                           # noqa: F401
-from .deepVCP_loss import get_rigid_transform, pose_from_forward, svd_optimization  # noqa: F401
+from .deepVCP_loss import deepVCP_loss, get_rigid_transform, pose_from_forward, svd_optimization  # noqa: F401
 from .get_cat_feat_src import Get_Cat_Feat_Src                         # noqa: F401
 from .get_cat_feat_tgt import Get_Cat_Feat_Tgt                         # noqa: F401
 from .pipeline import StreamedRegistration                             # noqa: F401

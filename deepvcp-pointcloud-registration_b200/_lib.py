@@ -64,6 +64,12 @@ SIGNATURES = {
     "dvcp_topk": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_keypoint_stage": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64,
                                     c_f32, c_i32, DfeParams, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dvcp_square_distance_f64": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "dvcp_ball_query_f64": (c_i32, [Cloud, Cloud, c_i32, c_i32, c_i32, c_f64, c_i32, c_vp, c_vp]),
+    "dvcp_sa_layer_f64": (c_i32, [Cloud, Cloud, c_i32, c_vp, c_i32, c_i32, c_i32, c_f64, c_i32,
+                                  ctypes.POINTER(MlpLayer), c_i32, c_vp, c_vp, c_vp]),
+    "dvcp_keypoint_stage_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i64,
+                                        c_f64, c_i32, DfeParams, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_grid_size": (c_i32, [c_f64, c_f64]),
     "dvcp_candidates": (c_i32, [c_vp, c_i64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "dvcp_knn": (c_i32, [Cloud, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
@@ -87,7 +93,7 @@ SIGNATURES = {
     "dvcp_ingest_kitti": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dvcp_kabsch": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_kabsch_refine": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
-                                   c_vp]),
+                                   c_vp, c_vp]),
 }
 
 # A set bit replicates the reference; a clear bit selects the semantics its code intends

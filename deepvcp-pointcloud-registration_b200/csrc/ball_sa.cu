@@ -143,7 +143,8 @@ __device__ __forceinline__ void sa_stage_weights(const SaParams &P, float *swt, 
 
 // Shared MLP of ONE member, evaluated by the whole warp (lane = output channel).
 // rel = member - centre; extra channels read from `feats` at original index pn.
-__device__ __forceinline__ void sa_member_mlp(const SaParams &P, const SaWeights &w, const Cloud &feats, int D,
+template <class FeatCloud>
+__device__ __forceinline__ void sa_member_mlp(const SaParams &P, const SaWeights &w, const FeatCloud &feats, int D,
                                               int b, int pn, float rx, float ry, float rz, float &best0,
                                               float &best1) {
     const int lane = lane_id();
@@ -157,7 +158,7 @@ __device__ __forceinline__ void sa_member_mlp(const SaParams &P, const SaWeights
         float acc0 = 0.f, acc1 = 0.f;
         if (l == 0) {
             for (int k = 0; k < cin; ++k) {
-                const float v = k == 0 ? rx : (k == 1 ? ry : (k == 2 ? rz : feats.at(b, pn, k - 3)));
+                const float v = k == 0 ? rx : (k == 1 ? ry : (k == 2 ? rz : (float)feats.at(b, pn, k - 3)));
                 if (o0 < co) acc0 = fmaf(W[o0 * cin + k], v, acc0);
                 if (o1 < co) acc1 = fmaf(W[o1 * cin + k], v, acc1);
             }
@@ -956,9 +957,162 @@ topk_kernel(const float *__restrict__ scores, int S, int K, int64_t *__restrict_
     }
 }
 
+// ------------------------------------------------------ float64 clouds -------
+// The reference's loaders hand over float64 clouds (ModelNet40Dataset.py:38,92; KITTIDataset.py:84,97 for
+// the target). torch then evaluates square_distance / query_ball_point in double (pointnet2_utils.py:35-40,
+// 100-102: fma-chain dot as the DGEMM does, compare against the Python double radius**2), groups in double
+// and casts to float right before the shared MLP (`conv(new_points.float())`, :198). These kernels follow
+// that; they walk the whole cloud (no spatial index): the float64 path is accepted, exact, and not tuned.
+__device__ __forceinline__ double norm2_nofma_d(double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+}
+__device__ __forceinline__ double sqdist_expanded_d(double qx, double qy, double qz, double qq, double px, double py,
+                                                    double pz, double pp) {
+    const double dot = __fma_rn(qz, pz, __fma_rn(qy, py, __dmul_rn(qx, px)));
+    return __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), qq), pp);
+}
+
+__global__ void square_distance_f64_kernel(CloudD src, CloudD dst, int S, int N, double *__restrict__ out) {
+    const int b = blockIdx.z, s = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const double qx = src.at(b, s, 0), qy = src.at(b, s, 1), qz = src.at(b, s, 2);
+    const double px = dst.at(b, n, 0), py = dst.at(b, n, 1), pz = dst.at(b, n, 2);
+    out[((int64_t)b * S + s) * N + n] =
+        sqdist_expanded_d(qx, qy, qz, norm2_nofma_d(qx, qy, qz), px, py, pz, norm2_nofma_d(px, py, pz));
+}
+
+// one warp per query, points in index order
+__global__ void __launch_bounds__(256)
+ball_query_f64_kernel(CloudD xyz, CloudD qry, int N, int S, double r2, int nsample, int64_t *__restrict__ out) {
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= S) return;
+    const double qx = qry.at(b, s, 0), qy = qry.at(b, s, 1), qz = qry.at(b, s, 2), qq = norm2_nofma_d(qx, qy, qz);
+    int64_t *row = out + ((int64_t)b * S + s) * nsample;
+    int cnt = 0, first = N;
+    for (int base = 0; base < N && cnt < nsample; base += 32) {
+        const int n = base + lane;
+        bool in = false;
+        if (n < N) {
+            const double px = xyz.at(b, n, 0), py = xyz.at(b, n, 1), pz = xyz.at(b, n, 2);
+            in = !(sqdist_expanded_d(qx, qy, qz, qq, px, py, pz, norm2_nofma_d(px, py, pz)) > r2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (m) {
+            if (first == N) first = base + __ffs(m) - 1;
+            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+            if (in && slot < nsample) row[slot] = n;
+            cnt += __popc(m);
+        }
+    }
+    for (int j = cnt + lane; j < nsample; j += 32) row[j] = first;   // padding (first == N: empty ball)
+}
+
+// one warp per centroid: ball query in double, relative coordinates formed in double and cast to float
+// (pointnet2_utils.py:128,198), then the shared MLP member after member
+__global__ void __launch_bounds__(SA_WARPS * 32)
+sa_layer_f64_kernel(CloudD xyz, CloudD feats, int D, const int32_t *__restrict__ cidx, int B, int N, int S, double r2,
+                    int nsample, SaParams P, float *__restrict__ out_feat, double *__restrict__ out_xyz) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SaWeights w;
+    sa_stage_weights(P, smem, w);
+    __syncthreads();
+    const int clast = P.cout[P.n_layers - 1];
+    const int64_t item = (int64_t)blockIdx.x * SA_WARPS + warp;
+    if (item >= (int64_t)B * S) return;
+    const int b = (int)(item / S), s = (int)(item - (int64_t)b * S);
+    const int c = cidx[(int64_t)b * S + s];
+    const double qx = xyz.at(b, c, 0), qy = xyz.at(b, c, 1), qz = xyz.at(b, c, 2), qq = norm2_nofma_d(qx, qy, qz);
+    if (out_xyz && lane < 3) out_xyz[((int64_t)b * S + s) * 3 + lane] = lane == 0 ? qx : (lane == 1 ? qy : qz);
+    float best0 = -INFINITY, best1 = -INFINITY;
+    int cnt = 0;
+    for (int base = 0; base < N && cnt < nsample; base += 32) {
+        const int n = base + lane;
+        bool in = false;
+        double px = 0.0, py = 0.0, pz = 0.0;
+        if (n < N) {
+            px = xyz.at(b, n, 0); py = xyz.at(b, n, 1); pz = xyz.at(b, n, 2);
+            in = !(sqdist_expanded_d(qx, qy, qz, qq, px, py, pz, norm2_nofma_d(px, py, pz)) > r2);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, in);
+        if (!m) continue;
+        int take = min(__popc(m), nsample - cnt);
+        cnt += __popc(m);
+        const float rx = (float)__dsub_rn(px, qx), ry = (float)__dsub_rn(py, qy), rz = (float)__dsub_rn(pz, qz);
+        while (take-- > 0) {
+            const int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            sa_member_mlp(P, w, feats, D, b, base + src_lane, __shfl_sync(0xffffffffu, rx, src_lane),
+                          __shfl_sync(0xffffffffu, ry, src_lane), __shfl_sync(0xffffffffu, rz, src_lane), best0, best1);
+        }
+    }
+    if (lane < clast) out_feat[((int64_t)b * S + s) * clast + lane] = best0;
+    if (lane + 32 < clast) out_feat[((int64_t)b * S + s) * clast + lane + 32] = best1;
+}
+
 }  // namespace dvcp
 
 using namespace dvcp;
+
+static int sa_params_from_layers(const dvcp_mlp_layer_t *layers, int n_layers, int D, SaParams &P, size_t &wfloats) {
+    if (n_layers < 1 || n_layers > 3 || 3 + D > SA_MAXIN) return DVCP_E_UNSUPPORTED;
+    P.n_layers = n_layers;
+    int cin = 3 + D;
+    wfloats = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (layers[l].in_ch != cin || layers[l].out_ch < 1 || layers[l].out_ch > SA_MAXC) return DVCP_E_UNSUPPORTED;
+        P.W[l] = layers[l].W; P.b[l] = layers[l].b; P.alpha[l] = layers[l].alpha; P.beta[l] = layers[l].beta;
+        if (!P.W[l] || !P.b[l] || !P.alpha[l] || !P.beta[l]) return DVCP_E_ARG;
+        P.cin[l] = cin; P.cout[l] = layers[l].out_ch;
+        wfloats += (size_t)cin * layers[l].out_ch + 3 * layers[l].out_ch;
+        cin = layers[l].out_ch;
+    }
+    for (int l = n_layers; l < 3; ++l) { P.W[l] = P.b[l] = P.alpha[l] = P.beta[l] = nullptr; P.cin[l] = P.cout[l] = 0; }
+    return 0;
+}
+
+extern "C" int dvcp_square_distance_f64(dvcp_cloud_t src, dvcp_cloud_t dst, int B, int S, int N, double *out,
+                                        dvcp_stream_t stream) {
+    if (!src.base || !dst.base || !out || B <= 0 || S <= 0 || N <= 0) return DVCP_E_ARG;
+    if (S > 65535 || B > 65535) return DVCP_E_UNSUPPORTED;
+    dim3 grid((N + 255) / 256, S, B);
+    square_distance_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(as_cloud_d(src), as_cloud_d(dst), S, N, out);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dvcp_ball_query_f64(dvcp_cloud_t xyz, dvcp_cloud_t new_xyz, int B, int N, int S, double radius2,
+                                   int nsample, int64_t *out, dvcp_stream_t stream) {
+    if (!xyz.base || !new_xyz.base || !out || B <= 0 || N <= 0 || S <= 0 || nsample <= 0) return DVCP_E_ARG;
+    if (B > 65535) return DVCP_E_UNSUPPORTED;
+    dim3 grid((S + 7) / 8, B);
+    ball_query_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(as_cloud_d(xyz), as_cloud_d(new_xyz), N, S, radius2,
+                                                                 nsample, out);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dvcp_sa_layer_f64(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *centroid_idx, int B,
+                                 int N, int S, double radius2, int nsample, const dvcp_mlp_layer_t *layers,
+                                 int n_layers, float *out_feat, double *out_xyz, dvcp_stream_t stream) {
+    if (!xyz.base || !centroid_idx || !layers || !out_feat || B <= 0 || N <= 0 || S <= 0 || nsample <= 0)
+        return DVCP_E_ARG;
+    if (D < 0 || (D > 0 && !feats.base)) return DVCP_E_ARG;
+    SaParams P;
+    size_t wfloats;
+    const int rc = sa_params_from_layers(layers, n_layers, D, P, wfloats);
+    if (rc) return rc;
+    CloudD f = D > 0 ? as_cloud_d(feats) : CloudD{nullptr, 0, 0, 0};
+    const size_t smem = wfloats * sizeof(float);
+    DVCP_CUDA(cudaFuncSetAttribute(sa_layer_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = ((int64_t)B * S + SA_WARPS - 1) / SA_WARPS;
+    sa_layer_f64_kernel<<<(unsigned)blocks, SA_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        as_cloud_d(xyz), f, D, centroid_idx, B, N, S, radius2, nsample, P, out_feat, out_xyz);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int dvcp_ball_query(dvcp_cloud_t xyz, dvcp_cloud_t new_xyz, int B, int N, int S, float radius2,
                                int nsample, int64_t *out, dvcp_stream_t stream) {

@@ -201,7 +201,8 @@ template <typename T>
 __global__ void __launch_bounds__(32)
 kabsch_refine_kernel(const T *__restrict__ x, const T *__restrict__ yp, int cs, int ps, const double *__restrict__ Rt,
                      const double *__restrict__ tt, int n, int keepn, bool fix_reflection, double *__restrict__ R2o,
-                     double *__restrict__ t2o, double *__restrict__ R1o, double *__restrict__ t1o) {
+                     double *__restrict__ t2o, double *__restrict__ R1o, double *__restrict__ t1o,
+                     int64_t *__restrict__ inliers) {
     __shared__ float s_ref[3][KR_MAXN];   // float32(y_pred1)
     __shared__ float s_d[KR_MAXN];        // 1-NN distance of y_true[i]
     __shared__ unsigned char s_keep[KR_MAXN];
@@ -240,6 +241,8 @@ kabsch_refine_kernel(const T *__restrict__ x, const T *__restrict__ yp, int cs, 
             rank += (dj < di) || (dj == di && j < i);
         }
         s_keep[i] = rank < keepn;
+        // the inlier list in the order of torch.topk(largest=False, sorted=True) (deepVCP_loss.py:77)
+        if (inliers && rank < keepn) inliers[(int64_t)b * keepn + rank] = i;
     }
     __syncwarp();
     double R2[9], t2[3];
@@ -271,12 +274,13 @@ extern "C" int dvcp_kabsch(const void *x, const void *y, int dtype, const double
 
 extern "C" int dvcp_kabsch_refine(const double *x, const double *y_pred, const double *R_true,
                                   const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
-                                  double *R1, double *t1, dvcp_stream_t stream) {
+                                  double *R1, double *t1, int64_t *inliers, dvcp_stream_t stream) {
     if (!x || !y_pred || !R_true || !t_true || !R2 || !t2 || B <= 0 || n <= 0 || keep <= 0 || keep > n)
         return DVCP_E_ARG;
     if (n > KR_MAXN) return DVCP_E_UNSUPPORTED;
     kabsch_refine_kernel<double><<<B, 32, 0, (cudaStream_t)stream>>>(x, y_pred, n, 1, R_true, t_true, n, keep,
-                                                                     !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2, R1, t1);
+                                                                     !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2, R1, t1,
+                                                                     inliers);
     DVCP_CHECK_LAUNCH();
     return 0;
 }
@@ -289,7 +293,7 @@ extern "C" int dvcp_pose_from_forward(const float *src_keypts, const float *tgt_
     if (n > KR_MAXN) return DVCP_E_UNSUPPORTED;
     kabsch_refine_kernel<float><<<B, 32, 0, (cudaStream_t)stream>>>(src_keypts, tgt_vcp, 1, 3, R_true, t_true, n, keep,
                                                                     !(quirks & DVCP_QUIRK_NO_REFLECTION_FIX), R2, t2,
-                                                                    nullptr, nullptr);
+                                                                    nullptr, nullptr, nullptr);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

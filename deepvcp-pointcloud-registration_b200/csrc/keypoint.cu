@@ -21,21 +21,45 @@ constexpr int KP_MAX = 128;     // key-points per pair supported
 constexpr int KP_MAXC = 8;      // input channels supported
 constexpr int KP_THREADS = 256;
 
+// arithmetic of the cloud's dtype T (float32, or float64 as the reference's loaders produce): every expression
+// below is evaluated in T exactly where torch evaluates it in the tensor's dtype; the cast to float32 happens
+// where the reference's `.float()` does (deep_feat_embedding.py:29)
+template <class T> struct KpArith;
+template <> struct KpArith<float> {
+    static __device__ __forceinline__ float sq3(float x, float y, float z) { return sq3_nofma(x, y, z); }
+    static __device__ __forceinline__ float sqd(float qx, float qy, float qz, float qq, float px, float py, float pz, float pp) {
+        return sqdist_expanded(qx, qy, qz, qq, px, py, pz, pp);
+    }
+    static __device__ __forceinline__ float root(float v) { return sqrtf(v); }
+};
+template <> struct KpArith<double> {
+    static __device__ __forceinline__ double sq3(double x, double y, double z) {
+        return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+    }
+    static __device__ __forceinline__ double sqd(double qx, double qy, double qz, double qq, double px, double py, double pz, double pp) {
+        const double dot = __fma_rn(qz, pz, __fma_rn(qy, py, __dmul_rn(qx, px)));
+        return __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), qq), pp);
+    }
+    static __device__ __forceinline__ double root(double v) { return sqrt(v); }
+};
+
+template <class T>
 __global__ void __launch_bounds__(KP_THREADS)
-keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const int64_t *__restrict__ topk,
+keypoint_stage_kernel(const T *__restrict__ src_pts, int C_in, int N, const int64_t *__restrict__ topk,
                       int Kp, const int64_t *__restrict__ kp_start, const float *__restrict__ src_feat, int S,
                       const double *__restrict__ R_init, const double *__restrict__ t_init, int64_t t_bstride,
-                      float radius2, int nsample, dvcp_dfe_params_t P, int ref_layout, float *__restrict__ keypts, int64_t *__restrict__ picked,
+                      T radius2, int nsample, dvcp_dfe_params_t P, int ref_layout, T *__restrict__ keypts, int64_t *__restrict__ picked,
                       float *__restrict__ src_cat, float *__restrict__ src_dfe, double *__restrict__ centres) {
+    using A = KpArith<T>;
     __shared__ __align__(16) float s_w[DFE_SMEM_FLOATS];
-    __shared__ float s_kp[KP_MAX * KP_MAXC];
-    __shared__ float s_x[KP_MAX], s_y[KP_MAX], s_z[KP_MAX], s_pp[KP_MAX];
+    __shared__ T s_kp[KP_MAX * KP_MAXC];
+    __shared__ T s_x[KP_MAX], s_y[KP_MAX], s_z[KP_MAX], s_pp[KP_MAX];
     __shared__ int s_fps[KP_MAX];
     __shared__ int s_pick[KP_MAX][32];
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = KP_THREADS / 32;
     dfe_stage_weights(P, s_w);
-    const float *pts = src_pts + (int64_t)b * C_in * N;
+    const T *pts = src_pts + (int64_t)b * C_in * N;
     const int64_t *tk = topk + (int64_t)b * Kp;
 
     // 1. gather
@@ -48,17 +72,17 @@ keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const 
             k = f / C_in;
             c = f - k * C_in;
         }
-        const float v = __ldg(pts + (int64_t)c * N + tk[k]);
+        const T v = __ldg(pts + (int64_t)c * N + tk[k]);
         s_kp[f] = v;
         if (keypts) keypts[(int64_t)b * Kp * C_in + f] = v;
     }
     __syncthreads();
     for (int k = tid; k < Kp; k += KP_THREADS) {
-        const float x = s_kp[k * C_in], y = s_kp[k * C_in + 1], z = s_kp[k * C_in + 2];
+        const T x = s_kp[k * C_in], y = s_kp[k * C_in + 1], z = s_kp[k * C_in + 2];
         s_x[k] = x;
         s_y[k] = y;
         s_z[k] = z;
-        s_pp[k] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+        s_pp[k] = A::sq3(x, y, z);
         if (centres) {
             const double *R = R_init + (int64_t)b * 9;
             double *o = centres + ((int64_t)b * Kp + k) * 3;
@@ -81,14 +105,16 @@ keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const 
         unsigned far = (unsigned)kp_start[b];
         for (int i = 0; i < Kp; ++i) {
             if (lane == 0) s_fps[i] = (int)far;
-            const float cx = s_x[far], cy = s_y[far], cz = s_z[far];
+            const T cx = s_x[far], cy = s_y[far], cz = s_z[far];
             unsigned hi = 0u, lo = 0u;
 #pragma unroll
             for (int t = 0; t < KP_MAX / 32; ++t) {
                 const int n = lane + 32 * t;
                 if (n < Kp) {
-                    const float d = sq3_nofma(s_x[n] - cx, s_y[n] - cy, s_z[n] - cz);
-                    if (d < dmin[t]) dmin[t] = d;
+                    // float64 clouds: formed in double, compared with the float32 running minimum, stored
+                    // rounded to float32 (pointnet2_utils.py:80-82)
+                    const T d = A::sq3(s_x[n] - cx, s_y[n] - cy, s_z[n] - cz);
+                    if (d < (T)dmin[t]) dmin[t] = (float)d;
                     const unsigned bits = __float_as_uint(dmin[t]);
                     const unsigned l = 0xffffffffu - (unsigned)n;
                     if (bits > hi || (bits == hi && l > lo)) {
@@ -106,13 +132,12 @@ keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const 
     // 2b. ball query of the permuted key-points among the key-points
     for (int i = warp; i < Kp; i += nwarps) {
         const int c = s_fps[i];
-        const float qx = s_x[c], qy = s_y[c], qz = s_z[c], qq = s_pp[c];
+        const T qx = s_x[c], qy = s_y[c], qz = s_z[c], qq = s_pp[c];
         int cnt = 0, first = Kp;
         for (int base = 0; base < Kp && cnt < nsample; base += 32) {
             const int n = base + lane;
             const bool ok = n < Kp;
-            const float d2 = ok ? sqdist_expanded(qx, qy, qz, qq, s_x[n], s_y[n], s_z[n], s_pp[n]) : INFINITY;
-            const bool in = ok && !(d2 > radius2);
+            const bool in = ok && !(A::sqd(qx, qy, qz, qq, s_x[ok ? n : 0], s_y[ok ? n : 0], s_z[ok ? n : 0], s_pp[ok ? n : 0]) > radius2);
             const unsigned m = __ballot_sync(0xffffffffu, in);
             if (m) {
                 if (first == Kp) first = base + __ffs(m) - 1;
@@ -134,27 +159,27 @@ keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const 
         const int c = s_fps[i];
         const int pj = s_pick[i][lane];
         // grouped_xyz_norm (pointnet2_utils.py:128): member - permuted key-point
-        const float gx = s_x[pj] - s_x[c], gy = s_y[pj] - s_y[c], gz = s_z[pj] - s_z[c];
+        const T gx = s_x[pj] - s_x[c], gy = s_y[pj] - s_y[c], gz = s_z[pj] - s_z[c];
         // get_cat_feat_src.py:37-45: || kp_i - grouped + 1e-6 ||_2 with the UN-permuted key-point i
-        const float kx = s_x[i], ky = s_y[i], kz = s_z[i];
-        const float ex = (kx - gx) + 1e-6f, ey = (ky - gy) + 1e-6f, ez = (kz - gz) + 1e-6f;
-        const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
-        float sum = dist;
+        const T kx = s_x[i], ky = s_y[i], kz = s_z[i];
+        const T ex = (kx - gx) + (T)1e-6, ey = (ky - gy) + (T)1e-6, ez = (kz - gz) + (T)1e-6;
+        const T dist = A::root(A::sq3(ex, ey, ez));
+        T sum = dist;
 #pragma unroll
         for (int s = 16; s; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-        const float wn = dist / sum;
-        float x[36];
-        x[0] = gx - kx;
-        x[1] = gy - ky;
-        x[2] = gz - kz;
+        const T wn = dist / sum;
+        float x[36];   // the concatenated row after the reference's X.float()
+        x[0] = (float)(gx - kx);
+        x[1] = (float)(gy - ky);
+        x[2] = (float)(gz - kz);
         const float4 *fp = reinterpret_cast<const float4 *>(src_feat + ((int64_t)b * S + pj) * 32);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float4 v = __ldg(fp + k);
-            x[3 + 4 * k] = v.x * wn;
-            x[4 + 4 * k] = v.y * wn;
-            x[5 + 4 * k] = v.z * wn;
-            x[6 + 4 * k] = v.w * wn;
+            x[3 + 4 * k] = (float)((T)v.x * wn);
+            x[4 + 4 * k] = (float)((T)v.y * wn);
+            x[5 + 4 * k] = (float)((T)v.z * wn);
+            x[6 + 4 * k] = (float)((T)v.w * wn);
         }
         x[35] = 0.f;
         if (src_cat) {
@@ -174,21 +199,39 @@ keypoint_stage_kernel(const float *__restrict__ src_pts, int C_in, int N, const 
 
 using namespace dvcp;
 
+template <class T>
+static int keypoint_stage_launch(const T *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
+                                 const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
+                                 const double *t_init, int64_t t_bstride, T radius2, int nsample,
+                                 dvcp_dfe_params_t dfe, int quirks, T *keypts, int64_t *picked, float *src_cat,
+                                 float *src_dfe, double *centres, dvcp_stream_t stream) {
+    if (!src_pts || !topk || !kp_start || !src_feat || B <= 0 || N <= 0 || S <= 0) return DVCP_E_ARG;
+    if (centres && !R_init) return DVCP_E_ARG;
+    if (!dfe.W1 || !dfe.b1 || !dfe.W2 || !dfe.b2 || !dfe.W3 || !dfe.b3) return DVCP_E_ARG;
+    if (C_in < 3 || C_in > KP_MAXC || Kp < 1 || Kp > KP_MAX || nsample != 32 || Kp > S) return DVCP_E_UNSUPPORTED;
+    keypoint_stage_kernel<T><<<B, KP_THREADS, 0, (cudaStream_t)stream>>>(
+        src_pts, C_in, N, topk, Kp, kp_start, src_feat, S, R_init, (quirks & DVCP_QUIRK_IGNORE_T_INIT) ? nullptr : t_init,
+        t_bstride, radius2, nsample, dfe, quirks & 1, keypts, picked, src_cat, src_dfe, centres);
+    DVCP_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int dvcp_keypoint_stage(const float *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
                                    const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
                                    const double *t_init, int64_t t_bstride, float radius2, int nsample,
                                    dvcp_dfe_params_t dfe, int quirks, float *keypts,
                                    int64_t *picked, float *src_cat, float *src_dfe, double *centres,
                                    dvcp_stream_t stream) {
-    if (!src_pts || !topk || !kp_start || !src_feat || B <= 0 || N <= 0 || S <= 0) return DVCP_E_ARG;
-    if (centres && !R_init) return DVCP_E_ARG;
-    if (!dfe.W1 || !dfe.b1 || !dfe.W2 || !dfe.b2 || !dfe.W3 || !dfe.b3) return DVCP_E_ARG;
-    if (C_in < 3 || C_in > KP_MAXC || Kp < 1 || Kp > KP_MAX || nsample != 32 || Kp > S) return DVCP_E_UNSUPPORTED;
-    keypoint_stage_kernel<<<B, KP_THREADS, 0, (cudaStream_t)stream>>>(src_pts, C_in, N, topk, Kp, kp_start, src_feat,
-                                                                    S, R_init,
-                                                                    (quirks & DVCP_QUIRK_IGNORE_T_INIT) ? nullptr : t_init,
-                                                                    t_bstride, radius2, nsample, dfe, quirks & 1,
-                                                                    keypts, picked, src_cat, src_dfe, centres);
-    DVCP_CHECK_LAUNCH();
-    return 0;
+    return keypoint_stage_launch<float>(src_pts, C_in, B, N, topk, Kp, kp_start, src_feat, S, R_init, t_init, t_bstride,
+                                        radius2, nsample, dfe, quirks, keypts, picked, src_cat, src_dfe, centres, stream);
+}
+
+extern "C" int dvcp_keypoint_stage_f64(const double *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
+                                       const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
+                                       const double *t_init, int64_t t_bstride, double radius2, int nsample,
+                                       dvcp_dfe_params_t dfe, int quirks, double *keypts,
+                                       int64_t *picked, float *src_cat, float *src_dfe, double *centres,
+                                       dvcp_stream_t stream) {
+    return keypoint_stage_launch<double>(src_pts, C_in, B, N, topk, Kp, kp_start, src_feat, S, R_init, t_init, t_bstride,
+                                         radius2, nsample, dfe, quirks, keypts, picked, src_cat, src_dfe, centres, stream);
 }

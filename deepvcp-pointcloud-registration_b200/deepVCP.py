@@ -98,8 +98,9 @@ class DeepVCP(nn.Module):
         long) beside the second half of the previous batch (pipeline.StreamedRegistration)."""
         if self.training:
             raise RuntimeError("DeepVCP (b200) is the inference path: call .eval() first")
-        if src_pts.dtype != torch.float32 or tgt_pts.dtype != torch.float32:
-            raise NotImplementedError("float32 clouds only (the reference's float64 promotion is not accelerated)")
+        for x in (src_pts, tgt_pts):
+            if x.dtype not in (torch.float32, torch.float64):
+                raise RuntimeError("clouds must be float32 or float64, got %s" % x.dtype)
         dev = self.cpg.conv1.weight.device
         if dev.type != "cuda":
             raise RuntimeError("DeepVCP (b200) needs its parameters on a CUDA device; there is no CPU fallback")
@@ -116,6 +117,8 @@ class DeepVCP(nn.Module):
         D = C_in - 3
         self._events = [] if self.profile else None
         mark = lambda name: self._mark(name, dev)
+        if src.dtype == torch.float64 or tgt.dtype == torch.float64:
+            return self._extract_features_mixed(src, tgt, starts, B, N, C_in, S, D, dev)
 
         with torch.no_grad():
             mark("begin")
@@ -169,11 +172,48 @@ class DeepVCP(nn.Module):
         return dict(src=src, tgt=tgt, both=both, index=index, fps2=fps2, feat2=feat2, starts=starts, B=B, N=N,
                     C_in=C_in, dev=dev)
 
+    def _extract_features_mixed(self, src, tgt, starts, B, N, C_in, S, D, dev):
+        """Feature extraction when a cloud is float64 -- what the reference's loaders hand over
+        (ModelNet40Dataset.py:38,92: both float64; KITTIDataset.py:84,97: float32 scan, float64 target).
+        torch's promotion rules are followed cloud by cloud: FPS distances and the ball query in double
+        (pointnet2_utils.py:80-82,35-40,100-102), relative coordinates formed in double and cast to float
+        before the shared MLP (:198). A float32 cloud goes through the float32 kernels. The target is
+        additionally kept as float32 for the KNN (knn_cuda casts its inputs) and the embedding."""
+        if self.FE1.chained:
+            raise NotImplementedError("chained_fe with float64 clouds")
+        sa = self.FE1.sa1
+        mlp = sa.folded()
+        mark = lambda name: self._mark(name, dev)
+        with torch.no_grad():
+            mark("begin")
+            fps, feat = [], []
+            for pts, st in ((src, starts[0]), (tgt, starts[2])):
+                xyz_cloud = cloud_cm(pts)
+                feat_cloud = cloud_cm(pts[:, 3:, :]) if D else None
+                if pts.dtype == torch.float64:
+                    _, f32i = F_.fps(xyz_cloud, dev, pts.dtype, B, N, S, st, want64=False, want32=True)
+                    _, ft = F_.sa_layer_f64(xyz_cloud, feat_cloud, D, f32i, B, N, S, sa.radius, sa.nsample, mlp, dev,
+                                            want_xyz=False)
+                else:
+                    idx = F_.SpatialIndex(B, N, dev) if F_.SpatialIndex.indexable(N) else None
+                    _, f32i = F_.fps(xyz_cloud, dev, pts.dtype, B, N, S, st, want64=False, want32=True, index=idx)
+                    _, ft = F_.sa_layer(xyz_cloud, feat_cloud, D, f32i, B, N, S, sa.radius, sa.nsample, mlp, dev,
+                                        want_xyz=False, index=idx)
+                fps.append(f32i)
+                feat.append(ft)
+            mark("fps")
+            mark("sa_layer")
+            tgt32 = tgt.float()                       # knn_cuda: ref.float()  (get_cat_feat_tgt.py:45,52)
+            index = F_.build_index(cloud_cm(tgt32), dev, B, N) if F_.SpatialIndex.indexable(N) else None
+        return dict(src=src, tgt=tgt32, both=None, index=index, index_lo=0, fps2=torch.cat(fps), feat2=torch.cat(feat),
+                    starts=starts, B=B, N=N, C_in=C_in, dev=dev)
+
     def match(self, fe, R_init, keep_stages=False, topk_override=None, t_init=None):
         """Second half of forward(): key-point selection, candidates, KNN, embedding, CPG
         (deepVCP.py:33-110) on the state extract_features() returned."""
         src, tgt, index, fps2, feat2, starts = fe["src"], fe["tgt"], fe["index"], fe["fps2"], fe["feat2"], fe["starts"]
         B, N, dev = fe["B"], fe["N"], fe["dev"]
+        ilo = fe.get("index_lo", B)   # target clouds are batch items ilo..ilo+B-1 of the index
         K, ns = self.K_topk, self.nsample
         R = R_init.to(dev, non_blocking=True)
         require_cuda(R)
@@ -196,10 +236,10 @@ class DeepVCP(nn.Module):
             C = G * G * G
             if index is not None and self.knn_pools and N >= self.knn_pools_min_n:
                 # one CTA per key-point: the target points around its candidate lattice are pooled in shared memory
-                kd, ki64, ki32 = F_.knn_groups(index, B, dev, B, N, cand.view(B, K * C, 3), ns, group=C, zline=G,
+                kd, ki64, ki32 = F_.knn_groups(index, ilo, dev, B, N, cand.view(B, K * C, 3), ns, group=C, zline=G,
                                                cell=self.s, want64=keep_stages, want32=True)
-            elif index is not None:   # target clouds are batch items B..2B-1 of the index
-                kd, ki64, ki32 = F_.knn_indexed(index, B, dev, B, N, cand.view(B, K * C, 3), ns, chain=G,
+            elif index is not None:
+                kd, ki64, ki32 = F_.knn_indexed(index, ilo, dev, B, N, cand.view(B, K * C, 3), ns, chain=G,
                                                 want64=keep_stages, want32=True)
             elif F_.SpatialIndex.knn_indexable(N):
                 # clouds above the sampling kernels' index capacity: multi-CTA index of the targets for the KNN

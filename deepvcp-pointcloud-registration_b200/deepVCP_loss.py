@@ -18,10 +18,24 @@ def get_rigid_transform(x, y, quirks=QUIRKS_REFERENCE, weights=None):
 def svd_optimization(x, y_pred, R_true, t_true, quirks=QUIRKS_REFERENCE):
     """Reference :57-90: solve, drop the 20 % of points with the largest 1-NN
     distance to the ground-truth transform of x, solve again.
-    Returns R2, t2, x1, y_pred2 like the reference would for its inlier set; the
-    inlier tensors are not materialised here (None)."""
-    R2, t2, _, _ = F_.kabsch_refine(x, y_pred, R_true, t_true, quirks=quirks)
-    return R2, t2, None, None
+    Returns R2, t2, x1 [B,3,n'], y_pred2 [B,3,n'] like the reference: x1 = the inliers of x in the order of
+    its topk(largest=False, sorted=True) (:77,82), y_pred2 = R2 x1 + t2 (:88)."""
+    R2, t2, _, _, inl = F_.kabsch_refine(x, y_pred, R_true, t_true, quirks=quirks, want_inliers=True)
+    x1 = torch.gather(x.double(), 2, inl.unsqueeze(1).expand(-1, 3, -1))
+    y_pred2 = torch.matmul(R2, x1) + t2
+    return R2, t2, x1, y_pred2
+
+
+def deepVCP_loss(x, y_pred, R_true, t_true, alpha):
+    """Reference :105-121 (value only: the CUDA path has no backward). x, y_pred [B,N,3]; returns
+    (loss, R [B,3,3], t [B,3,1]): alpha * L1(y_true_inliers, y_pred2) + (1 - alpha) * |mean(y_pred2 - y_true_inliers)|."""
+    xx = x.permute(0, 2, 1).double()
+    yy = y_pred.permute(0, 2, 1).double()
+    R, t, x_inl, y_opt = svd_optimization(xx, yy, R_true, t_true)
+    y_true_inl = torch.matmul(R_true.double(), x_inl) + t_true.double().reshape(x.shape[0], 3, -1)
+    loss1 = torch.mean(torch.abs(y_true_inl - y_opt))
+    loss2 = torch.abs(torch.mean(y_opt - y_true_inl))
+    return alpha * loss1 + (1 - alpha) * loss2, R, t
 
 
 def pose_from_forward(src_keypts, tgt_vcp, R_true, t_true, quirks=QUIRKS_REFERENCE):

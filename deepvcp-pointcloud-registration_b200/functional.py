@@ -137,9 +137,17 @@ def fps_plain(xyz_pm, npoint, start):
 
 
 def square_distance(src_pm, dst_pm):
+    """float32 clouds -> float32; a float64 cloud on either side -> double (torch's promotion)."""
     require_cuda(src_pm, dst_pm)
     B, S, _ = src_pm.shape
     N = dst_pm.shape[1]
+    if src_pm.dtype == torch.float64 or dst_pm.dtype == torch.float64:
+        src_pm, dst_pm = src_pm.double(), dst_pm.double()
+        out = torch.empty(B, S, N, dtype=torch.float64, device=src_pm.device)
+        check(lib().dvcp_square_distance_f64(cloud_pm(src_pm), cloud_pm(dst_pm), B, S, N, ptr(out),
+                                             stream_ptr(src_pm.device)), "dvcp_square_distance_f64")
+        _count(1)
+        return out
     out = torch.empty(B, S, N, dtype=torch.float32, device=src_pm.device)
     check(lib().dvcp_square_distance(cloud_pm(src_pm), cloud_pm(dst_pm), B, S, N, ptr(out),
                                      stream_ptr(src_pm.device)), "dvcp_square_distance")
@@ -157,6 +165,13 @@ def ball_query(radius, nsample, xyz_pm, new_xyz_pm):
     B, N, _ = xyz_pm.shape
     S = new_xyz_pm.shape[1]
     out = torch.empty(B, S, nsample, dtype=torch.int64, device=xyz_pm.device)
+    if xyz_pm.dtype == torch.float64 or new_xyz_pm.dtype == torch.float64:
+        # double arithmetic, bound = the Python double radius**2 (pointnet2_utils.py:102)
+        xyz_pm, new_xyz_pm = xyz_pm.double(), new_xyz_pm.double()
+        check(lib().dvcp_ball_query_f64(cloud_pm(xyz_pm), cloud_pm(new_xyz_pm), B, N, S, float(radius) ** 2, nsample,
+                                        ptr(out), stream_ptr(xyz_pm.device)), "dvcp_ball_query_f64")
+        _count(1)
+        return out
     check(lib().dvcp_ball_query(cloud_pm(xyz_pm), cloud_pm(new_xyz_pm), B, N, S, radius2_f32(radius), nsample,
                                 ptr(out), stream_ptr(xyz_pm.device)), "dvcp_ball_query")
     _count(1)
@@ -209,6 +224,18 @@ def sa_layer(xyz_cloud, feats_cloud, D, centroid_idx32, B, N, S, radius, nsample
     return oxyz, out
 
 
+def sa_layer_f64(xyz_cloud, feats_cloud, D, centroid_idx32, B, N, S, radius, nsample, mlp: FoldedMlp, device,
+                 want_xyz=True):
+    """SA layer of float64 clouds (xyz and features clouds of doubles): features float32 [B,S,C], xyz float64."""
+    out = torch.empty(B, S, mlp.out_ch, dtype=torch.float32, device=device)
+    oxyz = torch.empty(B, S, 3, dtype=torch.float64, device=device) if want_xyz else None
+    check(lib().dvcp_sa_layer_f64(xyz_cloud, feats_cloud if D > 0 else NULL_CLOUD, D, ptr(centroid_idx32), B, N, S,
+                                  float(radius) ** 2, nsample, mlp.layers, mlp.n, ptr(out), ptr(oxyz),
+                                  stream_ptr(device)), "dvcp_sa_layer_f64")
+    _count(1)
+    return oxyz, out
+
+
 def sa_layer_all(xyz_cloud, feats_cloud, D, identity_idx32, B, N, radius, nsample, mlp: FoldedMlp, device, index):
     """SA features of every point in original order: [B,N,out_ch]."""
     out = torch.empty(B, N, mlp.out_ch, dtype=torch.float32, device=device)
@@ -257,12 +284,14 @@ def topk(scores, K):
 
 def keypoint_stage(src_pts, topk_idx, kp_start, src_feat, R_init, radius, nsample, dfe, quirks,
                    want_cat=False, want_picked=False, t_init=None):
+    """src_pts [B,C_in,N] float32 or float64 (the key-points come back in that dtype, like the reference's)."""
     require_cuda(src_pts, topk_idx, src_feat, R_init)
     B, C_in, N = src_pts.shape
     Kp = topk_idx.shape[1]
     S = src_feat.shape[1]
     dev = src_pts.device
-    src_pts = _f32c(src_pts)
+    f64 = src_pts.dtype == torch.float64
+    src_pts = src_pts.contiguous() if f64 else _f32c(src_pts)
     src_feat = _f32c(src_feat)
     R_init = R_init.to(torch.float64).contiguous()
     kp_start = _starts_to_device(kp_start, B, dev)
@@ -272,15 +301,16 @@ def keypoint_stage(src_pts, topk_idx, kp_start, src_feat, R_init, radius, nsampl
         if t_dev.shape[0] not in (1, B):
             raise RuntimeError("t_init must be [1,3] or [B,3]")
         t_stride = 3 if t_dev.shape[0] == B and B > 1 else 0
-    keypts = torch.empty(B, Kp, C_in, dtype=torch.float32, device=dev)
+    keypts = torch.empty(B, Kp, C_in, dtype=src_pts.dtype, device=dev)
     picked = torch.empty(B, Kp, nsample, dtype=torch.int64, device=dev) if want_picked else None
     cat = torch.empty(B, Kp, nsample, 35, dtype=torch.float32, device=dev) if want_cat else None
     sdfe = torch.empty(B, Kp, 32, dtype=torch.float32, device=dev)
     centres = torch.empty(B, Kp, 3, dtype=torch.float64, device=dev)
-    code = lib().dvcp_keypoint_stage(ptr(src_pts), C_in, B, N, ptr(topk_idx.contiguous()), Kp, ptr(kp_start),
-                                     ptr(src_feat), S, ptr(R_init), ptr(t_dev), t_stride, radius2_f32(radius),
-                                     nsample, dfe, quirks,
-                                     ptr(keypts), ptr(picked), ptr(cat), ptr(sdfe), ptr(centres), stream_ptr(dev))
+    fn = lib().dvcp_keypoint_stage_f64 if f64 else lib().dvcp_keypoint_stage
+    r2 = float(radius) ** 2 if f64 else radius2_f32(radius)
+    code = fn(ptr(src_pts), C_in, B, N, ptr(topk_idx.contiguous()), Kp, ptr(kp_start),
+              ptr(src_feat), S, ptr(R_init), ptr(t_dev), t_stride, r2, nsample, dfe, quirks,
+              ptr(keypts), ptr(picked), ptr(cat), ptr(sdfe), ptr(centres), stream_ptr(dev))
     check(code, "dvcp_keypoint_stage")
     _count(1)
     return keypts, picked, cat, sdfe, centres
@@ -459,7 +489,8 @@ def kabsch(x, y, quirks=_lib.QUIRKS_REFERENCE, weights=None):
     return R, t
 
 
-def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False, quirks=_lib.QUIRKS_REFERENCE):
+def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False, quirks=_lib.QUIRKS_REFERENCE,
+                  want_inliers=False):
     require_cuda(x, y_pred, R_true, t_true)
     B, _, n = x.shape
     dev = x.device
@@ -472,9 +503,12 @@ def kabsch_refine(x, y_pred, R_true, t_true, inlier_ratio=0.8, want_first=False,
     t2 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev)
     R1 = torch.empty(B, 3, 3, dtype=torch.float64, device=dev) if want_first else None
     t1 = torch.empty(B, 3, 1, dtype=torch.float64, device=dev) if want_first else None
+    inl = torch.empty(B, keep, dtype=torch.int64, device=dev) if want_inliers else None
     check(lib().dvcp_kabsch_refine(ptr(x), ptr(y_pred), ptr(R_true), ptr(t_true), B, n, keep, quirks, ptr(R2), ptr(t2),
-                                   ptr(R1), ptr(t1), stream_ptr(dev)), "dvcp_kabsch_refine")
+                                   ptr(R1), ptr(t1), ptr(inl), stream_ptr(dev)), "dvcp_kabsch_refine")
     _count(1)
+    if want_inliers:
+        return R2, t2, R1, t1, inl
     return R2, t2, R1, t1
 
 

@@ -12,19 +12,24 @@ from . import functional as F_
 from ._lib import cloud_cm, cloud_pm, require_cuda
 
 
-def _as_f32_cloud(xyz):
-    if xyz.dtype != torch.float32:
-        raise NotImplementedError("only float32 clouds are accelerated for this op (got %s)" % xyz.dtype)
+def _float_cloud(xyz):
+    if xyz.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("float32 or float64 cloud expected (got %s)" % xyz.dtype)
     return xyz
 
 
 def square_distance(src, dst):
-    """[B,N,3], [B,M,3] -> [B,N,M], expanded form, float32 (reference :19-40)."""
-    return F_.square_distance(_as_f32_cloud(src), _as_f32_cloud(dst))
+    """[B,N,3], [B,M,3] -> [B,N,M], expanded form (reference :19-40); float32 clouds give float32, a
+    float64 cloud on either side gives float64 like torch's promotion."""
+    return F_.square_distance(_float_cloud(src), _float_cloud(dst))
 
 
 def index_points(points, idx):
-    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,(K),C] (reference :43-60)."""
+    """points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,(K),C] (reference :43-60), dtype of `points`."""
+    if points.dtype == torch.float64:   # a plain gather: torch's own kernel (plumbing, no arithmetic)
+        B = points.shape[0]
+        flat = idx.reshape(B, -1, 1).expand(-1, -1, points.shape[-1])
+        return torch.gather(points, 1, flat).reshape(*idx.shape, points.shape[-1])
     return F_.index_points(points, idx)
 
 
@@ -49,7 +54,7 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     B, N, _ = xyz.shape
     if N < nsample:
         raise IndexError("query_ball_point needs N >= nsample (reference :106)")
-    return F_.ball_query(radius, nsample, _as_f32_cloud(xyz), _as_f32_cloud(new_xyz))
+    return F_.ball_query(radius, nsample, _float_cloud(xyz), _float_cloud(new_xyz))
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, returnidx=False, start=None):
@@ -104,12 +109,22 @@ class PointNetSetAbstraction(nn.Module):
         if self.training:
             raise RuntimeError("train-mode BatchNorm statistics are out of scope: call .eval()")
         require_cuda(xyz, points)
-        _as_f32_cloud(xyz)
+        _float_cloud(xyz)
         B, _, N = xyz.shape
         S = self.npoint
         dev = xyz.device
         if start is None:
             start = F_.draw_fps_start(B, N)
+        if xyz.dtype == torch.float64 or (points is not None and points.dtype == torch.float64):
+            # torch promotes the grouped tensor to double and casts right before the MLP (reference :128-132,198)
+            xyz64 = xyz.double()
+            D = 0 if points is None else points.shape[1]
+            pts64 = points.double() if points is not None else None
+            fps64, fps32 = F_.fps(cloud_cm(xyz64), dev, xyz64.dtype, B, N, S, start, want64=return_fps, want32=True)
+            new_xyz, feats = F_.sa_layer_f64(cloud_cm(xyz64), cloud_cm(pts64) if D else None, D, fps32, B, N, S,
+                                             self.radius, self.nsample, self.folded(), dev)
+            out = (new_xyz.to(xyz.dtype).permute(0, 2, 1), feats.permute(0, 2, 1))
+            return out + (fps32,) if return_fps else out
         index = F_.SpatialIndex(B, N, dev) if F_.SpatialIndex.indexable(N) else None
         _, fps32 = F_.fps(cloud_cm(xyz), dev, xyz.dtype, B, N, S, start, want64=return_fps, want32=True, index=index)
         D = 0 if points is None else points.shape[1]

@@ -37,10 +37,22 @@ def _random_pose(g: torch.Generator, max_angle: float = 2 * math.pi):
     return R, t
 
 
-def modelnet_pair(pair_id: int, n_points: int = 1024):
+def _cast(src64, tgt64, dtype):
+    """dtype "f32": what every benchmark uses; "f64": as ModelNet40Dataset.py:38,92 hands the clouds over
+    (float64 arrays); "mixed": as KITTIDataset.py:84,97 does (float32 scan, target = R @ src + t in float64)."""
+    if dtype == "f32":
+        return src64.float(), tgt64.float()
+    if dtype == "f64":
+        return src64, tgt64
+    if dtype == "mixed":
+        return src64.float(), tgt64
+    raise ValueError("dtype must be f32, f64 or mixed")
+
+
+def modelnet_pair(pair_id: int, n_points: int = 1024, dtype: str = "f32"):
     """One ModelNet40-shaped pair.
 
-    Returns ``src[6,N] f32, tgt[6,N] f32, R[3,3] f64, t[3] f64``.
+    Returns ``src[6,N], tgt[6,N] (float32 by default), R[3,3] f64, t[3] f64``.
     """
     g = torch.Generator().manual_seed(1234 + int(pair_id))
     d = torch.randn(n_points, 3, generator=g, dtype=torch.float64)
@@ -50,8 +62,7 @@ def modelnet_pair(pair_id: int, n_points: int = 1024):
     R, t = _random_pose(g)
     tgt_xyz = xyz @ R.T + t
     tgt_nrm = d @ R.T
-    src = torch.cat([xyz, d], dim=1).T.contiguous().float()
-    tgt = torch.cat([tgt_xyz, tgt_nrm], dim=1).T.contiguous().float()
+    src, tgt = _cast(torch.cat([xyz, d], dim=1).T.contiguous(), torch.cat([tgt_xyz, tgt_nrm], dim=1).T.contiguous(), dtype)
     return src, tgt, R, t
 
 
@@ -81,19 +92,22 @@ def _kitti_scan(g: torch.Generator, n_points: int) -> torch.Tensor:
     return torch.tensor(rows, dtype=torch.float64) / 10.0
 
 
-def kitti_pair(pair_id: int, n_points: int = 16384, max_angle: float = 2 * math.pi):
-    """One KITTI-shaped pair: ``src[3,N] f32, tgt[3,N] f32, R f64, t f64``."""
+def kitti_pair(pair_id: int, n_points: int = 16384, max_angle: float = 2 * math.pi, dtype: str = "f32"):
+    """One KITTI-shaped pair: ``src[3,N], tgt[3,N] (float32 by default), R f64, t f64``."""
     g = torch.Generator().manual_seed(4321 + int(pair_id))
     xyz = _kitti_scan(g, n_points)
     R, t = _random_pose(g, max_angle)
+    if dtype == "mixed":   # the loader transforms the float32 scan in float64 (KITTIDataset.py:84)
+        xyz = xyz.float().double()
     tgt_xyz = xyz @ R.T + t
-    return xyz.T.contiguous().float(), tgt_xyz.T.contiguous().float(), R, t
+    src, tgt = _cast(xyz.T.contiguous(), tgt_xyz.T.contiguous(), dtype)
+    return src, tgt, R, t
 
 
-def make_batch(kind: str, pair_ids, n_points: int):
-    """Stack pairs: ``src[B,C,N], tgt[B,C,N] f32, R[B,3,3] f64, t[B,3] f64``."""
+def make_batch(kind: str, pair_ids, n_points: int, dtype: str = "f32"):
+    """Stack pairs: ``src[B,C,N], tgt[B,C,N] (float32 unless dtype says otherwise), R[B,3,3] f64, t[B,3] f64``."""
     fn = {"modelnet": modelnet_pair, "kitti": kitti_pair}[kind]
-    items = [fn(i, n_points) for i in pair_ids]
+    items = [fn(i, n_points, dtype=dtype) for i in pair_ids]
     src = torch.stack([it[0] for it in items])
     tgt = torch.stack([it[1] for it in items])
     R = torch.stack([it[2] for it in items])

@@ -298,6 +298,30 @@ DVCP_API int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int layou
              int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
              int64_t workspace_bytes, int path, dvcp_stream_t stream);
 
+/* ---- float64 clouds -- what the reference's own loaders produce (ModelNet40Dataset.py:38,92: float64 clouds;
+ * KITTIDataset.py:84,97: float32 scan, float64 target). torch then evaluates these functions in double and casts
+ * to float right before the shared MLP (pointnet2_utils.py:198) / the embedding (deep_feat_embedding.py:29):
+ *   square_distance / query_ball_point   pointnet2_utils.py:35-40,100-102 in double (fma-chain dot, Python double
+ *                                        radius**2 as the bound)
+ *   sa_layer_f64                         sample_and_group + PointNetSetAbstraction with float64 xyz / features
+ *                                        (clouds of doubles; relative coordinates formed in double, then .float())
+ *   keypoint_stage_f64                   deepVCP.py:44-67,86-91 with a float64 source cloud: key-points, their
+ *                                        grouping and Get_Cat_Feat_Src in double; keypts out [B,Kp,C_in] double.
+ * dvcp_fps takes dtype 1 for float64 clouds. These entry points walk the whole cloud (exact, not tuned). */
+DVCP_API int dvcp_square_distance_f64(dvcp_cloud_t src, dvcp_cloud_t dst, int B, int S, int N, double *out,
+                             dvcp_stream_t stream);
+DVCP_API int dvcp_ball_query_f64(dvcp_cloud_t xyz, dvcp_cloud_t new_xyz, int B, int N, int S, double radius2,
+                        int nsample, int64_t *out, dvcp_stream_t stream);
+DVCP_API int dvcp_sa_layer_f64(dvcp_cloud_t xyz, dvcp_cloud_t feats, int D, const int32_t *centroid_idx, int B,
+                      int N, int S, double radius2, int nsample, const dvcp_mlp_layer_t *layers,
+                      int n_layers, float *out_feat, double *out_xyz, dvcp_stream_t stream);
+DVCP_API int dvcp_keypoint_stage_f64(const double *src_pts, int C_in, int B, int N, const int64_t *topk, int Kp,
+                            const int64_t *kp_start, const float *src_feat, int S, const double *R_init,
+                            const double *t_init, int64_t t_bstride, double radius2, int nsample,
+                            dvcp_dfe_params_t dfe, int quirks, double *keypts,
+                            int64_t *picked, float *src_cat, float *src_dfe, double *centres,
+                            dvcp_stream_t stream);
+
 /* ---- a17 get_rigid_transform(x, y)                   deepVCP_loss.py:13-44
  * x, y [B,3,n] (dtype 0 float32 / 1 float64); R [B,3,3], t [B,3] float64.
  * quirks & DVCP_QUIRK_NO_REFLECTION_FIX: R = V U^T as the reference computes it (Q10); clear: the
@@ -309,10 +333,12 @@ DVCP_API int dvcp_kabsch(const void *x, const void *y, int dtype, const double *
 /* ---- a18 svd_optimization(x, y_pred, R_true, t_true)  deepVCP_loss.py:57-90
  * x, y_pred [B,3,n] float64; R_true [B,3,3], t_true [B,3] float64; keep =
  * int(0.8 n). Outputs R2 [B,3,3], t2 [B,3] float64; R1/t1 (first solve) may be
- * null. n <= 1024. quirks: DVCP_QUIRK_NO_REFLECTION_FIX as in dvcp_kabsch (both solves). */
+ * null. n <= 1024. quirks: DVCP_QUIRK_NO_REFLECTION_FIX as in dvcp_kabsch (both solves). inliers (nullable)
+ * [B,keep] int64: the kept point indices in the order of the reference's topk(largest=False, sorted=True)
+ * (:77), from which the caller forms x1 and y_pred2 (:82-88). */
 DVCP_API int dvcp_kabsch_refine(const double *x, const double *y_pred, const double *R_true,
                        const double *t_true, int B, int n, int keep, int quirks, double *R2, double *t2,
-                       double *R1, double *t1, dvcp_stream_t stream);
+                       double *R1, double *t1, int64_t *inliers, dvcp_stream_t stream);
 
 /* train.py:110 -> deepVCP_loss.py:105-107,121: svd_optimization on the forward's own outputs. src_keypts,
  * tgt_vcp [B,n,3] float32 (cast to float64 like .double(), read in place: no permute / cast copies);

@@ -28,12 +28,15 @@ def lib():
         L.orc_fps_f64.argtypes = [vp, i64, i64, i64, vp]
         L.orc_square_distance_f32.argtypes = [vp, i64, vp, i64, vp]
         L.orc_ball_query_f32.argtypes = [vp, i64, vp, i64, f32, i64, vp]
+        L.orc_ball_query_f64.argtypes = [vp, i64, vp, i64, f64, i64, vp]
+        L.orc_square_distance_f64.argtypes = [vp, i64, vp, i64, vp]
         L.orc_knn_f32.argtypes = [vp, i64, vp, i64, i64, vp, vp]
         L.orc_candidates.argtypes = [vp, i64, f64, f64, i64, vp]
         L.orc_grid_size.argtypes = [f64, f64, f64]
         L.orc_grid_size.restype = i64
         for fn in (L.orc_fps_f32, L.orc_fps_f64, L.orc_square_distance_f32,
-                   L.orc_ball_query_f32, L.orc_knn_f32, L.orc_candidates):
+                   L.orc_ball_query_f32, L.orc_knn_f32, L.orc_candidates, L.orc_ball_query_f64,
+                   L.orc_square_distance_f64):
             fn.restype = None
         _lib = L
     return _lib
@@ -62,6 +65,12 @@ def fps(xyz: torch.Tensor, npoint: int, start) -> torch.Tensor:
 def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     B, S, _ = src.shape
     N = dst.shape[1]
+    if src.dtype == torch.float64 or dst.dtype == torch.float64:   # torch promotes: the matmul runs in double
+        a, d = _c(src, torch.float64), _c(dst, torch.float64)
+        out = torch.empty(B, S, N, dtype=torch.float64)
+        for b in range(B):
+            lib().orc_square_distance_f64(a[b].data_ptr(), S, d[b].data_ptr(), N, out[b].data_ptr())
+        return out
     a, d = _c(src, torch.float32), _c(dst, torch.float32)
     out = torch.empty(B, S, N, dtype=torch.float32)
     for b in range(B):
@@ -72,9 +81,15 @@ def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 def ball_query(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
+    out = torch.empty(B, S, nsample, dtype=torch.int64)
+    if xyz.dtype == torch.float64 or new_xyz.dtype == torch.float64:
+        x, q = _c(xyz, torch.float64), _c(new_xyz, torch.float64)
+        for b in range(B):
+            lib().orc_ball_query_f64(x[b].data_ptr(), N, q[b].data_ptr(), S, float(radius ** 2), nsample,
+                                     out[b].data_ptr())
+        return out
     x, q = _c(xyz, torch.float32), _c(new_xyz, torch.float32)
     r2 = float(np.float32(radius ** 2))
-    out = torch.empty(B, S, nsample, dtype=torch.int64)
     for b in range(B):
         lib().orc_ball_query_f32(x[b].data_ptr(), N, q[b].data_ptr(), S, r2, nsample, out[b].data_ptr())
     return out

@@ -40,9 +40,9 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
-def forward_case(name, kind, n_points, r, s, model_seed, rng_seed, pair_id=0, stride=16):
+def forward_case(name, kind, n_points, r, s, model_seed, rng_seed, pair_id=0, stride=16, dtype="f32"):
     use_normal = kind == "modelnet"
-    src, tgt, R, t = syn.make_batch(kind, [pair_id], n_points)
+    src, tgt, R, t = syn.make_batch(kind, [pair_id], n_points, dtype=dtype)
     model = rs.make_model(use_normal, n_points, seed=model_seed)
     m = rs.load()
     pu = m.pointnet2_utils
@@ -74,7 +74,7 @@ def forward_case(name, kind, n_points, r, s, model_seed, rng_seed, pair_id=0, st
         R1, t1 = m.deepVCP_loss.get_rigid_transform(x, y)
         R2, t2, x1, y2 = m.deepVCP_loss.svd_optimization(x, y, R, t.view(1, 3, 1))
     out = {
-        "kind": kind, "r": r, "s": s, "n_points": n_points,
+        "kind": kind, "r": r, "s": s, "n_points": n_points, "dtype": dtype, "pair_id": pair_id,
         "src": npy(src), "tgt": npy(tgt), "R": npy(R), "t": npy(t),
         "starts": np.array([int(fps_log[0][0, 0]), int(fps_log[1][0, 0]), int(fps_log[2][0, 0])]),
         "src_fps": npy(fps_log[0]).astype(np.int32), "kp_fps": npy(fps_log[1]).astype(np.int32),
@@ -90,7 +90,7 @@ def forward_case(name, kind, n_points, r, s, model_seed, rng_seed, pair_id=0, st
         "candidates": npy(rec["candidates"]),
         "src_dfe": npy(rec["src_dfe"]),
         "vcp": npy(vcp), "src_keypts": npy(kp),
-        "R1": npy(R1), "t1": npy(t1), "R2": npy(R2), "t2": npy(t2),
+        "R1": npy(R1), "t1": npy(t1), "R2": npy(R2), "t2": npy(t2), "x1": npy(x1), "y_pred2": npy(y2),
         "stride": stride,
     }
     # target-side tensors: strided sample over candidates (axis 2)
@@ -243,9 +243,21 @@ def primitives_case():
     print("primitives ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def dtype_cases():
+    """The dtypes the reference's own loaders produce: float64 clouds (ModelNet40Dataset.py:38,92) and a
+    float32 scan with a float64 target (KITTIDataset.py:84,97)."""
+    forward_case("fwd_modelnet_f64_n1024_g5", "modelnet", 1024, 0.8, 0.4, model_seed=5, rng_seed=21, pair_id=7,
+                 dtype="f64")
+    forward_case("fwd_kitti_mixed_n2048_g7", "kitti", 2048, syn.grid_radius(7), 0.4, model_seed=6, rng_seed=22,
+                 pair_id=4, stride=32, dtype="mixed")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "native":
         native_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dtypes":
+        dtype_cases()
         sys.exit(0)
     primitives_case()
     native_case()
@@ -253,3 +265,4 @@ if __name__ == "__main__":
     forward_case("fwd_modelnet_n512_g6", "modelnet", 512, 1.0, 0.4, model_seed=1, rng_seed=8, pair_id=3)
     forward_case("fwd_kitti_n2048_g7", "kitti", 2048, syn.grid_radius(7), 0.4, model_seed=2, rng_seed=9,
                  pair_id=1, stride=32)
+    dtype_cases()

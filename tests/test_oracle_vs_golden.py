@@ -8,7 +8,10 @@ from conftest import golden_state_dict, load_golden
 from oracle import native, stages
 
 T = torch.from_numpy
-FWD_CASES = ["fwd_modelnet_n1024_g5", "fwd_modelnet_n512_g6", "fwd_kitti_n2048_g7"]
+FWD_CASES = ["fwd_modelnet_n1024_g5", "fwd_modelnet_n512_g6", "fwd_kitti_n2048_g7",
+             # the dtypes the reference's own loaders produce: float64 clouds (ModelNet40Dataset.py:38,92) and a
+             # float32 scan with a float64 target (KITTIDataset.py:84,97)
+             "fwd_modelnet_f64_n1024_g5", "fwd_kitti_mixed_n2048_g7"]
 
 
 def assert_topk_equivalent(scores, a, b):
