@@ -151,7 +151,7 @@ def time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, steps, barrier=None):
     return e0.elapsed_time(e1), poses
 
 
-def extra_config(torch, dv, dev, kind, B, N, G, use_normal, steps, depth):
+def extra_config(torch, dv, dev, kind, B, N, G, use_normal, steps, depth, graphs=True):
     """One of the other BASELINE.json configurations, measured in the same run with the same method
     (streamed API, device time, rotating input copies larger than L2 together with the intermediates)."""
     r = dv.synthetic.grid_radius(G)
@@ -164,7 +164,8 @@ def extra_config(torch, dv, dev, kind, B, N, G, use_normal, steps, depth):
     d_src, d_tgt, d_R, d_t = src.to(dev), tgt.to(dev), R.to(dev), t.view(B, 3, 1).to(dev)
     n_rot = max(2, int(160e6 // (d_src.numel() * 8)) + 1)
     rot = [(d_src.clone(), d_tgt.clone()) for _ in range(min(n_rot, 64))]
-    pipe = dv.StreamedRegistration(model, depth=depth)
+    pipe = (dv.GraphedRegistration(model, B, src.shape[1], N, depth=depth) if graphs
+            else dv.StreamedRegistration(model, depth=depth))
     time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, 3 * depth + 2)      # warm-up: pipeline + allocator pools
     ms, _ = time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, steps)
     return {"pairs_per_gpu": B, "n_points": N, "grid": "%d^3" % G, "steps": steps,
@@ -277,7 +278,9 @@ def run_ours(args):
 
     # ---- timed region: K steps through the streamed API (batch i+1's sampling overlaps batch i's dense
     #      stages; --depth 1 = strictly one batch at a time), device time, clocks sampled ----
-    pipe = dv.StreamedRegistration(model, depth=args.depth)
+    # both halves of the step captured once into CUDA graphs and replayed (--no-graphs: eager launches)
+    pipe = (dv.GraphedRegistration(model, B, 3, N, depth=args.depth) if args.graphs
+            else dv.StreamedRegistration(model, depth=args.depth))
     # Between timed iterations nothing may stay L2-resident: every step reads its clouds from a different
     # copy, and the copies together (plus the ~0.4 GB of intermediates each step writes and reads) exceed
     # the 126 MB L2 several times. (A flush kernel between pipelined steps would itself be scheduled
@@ -291,13 +294,8 @@ def run_ours(args):
         sampler.wait_first()
         sampler.mark()
     launches0 = F_.LAUNCHES
-    pipe.timing = os.environ.get("DVCP_BENCH_TRACE") == "1"
-    pipe.trace = []
     ms_total, poses = time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, args.steps, barrier)
-    if pipe.timing:
-        sys.stderr.write("trace: " + " ".join("fe%d/m%d" % (i, i) for i, _ in enumerate(pipe.trace)) + "\n")
-        pipe.timing = False
-    launches = F_.LAUNCHES - launches0
+    launches = pipe.launches_per_batch * args.steps if args.graphs else F_.LAUNCHES - launches0
     # ---- sustained pass: the same loop for >= args.sustain seconds of device time (clocks settle) ----
     sustained = None
     if args.sustain > 0:
@@ -371,6 +369,7 @@ def run_ours(args):
                        "is L2-resident between iterations; the per-stage pass flushes L2 (256 MiB write) before "
                        "each step" % (n_rot, n_rot * (d_src.numel() + d_tgt.numel()) * 4 / 1e6),
                        "pipeline_depth": args.depth,
+                       "cuda_graphs": bool(args.graphs),
                        "pipeline": "StreamedRegistration: batches alternate between %d streams, so the sampling of "
                                    "batch i+1 overlaps the dense stages of batch i; every batch runs the complete "
                                    "forward + pose solve" % args.depth,
@@ -387,8 +386,8 @@ def run_ours(args):
         if world == 1 and not args.no_extra:
             # the other BASELINE.json configurations in the same run (configs[1] and one rank's share of configs[3])
             out["extra_configs"] = {
-                "M64": extra_config(torch, dv, dev, "modelnet", 64, 1024, 5, True, 20, args.depth),
-                "K256_per_gpu_32": extra_config(torch, dv, dev, "kitti", 32, 16384, 11, False, 5, args.depth),
+                "M64": extra_config(torch, dv, dev, "modelnet", 64, 1024, 5, True, 20, args.depth, args.graphs),
+                "K256_per_gpu_32": extra_config(torch, dv, dev, "kitti", 32, 16384, 11, False, 5, args.depth, args.graphs),
             }
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
@@ -472,6 +471,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=2, help="batches in flight (1 = one at a time)")
+    ap.add_argument("--no-graphs", dest="graphs", action="store_false",
+                    help="eager kernel launches instead of the captured CUDA graphs")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the extra sustained timed pass (0 = skip)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs (M64, K256 share) measurements")
     args = ap.parse_args()

@@ -19,7 +19,7 @@ from .deepVCP import DeepVCP                                           # noqa: F
 from .deepVCP_loss import deepVCP_loss, get_rigid_transform, pose_from_forward, svd_optimization  # noqa: F401
 from .get_cat_feat_src import Get_Cat_Feat_Src                         # noqa: F401
 from .get_cat_feat_tgt import Get_Cat_Feat_Tgt                         # noqa: F401
-from .pipeline import StreamedRegistration                             # noqa: F401
+from .pipeline import GraphedRegistration, StreamedRegistration        # noqa: F401
 from .knn_cuda import KNN                                              # noqa: F401
 from .pointnet2_utils import (PointNetSetAbstraction, farthest_point_sample, index_points,  # noqa: F401
                               query_ball_point, sample_and_group, square_distance)

@@ -95,3 +95,119 @@ class StreamedRegistration:
         self.pending = []
         self.done = []
         return out
+
+
+class GraphedRegistration:
+    """StreamedRegistration with the two halves of the forward captured ONCE into CUDA graphs and replayed.
+
+    One batch of a fixed shape (B, C_in, N, dtype float32) costs two graph launches instead of ~20 kernel
+    launches, a dozen allocator calls and as many ctypes transitions: the host leaves the critical path, which
+    is what the max-over-ranks time of a multi-GPU run is sensitive to (8 processes on shared cores). `slots`
+    sets of static buffers and graphs are used round-robin, so that batch k+1's feature half runs beside batch
+    k's match half exactly as in StreamedRegistration; results are identical to it (same kernels, same order).
+    The reference has no counterpart (train.py:105 calls the eager model once per pair)."""
+
+    def __init__(self, model, B, C_in, N, depth=2):
+        dev = model.cpg.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedRegistration needs the model on a CUDA device")
+        from . import functional as F_
+        self.model, self.dev, self.depth = model, dev, max(1, depth)
+        self.B, self.C_in, self.N = B, C_in, N
+        self.fe_stream = torch.cuda.Stream(device=dev)
+        self.match_stream = torch.cuda.Stream(device=dev) if self.depth > 1 else self.fe_stream
+        self.streams = [self.fe_stream, self.match_stream]
+        self.slots = []
+        self.pending = []
+        self.launches_per_batch = 0
+        K = model.K_topk
+        g = torch.Generator().manual_seed(0)
+        for _ in range(self.depth + 1 if self.depth > 1 else 1):
+            s = dict(src=torch.zeros(B, C_in, N, device=dev), tgt=torch.zeros(B, C_in, N, device=dev),
+                     Ri=torch.eye(3, dtype=torch.float64, device=dev).repeat(B, 1, 1),
+                     Rt=torch.eye(3, dtype=torch.float64, device=dev).repeat(B, 1, 1),
+                     tt=torch.zeros(B, 3, 1, dtype=torch.float64, device=dev),
+                     st=[torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3)],
+                     free=None)
+            # plausible contents for the warm-up / capture runs (the kernels must not see degenerate clouds)
+            s["src"].copy_(torch.rand(B, C_in, N, generator=g) * 20 - 10)
+            s["tgt"].copy_(torch.rand(B, C_in, N, generator=g) * 20 - 10)
+            self.slots.append(s)
+        for s in self.slots:
+            self._capture(s, F_)
+
+    def _run_fe(self, s):
+        return self.model.extract_features(s["src"], s["tgt"], (s["st"][0], s["st"][1], s["st"][2]))
+
+    def _run_match(self, s, fe):
+        kp, vcp = self.model.match(fe, s["Ri"])
+        R2, t2 = pose_from_forward(kp, vcp, s["Rt"], s["tt"], quirks=self.model.quirks)
+        return pack_poses(R2, t2)
+
+    def _capture(self, s, F_):
+        fs, ms = self.fe_stream, self.match_stream
+        cur = torch.cuda.current_stream(self.dev)
+        fs.wait_stream(cur)
+        with torch.cuda.stream(fs):           # eager warm-up: lazy initialisation must not happen under capture
+            for _ in range(2):
+                fe = self._run_fe(s)
+                self._run_match(s, fe)
+        fs.synchronize()
+        n0 = F_.LAUNCHES
+        s["g_fe"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(s["g_fe"], stream=fs):
+            s["fe"] = self._run_fe(s)
+        ms.wait_stream(fs)
+        s["g_match"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(s["g_match"], stream=ms):
+            s["poses"] = self._run_match(s, s["fe"])
+        self.launches_per_batch = F_.LAUNCHES - n0
+        torch.cuda.synchronize(self.dev)
+
+    def submit(self, src, tgt, R_init, R_true, t_true, starts, host_out=None):
+        """Enqueue one batch (shapes as given to the constructor; host or device tensors; starts = the three
+        FPS start index tensors [B]). Poses are copied into host_out (pinned [B,12] float64) if given."""
+        k = len(self.pending)
+        s = self.slots[k % len(self.slots)]
+        fs, ms = self.fe_stream, self.match_stream
+        cur = torch.cuda.current_stream(self.dev)
+        fs.wait_stream(cur)
+        with torch.cuda.stream(fs):
+            if s["free"] is not None:
+                fs.wait_event(s["free"])      # the slot's previous batch has left the match half
+            s["src"].copy_(src, non_blocking=True)
+            s["tgt"].copy_(tgt, non_blocking=True)
+            s["Ri"].copy_(R_init, non_blocking=True)
+            s["Rt"].copy_(R_true, non_blocking=True)
+            s["tt"].copy_(t_true.reshape(self.B, 3, 1), non_blocking=True)
+            for d, v in zip(s["st"], starts):
+                d.copy_(torch.as_tensor(v).reshape(-1), non_blocking=True)
+            for x in (src, tgt, R_init, R_true, t_true) + tuple(v for v in starts if torch.is_tensor(v)):
+                if x.is_cuda:
+                    x.record_stream(fs)       # the caller's tensor is read on this stream: keep its memory until then
+            if self.depth > 1 and k >= self.depth:
+                fs.wait_event(self.pending[k - self.depth][0])   # run ahead by at most `depth` batches
+            s["g_fe"].replay()
+            ev_fe = torch.cuda.Event()
+            ev_fe.record(fs)
+        with torch.cuda.stream(ms):
+            ms.wait_event(ev_fe)
+            s["g_match"].replay()
+            out = s["poses"]
+            if host_out is not None:
+                host_out.copy_(out, non_blocking=True)
+            else:
+                out = out.clone()            # the static output buffer is overwritten by the slot's next batch
+            ev = torch.cuda.Event()
+            ev.record(ms)
+        s["free"] = ev
+        self.pending.append((ev, out if host_out is None else host_out))
+        return k
+
+    def collect(self):
+        out = []
+        for ev, poses in self.pending:
+            ev.synchronize()
+            out.append(poses)
+        self.pending = []
+        return out

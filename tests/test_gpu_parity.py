@@ -740,6 +740,36 @@ def test_streamed_registration_equals_one_batch_at_a_time(dv, synthetic):
         assert torch.equal(a.cpu(), b) and torch.equal(h, b)
 
 
+def test_graphed_registration_equals_streamed(dv, synthetic):
+    """The forward + pose solve captured into CUDA graphs (GraphedRegistration) and replayed for a stream of
+    different batches gives bit-identical poses to the eager streamed path, in submission order."""
+    N, B = 4096, 2
+    torch.manual_seed(5)
+    model = dv.DeepVCP(use_normal=False, npoint=N, r=1.2000000000000002, s=0.4).to(DEV).eval()
+    batches = []
+    for k in range(5):
+        src, tgt, R, t = synthetic.make_batch("kitti", [2 * k, 2 * k + 1], N)
+        starts = (torch.tensor([k, k + 1]), torch.tensor([k + 2, k + 3]), torch.tensor([k + 4, k + 5]))
+        batches.append((src, tgt, R, t.view(B, 3, 1), starts))
+    eager = dv.StreamedRegistration(model, depth=2)
+    for src, tgt, R, t, starts in batches:
+        eager.submit(src.to(DEV), tgt.to(DEV), R.to(DEV), R.to(DEV), t.to(DEV), starts=starts)
+    ref = [p.cpu() for p in eager.collect()]
+    for depth in (2, 1):
+        gr = dv.GraphedRegistration(model, B, 3, N, depth=depth)
+        assert gr.launches_per_batch >= 10
+        host = [torch.empty(B, 12, dtype=torch.float64).pin_memory() for _ in batches]
+        for i, (src, tgt, R, t, starts) in enumerate(batches):
+            if i % 2:    # device inputs, device outputs
+                gr.submit(src.to(DEV), tgt.to(DEV), R.to(DEV), R.to(DEV), t.to(DEV), starts)
+            else:        # pinned host inputs, pinned host outputs
+                gr.submit(src.pin_memory(), tgt.pin_memory(), R.pin_memory(), R.pin_memory(), t.pin_memory(), starts,
+                          host_out=host[i])
+        out = gr.collect()
+        for i, p in enumerate(out):
+            assert torch.equal(p.cpu(), ref[i]), "batch %d differs (depth %d)" % (i, depth)
+
+
 def test_reference_native_shape_with_normals_vs_oracle(dv, synthetic):
     """The reference's own operating point (deepVCP.py:76-77, deep_feat_extraction.py:10): N = 10000
     points WITH normals, r = 1.0, s = 0.4 (6^3 candidates). Exercises the overlapped feature half
