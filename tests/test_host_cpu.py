@@ -148,3 +148,20 @@ def test_kitti_downsample_indices_follow_the_reference_draw(dv):
     assert np.array_equal(dv.KITTIDataset.downsample_indices(500, 10000), np.arange(500))
     with pytest.raises(RuntimeError):
         dv.KITTIDataset.ingest([np.zeros((10, 4), np.float32)], None, device="cpu")
+
+
+def test_registration_error_metrics_follow_train_py(pkg):
+    """train.py:113-120: Euler-xyz (degrees) L2 rotation error via scipy, PairwiseDistance translation error."""
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(1)
+    ang = torch.rand(4, 3, generator=g, dtype=torch.float64) * 6.0 - 3.0
+    Rp = torch.from_numpy(Rotation.from_euler("xyz", ang.numpy()).as_matrix())
+    Rg = torch.from_numpy(Rotation.from_euler("xyz", (ang + 0.01).numpy()).as_matrix())
+    tp, tg = torch.randn(4, 3, 1, generator=g, dtype=torch.float64), torch.randn(4, 3, 1, generator=g, dtype=torch.float64)
+    rot, tr = pkg.metrics.registration_errors(Rp, tp, Rg, tg)
+    for b in range(4):
+        a = torch.tensor(Rotation.from_matrix(Rp[b].numpy()).as_euler("xyz", degrees=True)).reshape(1, 3)
+        c = torch.tensor(Rotation.from_matrix(Rg[b].numpy()).as_euler("xyz", degrees=True)).reshape(1, 3)
+        pd = torch.nn.PairwiseDistance(p=2)
+        assert abs(float(rot[b]) - float((a - c).norm())) < 1e-9
+        assert abs(float(tr[b]) - float(pd(tp[b].reshape(1, 3), tg[b].reshape(1, 3)))) < 1e-9
