@@ -919,41 +919,96 @@ __device__ __forceinline__ unsigned ordered_key(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// Radix select instead of K block-wide argmax rounds: the K-th largest composite key
+// (ordered score bits << 32 | ~index) is found byte by byte from the top (per-warp histograms in shared
+// memory, at most 8 passes, usually 3: the walk stops as soon as the keys under the chosen prefix are exactly
+// the ones still wanted); the K keys at or above it are collected and ranked among themselves.
+constexpr int TK_WARPS = 32;
+
+__global__ void __launch_bounds__(TK_WARPS * 32, 1)
 topk_kernel(const float *__restrict__ scores, int S, int K, int64_t *__restrict__ out) {
-    extern __shared__ unsigned skey[];   // S keys; 0 = taken
-    __shared__ unsigned s_hi[2][32], s_lo[2][32];
+    extern __shared__ unsigned skey[];   // S ordered keys
+    __shared__ unsigned s_hist[TK_WARPS][256];
+    __shared__ unsigned s_tot[256];
+    __shared__ unsigned long long s_sel[1024];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_krem, s_done, s_nsel;
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int n = tid; n < S; n += blockDim.x) {
         const float v = scores[(int64_t)b * S + n];
-        skey[n] = (v != v) ? 1u : max(ordered_key(v), 1u);   // NaN last; 0 reserved
+        skey[n] = (v != v) ? 1u : max(ordered_key(v), 1u);   // NaN last
+    }
+    if (tid == 0) {
+        s_prefix = 0ull;
+        s_krem = K;
+        s_done = 0;
+        s_nsel = 0;
     }
     __syncthreads();
-    for (int i = 0; i < K; ++i) {
-        unsigned hi = 0u, lo = 0u;
+    auto composite = [&](int n) { return ((unsigned long long)skey[n] << 32) | (0xffffffffu - (unsigned)n); };
+    int pass_byte = 7;
+    for (; pass_byte >= 0; --pass_byte) {
+        for (int i = lane; i < 256; i += 32) s_hist[warp][i] = 0u;
+        __syncwarp();
+        const unsigned long long prefix = s_prefix;
+        const int sh = 8 * (pass_byte + 1);
         for (int n = tid; n < S; n += blockDim.x) {
-            const unsigned k = skey[n];
-            const unsigned l = 0xffffffffu - (unsigned)n;
-            if (k > hi || (k == hi && l > lo)) {
-                hi = k;
-                lo = l;
+            const unsigned long long ck = composite(n);
+            if (pass_byte == 7 || (ck >> sh) == prefix) atomicAdd(&s_hist[warp][(unsigned)(ck >> (8 * pass_byte)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned t = 0;
+#pragma unroll 8
+            for (int w = 0; w < TK_WARPS; ++w) t += s_hist[w][tid];
+            s_tot[tid] = t;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns digits 8 l .. 8 l + 7; suffix counts from the top
+            unsigned c[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = s_tot[8 * lane + j];
+                mine += c[j];
+            }
+            unsigned above = 0;   // keys in the lanes above mine (plain suffix sum over 32 lanes)
+            for (int l = 31; l > 0; --l) {
+                const unsigned t = __shfl_sync(0xffffffffu, mine, l);
+                if (lane < l) above += t;
+            }
+            const unsigned krem = (unsigned)s_krem;
+            unsigned gt = above;   // keys with a larger digit than the one examined
+#pragma unroll
+            for (int j = 7; j >= 0; --j) {
+                if (gt < krem && krem <= gt + c[j]) {   // the K-th key has this digit (exactly one lane / digit hits)
+                    s_prefix = (prefix << 8) | (unsigned)(8 * lane + j);
+                    s_krem = (int)(krem - gt);
+                    s_done = (c[j] == krem - gt);       // every key under the new prefix is wanted
+                }
+                gt += c[j];
             }
         }
-        warp_max_pair(hi, lo);
-        if (lane == 0) {
-            s_hi[i & 1][warp] = hi;
-            s_lo[i & 1][warp] = lo;
-        }
         __syncthreads();
-        hi = s_hi[i & 1][lane];
-        lo = s_lo[i & 1][lane];
-        warp_max_pair(hi, lo);
-        const unsigned win = 0xffffffffu - lo;
-        if (tid == 0) {
-            out[(int64_t)b * K + i] = win;
-            skey[win] = 0u;
+        if (s_done) break;
+    }
+    // threshold = the smallest composite with the chosen prefix; exactly K keys are >= it
+    const int low = pass_byte < 0 ? 0 : 8 * pass_byte;
+    const unsigned long long T = s_prefix << low;
+    for (int n = tid; n < S; n += blockDim.x) {
+        const unsigned long long ck = composite(n);
+        if (ck >= T) {
+            const int at = atomicAdd(&s_nsel, 1);
+            if (at < 1024) s_sel[at] = ck;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    const int nsel = min(s_nsel, K);
+    if (tid < nsel) {
+        const unsigned long long mine = s_sel[tid];
+        int r = 0;
+        for (int j = 0; j < nsel; ++j) r += s_sel[j] > mine;
+        out[(int64_t)b * K + r] = (int64_t)(0xffffffffu - (unsigned)(mine & 0xffffffffu));
     }
 }
 
@@ -1303,9 +1358,9 @@ extern "C" int dvcp_weighting_scores(const float *X, int B, int S, const float *
 extern "C" int dvcp_topk(const float *scores, int B, int S, int K, int64_t *topk, dvcp_stream_t stream) {
     if (!scores || !topk || B <= 0 || S <= 0 || K <= 0 || K > S) return DVCP_E_ARG;
     const size_t smem = (size_t)S * sizeof(unsigned);
-    if (smem > 200 * 1024) return DVCP_E_UNSUPPORTED;
+    if (smem > 160 * 1024 || K > 1024) return DVCP_E_UNSUPPORTED;
     DVCP_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(scores, S, K, topk);
+    topk_kernel<<<B, TK_WARPS * 32, smem, (cudaStream_t)stream>>>(scores, S, K, topk);
     DVCP_CHECK_LAUNCH();
     return 0;
 }

@@ -56,8 +56,12 @@ keypoint_stage_kernel(const T *__restrict__ src_pts, int C_in, int N, const int6
     __shared__ T s_x[KP_MAX], s_y[KP_MAX], s_z[KP_MAX], s_pp[KP_MAX];
     __shared__ int s_fps[KP_MAX];
     __shared__ int s_pick[KP_MAX][32];
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // grid = (KP_SPLIT, B): every CTA of a pair repeats the cheap serial part (gather, FPS and ball query among
+    // the K key-points) and takes every KP_SPLIT-th key-point row of the embedding; CTA 0 writes the shared outputs
+    const int b = blockIdx.y, part = blockIdx.x, nparts = gridDim.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = KP_THREADS / 32;
+    const bool lead = part == 0;
     dfe_stage_weights(P, s_w);
     const T *pts = src_pts + (int64_t)b * C_in * N;
     const int64_t *tk = topk + (int64_t)b * Kp;
@@ -74,7 +78,7 @@ keypoint_stage_kernel(const T *__restrict__ src_pts, int C_in, int N, const int6
         }
         const T v = __ldg(pts + (int64_t)c * N + tk[k]);
         s_kp[f] = v;
-        if (keypts) keypts[(int64_t)b * Kp * C_in + f] = v;
+        if (keypts && lead) keypts[(int64_t)b * Kp * C_in + f] = v;
     }
     __syncthreads();
     for (int k = tid; k < Kp; k += KP_THREADS) {
@@ -83,7 +87,7 @@ keypoint_stage_kernel(const T *__restrict__ src_pts, int C_in, int N, const int6
         s_y[k] = y;
         s_z[k] = z;
         s_pp[k] = A::sq3(x, y, z);
-        if (centres) {
+        if (centres && lead) {
             const double *R = R_init + (int64_t)b * 9;
             double *o = centres + ((int64_t)b * Kp + k) * 3;
 #pragma unroll
@@ -149,13 +153,13 @@ keypoint_stage_kernel(const T *__restrict__ src_pts, int C_in, int N, const int6
         __syncwarp();
         if (lane >= cnt && lane < nsample) s_pick[i][lane] = first;
         __syncwarp();
-        if (picked && lane < nsample) picked[((int64_t)b * Kp + i) * nsample + lane] = s_pick[i][lane];
+        if (picked && lead && lane < nsample) picked[((int64_t)b * Kp + i) * nsample + lane] = s_pick[i][lane];
     }
     __syncthreads();
 
     // 3-5. per key-point row i: lanes over the nsample (= 32) group members
     const DfeSmem W(s_w);
-    for (int i = warp; i < Kp; i += nwarps) {
+    for (int i = part * nwarps + warp; i < Kp; i += nparts * nwarps) {
         const int c = s_fps[i];
         const int pj = s_pick[i][lane];
         // grouped_xyz_norm (pointnet2_utils.py:128): member - permuted key-point
@@ -208,8 +212,9 @@ static int keypoint_stage_launch(const T *src_pts, int C_in, int B, int N, const
     if (!src_pts || !topk || !kp_start || !src_feat || B <= 0 || N <= 0 || S <= 0) return DVCP_E_ARG;
     if (centres && !R_init) return DVCP_E_ARG;
     if (!dfe.W1 || !dfe.b1 || !dfe.W2 || !dfe.b2 || !dfe.W3 || !dfe.b3) return DVCP_E_ARG;
-    if (C_in < 3 || C_in > KP_MAXC || Kp < 1 || Kp > KP_MAX || nsample != 32 || Kp > S) return DVCP_E_UNSUPPORTED;
-    keypoint_stage_kernel<T><<<B, KP_THREADS, 0, (cudaStream_t)stream>>>(
+    if (C_in < 3 || C_in > KP_MAXC || Kp < 1 || Kp > KP_MAX || nsample != 32 || Kp > S || B > 65535) return DVCP_E_UNSUPPORTED;
+    const int split = (Kp + KP_THREADS / 32 - 1) / (KP_THREADS / 32);   // one key-point row per warp
+    keypoint_stage_kernel<T><<<dim3(split, B), KP_THREADS, 0, (cudaStream_t)stream>>>(
         src_pts, C_in, N, topk, Kp, kp_start, src_feat, S, R_init, (quirks & DVCP_QUIRK_IGNORE_T_INIT) ? nullptr : t_init,
         t_bstride, radius2, nsample, dfe, quirks & 1, keypts, picked, src_cat, src_dfe, centres);
     DVCP_CHECK_LAUNCH();
