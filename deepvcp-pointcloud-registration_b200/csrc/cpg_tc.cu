@@ -114,7 +114,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
     // shared memory: A planes [hi k0 | hi k1 | lo k0 | lo k1][R rows][16 B]; B image of the current octet; W2; W3
     float4 *sA = reinterpret_cast<float4 *>(ct_smem);
     float *sB = reinterpret_cast<float *>(ct_smem + (size_t)4 * R * 16);
-    float *W2 = sB + CT_B_FLOATS_Q;    // [27][16][4]
+    float *W2 = sB + 2 * CT_B_FLOATS_Q;   // [27][16][4] (two B buffers before it)
     float *W3 = W2 + 27 * 16 * 4;      // [27][4] (padded to 112)
     // after conv1 the A region is dead and holds conv1 out [16][Cp], conv2 out [4][Cp], logits [Cp]
     float *A1 = reinterpret_cast<float *>(ct_smem), *O2 = A1 + 16 * Cp, *LG = O2 + 4 * Cp;
@@ -150,15 +150,37 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         for (int i = tid; i < 4 * R; i += CT_THREADS) sA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < 32) s_src[tid] = __ldg(src + m * 32 + tid);
         __syncthreads();
-        for (int q = 0; q < 4; ++q) {
-            // ---- weights of this channel octet (pre-split image, 27 KB) ----
+        // software pipeline over the four channel octets: the weight image of octet q+1 (cp.async into the other
+        // B buffer) and its target values (registers) are fetched while the tensor core works on octet q
+        constexpr int CT_VPT = 3;   // voxels per thread: ceil(11^3 / 512)
+        float4 pt0[CT_VPT], pt1[CT_VPT];
+        auto fetch_tgt = [&](int q) {
+#pragma unroll
+            for (int u = 0; u < CT_VPT; ++u) {
+                const int c = tid + u * CT_THREADS;
+                if (c < C) {
+                    pt0[u] = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q));
+                    pt1[u] = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q + 4));
+                }
+            }
+        };
+        auto fetch_b = [&](int q) {
             const float4 *bi = reinterpret_cast<const float4 *>(bimage + (size_t)q * CT_B_FLOATS_Q);
-            for (int i = tid; i < CT_B_FLOATS_Q / 4; i += CT_THREADS) reinterpret_cast<float4 *>(sB)[i] = __ldg(bi + i);
+            const uint32_t dst = ct_smem_u32(sB) + (uint32_t)(q & 1) * (CT_B_FLOATS_Q * 4);
+            for (int i = tid; i < CT_B_FLOATS_Q / 4; i += CT_THREADS)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(bi + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        fetch_b(0);
+        fetch_tgt(0);
+        for (int q = 0; q < 4; ++q) {
             // ---- cost volume of channels 8q .. 8q+7: cost[c', f'] = (src[f'] - flat[c' * 32 + f'])^2 ----
             const float4 s0 = *reinterpret_cast<const float4 *>(s_src + 8 * q), s1 = *reinterpret_cast<const float4 *>(s_src + 8 * q + 4);
-            for (int c = tid; c < C; c += CT_THREADS) {
-                const float4 t0 = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q));
-                const float4 t1 = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q + 4));
+#pragma unroll
+            for (int u = 0; u < CT_VPT; ++u) {
+                const int c = tid + u * CT_THREADS;
+                if (c >= C) continue;
+                const float4 t0 = pt0[u], t1 = pt1[u];
                 const int z = c % G, y = (c / G) % G, x = c / (G * G);
                 const int r = ((x + 1) * Gp + (y + 1)) * Gp + (z + 1);
                 float4 v0, v1, h0, h1;
@@ -172,6 +194,11 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                 sA[R + r] = h1;
                 sA[2 * R + r] = make_float4(v0.x - h0.x, v0.y - h0.y, v0.z - h0.z, v0.w - h0.w);
                 sA[3 * R + r] = make_float4(v1.x - h1.x, v1.y - h1.y, v1.z - h1.z, v1.w - h1.w);
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");   // this octet's weight image has landed
+            if (q < 3) {
+                fetch_b(q + 1);     // the other B buffer: its last readers (octet q-1's MMAs) were waited for
+                fetch_tgt(q + 1);
             }
             // operands were written with ordinary stores: make them visible to the tensor core's (async) proxy
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -188,7 +215,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                     const uint32_t d = tmem_base + (uint32_t)tile * 32u;   // columns 0..15: Vh Wh + Vl Wh, 16..31: Vh Wl
                     const uint32_t row0 = (uint32_t)(m_lo + tile * 128);
                     const uint64_t a0 = ct_desc(a_base + row0 * 16u, plane, 128u);
-                    const uint64_t w0 = ct_desc(b_base, 512u, 128u);
+                    const uint64_t w0 = ct_desc(b_base + (uint32_t)(q & 1) * (CT_B_FLOATS_Q * 4), 512u, 128u);
 #pragma unroll
                     for (int tap = 0; tap < 27; ++tap) {
                         const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;
@@ -242,15 +269,16 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
         __syncthreads();
-        // ---- conv2 16 -> 4: thread = (line (x, y), group of 4 z), packed FFMA2 ----
+        // ---- conv2 16 -> 4: thread = (line (x, y), group of 3 z) -- 484 of the 512 threads at G = 11 --, packed FFMA2 ----
         {
-            const int NG = (G + 3) >> 2, items = G * G * NG;
-            if (tid < items) {
-                const int line = tid / NG, zg = tid - line * NG;
-                const int x = line / G, y = line - x * G, z0 = zg * 4;
-                float2 a2[4][2];
+            constexpr int ZV = 3;
+            const int NG = (G + ZV - 1) / ZV, items = G * G * NG;
+            for (int it = tid; it < items; it += CT_THREADS) {
+                const int line = it / NG, zg = it - line * NG;
+                const int x = line / G, y = line - x * G, z0 = zg * ZV;
+                float2 a2[ZV][2];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
+                for (int v = 0; v < ZV; ++v) {
                     a2[v][0] = make_float2(__ldg(p.b2), __ldg(p.b2 + 1));
                     a2[v][1] = make_float2(__ldg(p.b2 + 2), __ldg(p.b2 + 3));
                 }
@@ -264,9 +292,9 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                         const float *col = A1 + (xx * G + yy) * G + z0 - 1;
 #pragma unroll 4
                         for (int ci = 0; ci < 16; ++ci) {
-                            float in[6];
+                            float in[ZV + 2];
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) {
+                            for (int k = 0; k < ZV + 2; ++k) {
                                 const int z = z0 - 1 + k;
                                 in[k] = (z >= 0 && z < G) ? col[ci * Cp + k] : 0.f;
                             }
@@ -274,7 +302,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                             for (int dz = 0; dz < 3; ++dz) {
                                 const float4 w = *reinterpret_cast<const float4 *>(W2 + ((tap0 + dz) * 16 + ci) * 4);
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) {
+                                for (int v = 0; v < ZV; ++v) {
                                     const float2 x2 = make_float2(in[v + dz], in[v + dz]);
                                     a2[v][0] = __ffma2_rn(make_float2(w.x, w.y), x2, a2[v][0]);
                                     a2[v][1] = __ffma2_rn(make_float2(w.z, w.w), x2, a2[v][1]);
@@ -285,7 +313,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
                 }
                 const int c0 = (x * G + y) * G + z0;
 #pragma unroll
-                for (int v = 0; v < 4; ++v)
+                for (int v = 0; v < ZV; ++v)
                     if (z0 + v < G) {
 #pragma unroll
                         for (int o = 0; o < 2; ++o) {
@@ -378,7 +406,7 @@ int cpg_tc_launch(const float *src_dfe, const float *tgt_dfe, const float *cand,
     cpg_tc_prepare_kernel<<<(CT_B_FLOATS + 255) / 256, 256, 0, st>>>(p.w1, image);
     DVCP_CHECK_LAUNCH();
     const int R = ct_rows(G);
-    const int smem = 4 * R * 16 + (CT_B_FLOATS_Q + 27 * 16 * 4 + 112) * (int)sizeof(float);
+    const int smem = 4 * R * 16 + (2 * CT_B_FLOATS_Q + 27 * 16 * 4 + 112) * (int)sizeof(float);
     DVCP_CUDA(cudaFuncSetAttribute(cpg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int64_t grid = M < DVCP_NUM_SMS ? M : DVCP_NUM_SMS;
     cpg_tc_kernel<<<(unsigned)grid, CT_THREADS, smem, st>>>(src_dfe, tgt_dfe, cand, M, G, R, image, p, vcp, logits);

@@ -116,6 +116,7 @@ class GraphedRegistration:
         self.B, self.C_in, self.N = B, C_in, N
         self.fe_stream = torch.cuda.Stream(device=dev)
         self.match_stream = torch.cuda.Stream(device=dev) if self.depth > 1 else self.fe_stream
+        self.copy_stream = torch.cuda.Stream(device=dev)   # input copies run ahead of the (in-order) feature stream
         self.streams = [self.fe_stream, self.match_stream]
         self.slots = []
         self.pending = []
@@ -128,6 +129,7 @@ class GraphedRegistration:
                      Rt=torch.eye(3, dtype=torch.float64, device=dev).repeat(B, 1, 1),
                      tt=torch.zeros(B, 3, 1, dtype=torch.float64, device=dev),
                      st=[torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(3)],
+                     st_pin=torch.zeros(3, B, dtype=torch.int64).pin_memory(), st_ev=None,
                      free=None)
             # plausible contents for the warm-up / capture runs (the kernels must not see degenerate clouds)
             s["src"].copy_(torch.rand(B, C_in, N, generator=g) * 20 - 10)
@@ -169,22 +171,38 @@ class GraphedRegistration:
         FPS start index tensors [B]). Poses are copied into host_out (pinned [B,12] float64) if given."""
         k = len(self.pending)
         s = self.slots[k % len(self.slots)]
-        fs, ms = self.fe_stream, self.match_stream
+        fs, ms, cs = self.fe_stream, self.match_stream, self.copy_stream
         cur = torch.cuda.current_stream(self.dev)
-        fs.wait_stream(cur)
-        with torch.cuda.stream(fs):
+        cs.wait_stream(cur)
+        # The inputs go into the slot's static buffers on their OWN stream: queued behind the previous batch's
+        # feature half they would start ~0.2 ms late, the match half of the batch before would take the SMs first
+        # and the sampling clusters would have to wait for them (measured: 4.5 -> 5.3 ms per step).
+        with torch.cuda.stream(cs):
             if s["free"] is not None:
-                fs.wait_event(s["free"])      # the slot's previous batch has left the match half
+                cs.wait_event(s["free"])      # the slot's previous batch has left the match half
             s["src"].copy_(src, non_blocking=True)
             s["tgt"].copy_(tgt, non_blocking=True)
             s["Ri"].copy_(R_init, non_blocking=True)
             s["Rt"].copy_(R_true, non_blocking=True)
             s["tt"].copy_(t_true.reshape(self.B, 3, 1), non_blocking=True)
-            for d, v in zip(s["st"], starts):
-                d.copy_(torch.as_tensor(v).reshape(-1), non_blocking=True)
+            # FPS starts usually arrive as pageable host tensors: a copy from pageable memory would block the host
+            # until the stream gets there (i.e. until the slot is free) -- stage them through the slot's pinned row
+            if s["st_ev"] is not None:
+                s["st_ev"].synchronize()      # the previous copy out of the pinned row (three batches ago) is done
+            for j, (d, v) in enumerate(zip(s["st"], starts)):
+                v = torch.as_tensor(v).reshape(-1)
+                if v.is_cuda:
+                    d.copy_(v, non_blocking=True)
+                else:
+                    s["st_pin"][j].copy_(v)
+                    d.copy_(s["st_pin"][j], non_blocking=True)
+            s["st_ev"] = torch.cuda.Event()
+            s["st_ev"].record(cs)
             for x in (src, tgt, R_init, R_true, t_true) + tuple(v for v in starts if torch.is_tensor(v)):
                 if x.is_cuda:
-                    x.record_stream(fs)       # the caller's tensor is read on this stream: keep its memory until then
+                    x.record_stream(cs)       # the caller's tensor is read on this stream: keep its memory until then
+        with torch.cuda.stream(fs):
+            fs.wait_event(s["st_ev"])
             if self.depth > 1 and k >= self.depth:
                 fs.wait_event(self.pending[k - self.depth][0])   # run ahead by at most `depth` batches
             s["g_fe"].replay()

@@ -20,10 +20,17 @@ def main():
             continue
         rd = float(r[col["dram__bytes_read.sum"]]) * scale[unit["dram__bytes_read.sum"]]
         wr = float(r[col["dram__bytes_write.sum"]]) * scale[unit["dram__bytes_write.sum"]]
-        k = out.setdefault(name, {"dram_bytes": 0.0, "launches": 0, "time_ms": 0.0})
+        k = out.setdefault(name, {"dram_bytes": 0.0, "launches": 0, "time_ms": 0.0, "warp_instructions": 0.0,
+                                  "issue_active_pct": 0.0, "tensor_pipe_active_pct": 0.0})
         k["dram_bytes"] += rd + wr
         k["launches"] += 1
         k["time_ms"] += float(r[col["gpu__time_duration.sum"]])
+        if "smsp__inst_executed.sum" in col:
+            k["warp_instructions"] += float(r[col["smsp__inst_executed.sum"]])
+        if "smsp__issue_active.avg.pct_of_peak_sustained_active" in col:
+            k["issue_active_pct"] = float(r[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]])
+        if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in col:
+            k["tensor_pipe_active_pct"] = float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])
     print(json.dumps({"source": "%s (ncu --set full --clock-control none, one K8 forward + pose solve, B=8)" % path,
                       "kernels": out}, indent=1))
 
