@@ -552,32 +552,525 @@ knn_deferred_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, i
     }
 }
 
+// =====================================================================================================
+// Two-kernel form (the default): the pools live in GLOBAL memory (L2 / L1 resident: ~1 K points per group).
+//   knn_pool_build_kernel   one CTA per group: exact probes (centre, then the 8 corners bounded through the
+//                           centre: d_K is 1-Lipschitz), 26-plane pool shape, counting sort of the pool points by
+//                           (x, y) cell into the group's slice of the workspace, per-group meta data;
+//   knn_pool_query_kernel   like knn_indexed_kernel: 4-warp CTAs, one warp per CHAIN of z-lines, but the
+//                           candidates of a query come from the cells of its group's pool within sqrt(thr)
+//                           (runs of consecutive pool entries, float4 loads) instead of a walk over the cloud's
+//                           bucket boxes; certificate per query; what is not certified goes to the work list;
+//   knn_deferred_kernel     the work list through the index search, one warp per query.
+// The monolithic knn_pool_kernel above keeps a group's pool in shared memory; it loses to this form on
+// occupancy and on load balance (a dense group is 5-10 x the work of a sparse one).
+struct KpMeta {
+    float off[32];            // pool planes
+    float cx[8], cy[8], cz[8], cD[8];   // the probed corners and their K-th distances (Lipschitz bounds for cold starts)
+    float g0x, g0y, g0z, inv_cell;
+    int nc, npool, whole, ok;
+};
+constexpr int KP3_MAXNC = 20;                                   // cells per axis of the 3-D cell grid
+constexpr int KP3_CELLS = KP3_MAXNC * KP3_MAXNC * KP3_MAXNC;
+constexpr int KP_STARTS = KP3_CELLS + 8;                        // u16 entries per group
+
+struct KpBuildShared {
+    unsigned long long buf[KP_WARPS][KP_BUF];
+    unsigned short start[KP3_CELLS + 8];
+    unsigned short cur[KP3_CELLS + 8];
+    unsigned short blist[KP_BLIST];
+    float red[6][KP_WARPS];
+    float qlo[3], qhi[3];
+    float off[32];
+    float cD[8];
+    float g0[3], inv_cell, d0;
+    int nc, nblist, npool, whole;
+};
+
+template <int T, bool BIG>
+__global__ void __launch_bounds__(KP_THREADS)
+knn_pool_build_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, int64_t Q, int K, int gsz, float cell_in,
+                      int nvalid, int pool_cap, float halo_scale, float4 *__restrict__ pools,
+                      unsigned short *__restrict__ starts_g, KpMeta *__restrict__ metas) {
+    constexpr int TT = T < 32 ? T : 32;
+    constexpr int SB = (T + 31) / 32;
+    constexpr int NBUCKETS = T * 32;
+    __shared__ KpBuildShared S;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cap = index.cap;
+    const float *box = index.bucket_box + (int64_t)b * (cap / 32) * 8;
+    const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
+    const int64_t q_begin = (int64_t)blockIdx.x * gsz;
+    const int nq = (int)min((int64_t)gsz, Q - q_begin);
+    const float *qg = query + ((int64_t)b * Q + q_begin) * 3;
+    const int64_t gid = (int64_t)b * gridDim.x + blockIdx.x;
+    float4 *pool = pools + gid * pool_cap;
+    unsigned short *starts = starts_g + gid * KP_STARTS;
+    KpMeta &M = metas[gid];
+
+    // ---- query box ----
+    {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = tid; i < nq; i += KP_THREADS) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = __ldg(qg + 3 * i + c);
+                mn[c] = fminf(mn[c], v);
+                mx[c] = fmaxf(mx[c], v);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], s));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], s));
+            }
+            if (lane == 0) {
+                S.red[c][warp] = mn[c];
+                S.red[3 + c][warp] = mx[c];
+            }
+        }
+        __syncthreads();
+        if (tid < 3) {
+            float a = INFINITY, z = -INFINITY;
+            for (int w = 0; w < KP_WARPS; ++w) {
+                a = fminf(a, S.red[tid][w]);
+                z = fmaxf(z, S.red[3 + tid][w]);
+            }
+            S.qlo[tid] = a;
+            S.qhi[tid] = z;
+        }
+        __syncthreads();
+    }
+    const float qlx = S.qlo[0], qly = S.qlo[1], qlz = S.qlo[2], qhx = S.qhi[0], qhy = S.qhi[1], qhz = S.qhi[2];
+    float cell = cell_in;
+    const float ext3 = fmaxf(fmaxf(qhx - qlx, qhy - qly), qhz - qlz);
+    {
+        const float need = ext3 / (float)(KP3_MAXNC - 2 * KP_HALO - 2);
+        if (!(cell > need)) cell = need * 1.0001f + 1e-20f;
+    }
+    KnnCtx ctx;
+    ctx.box = box;
+    ctx.spt = spt;
+    ctx.buf = S.buf[warp];
+    ctx.spt_lane = spt + lane;
+    ctx.box_lane = reinterpret_cast<const float4 *>(box) + lane * 2;
+    ctx.K = K;
+    ctx.loose = INFINITY;
+    Box6 sb[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) sb[s] = load_super_box(box, TT, s * 32 + lane);
+
+    // ---- probes: the centre cold (best-first), then the corners bounded through it (1-Lipschitz) ----
+    const bool probe = nvalid > pool_cap;
+    if (probe) {
+        const float mx_ = 0.5f * (qlx + qhx), my_ = 0.5f * (qly + qhy), mz_ = 0.5f * (qlz + qhz);
+        if (warp == 0) {
+            const unsigned long long r = knn_query_thr<T, BIG>(ctx, sb, mx_, my_, mz_, INFINITY, lane);
+            const unsigned long long rk = __shfl_sync(0xffffffffu, r, K - 1);
+            if (lane == 0) S.d0 = sqrtf(__uint_as_float(KnnKey<BIG>::d2bits(rk)));
+        }
+        __syncthreads();
+        const float d0 = S.d0;
+        for (int cn = warp; cn < 8; cn += KP_WARPS) {
+            const float cx = (cn & 1) ? qhx : qlx, cy = (cn & 2) ? qhy : qly, cz = (cn & 4) ? qhz : qlz;
+            const float hd = sqrtf((cx - mx_) * (cx - mx_) + (cy - my_) * (cy - my_) + (cz - mz_) * (cz - mz_));
+            const float bd = fmaf(d0 + hd, 1.0001f, 1e-5f * (fabsf(cx) + fabsf(cy) + fabsf(cz)) + 1e-6f);
+            const unsigned long long r = knn_query_thr<T, BIG>(ctx, sb, cx, cy, cz, bd * bd, lane);
+            const unsigned long long rk = __shfl_sync(0xffffffffu, r, K - 1);
+            if (lane == 0) S.cD[cn] = sqrtf(__uint_as_float(KnnKey<BIG>::d2bits(rk)));
+        }
+    }
+    if (tid == 0) {
+        int nc = (int)(ext3 / cell) + 1 + 2 * KP_HALO;
+        if (nc > KP3_MAXNC) nc = KP3_MAXNC;
+        S.nc = nc;
+        S.g0[0] = qlx - KP_HALO * cell;
+        S.g0[1] = qly - KP_HALO * cell;
+        S.g0[2] = qlz - KP_HALO * cell;
+        S.inv_cell = 1.0f / cell;
+    }
+    __syncthreads();
+    const int nc = S.nc, ncell = nc * nc * nc;
+    const float g0x = S.g0[0], g0y = S.g0[1], g0z = S.g0[2], inv_cell = S.inv_cell;
+    auto cell_of = [&](const float4 &P) {
+        return (kp_cell(P.x, g0x, inv_cell, nc) * nc + kp_cell(P.y, g0y, inv_cell, nc)) * nc + kp_cell(P.z, g0z, inv_cell, nc);
+    };
+    bool pool_ok = false;
+    float lx = 0.f, ly = 0.f, lz = 0.f, hx = 0.f, hy = 0.f, hz = 0.f;
+    for (int attempt = 0; attempt < 4 && !pool_ok; ++attempt) {
+        __syncthreads();
+        if (tid < 32) {
+            float o = INFINITY;
+            if (probe && tid < 26) {
+                const float shrink[4] = {1.0f, 0.2f, 0.04f, 0.008f};
+                const float scale = 1.0f + shrink[attempt] * (halo_scale - 1.0f);
+                float vx, vy, vz;
+                kp_dir(tid, vx, vy, vz);
+                const float vn = sqrtf(vx * vx + vy * vy + vz * vz);
+                o = -INFINITY;
+                for (int cn = 0; cn < 8; ++cn) {
+                    const float cx = (cn & 1) ? qhx : qlx, cy = (cn & 2) ? qhy : qly, cz = (cn & 4) ? qhz : qlz;
+                    const float D = fmaf(S.cD[cn], scale, 1e-5f * (fabsf(cx) + fabsf(cy) + fabsf(cz)) + 1e-6f);
+                    o = fmaxf(o, vx * cx + vy * cy + vz * cz + vn * D);
+                }
+            }
+            S.off[tid] = o;
+        }
+        __syncthreads();
+        lx = -S.off[4]; hx = S.off[21]; ly = -S.off[10]; hy = S.off[15]; lz = -S.off[12]; hz = S.off[13];
+        for (int i = tid; i < ncell + 2; i += KP_THREADS) S.cur[i] = 0;
+        if (tid == 0) {
+            S.nblist = 0;
+            S.npool = 0;
+        }
+        __syncthreads();
+        for (int j = tid; j < NBUCKETS; j += KP_THREADS) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)j * 8) + 1);
+            if (b1.z > 0.f && b0.x <= hx && b0.w >= lx && b0.y <= hy && b1.x >= ly && b0.z <= hz && b1.y >= lz) {
+                const int at = atomicAdd(&S.nblist, 1);
+                if (at < KP_BLIST) S.blist[at] = (unsigned short)j;
+            }
+        }
+        __syncthreads();
+        const int nbl = S.nblist;
+        if (nbl <= KP_BLIST) {
+            int mine = 0;
+            for (int i = warp; i < nbl; i += KP_WARPS) {
+                const float4 P = __ldg(spt + (int)S.blist[i] * 32 + lane);
+                const bool in = kp_inside(P, S.off);
+                if (in) {
+                    const int c = cell_of(P);
+                    atomicAdd(reinterpret_cast<unsigned int *>(S.cur) + (c >> 1), 1u << (16 * (c & 1)));
+                }
+                mine += __popc(__ballot_sync(0xffffffffu, in));
+            }
+            if (lane == 0 && mine) atomicAdd(&S.npool, mine);
+        }
+        __syncthreads();
+        pool_ok = nbl <= KP_BLIST && S.npool <= pool_cap;
+        __syncthreads();
+        if (!probe) break;
+    }
+    if (pool_ok) {
+        const int nbl = S.nblist;
+        if (warp == 0) {
+            int run = 0;
+            for (int base = 0; base < ncell; base += 32) {
+                const int i = base + lane;
+                const int v = i < ncell ? S.cur[i] : 0;
+                int inc = v;
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, s);
+                    if (lane >= s) inc += t;
+                }
+                if (i < ncell) S.start[i] = (unsigned short)(run + inc - v);
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) {
+                S.start[ncell] = (unsigned short)run;
+                S.whole = run == nvalid;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < ncell + 2; i += KP_THREADS) S.cur[i] = 0;
+        __syncthreads();
+        for (int i = warp; i < nbl; i += KP_WARPS) {
+            const float4 P = __ldg(spt + (int)S.blist[i] * 32 + lane);
+            if (kp_inside(P, S.off)) {
+                const int c = cell_of(P);
+                const unsigned old = atomicAdd(reinterpret_cast<unsigned int *>(S.cur) + (c >> 1), 1u << (16 * (c & 1)));
+                pool[S.start[c] + ((old >> (16 * (c & 1))) & 0xffffu)] = P;
+            }
+        }
+        for (int i = tid; i < ncell + 1; i += KP_THREADS) starts[i] = S.start[i];
+    }
+    // ---- meta data ----
+    if (tid < 32) M.off[tid] = S.off[tid];
+    if (tid < 8) {
+        M.cx[tid] = (tid & 1) ? qhx : qlx;
+        M.cy[tid] = (tid & 2) ? qhy : qly;
+        M.cz[tid] = (tid & 4) ? qhz : qlz;
+        M.cD[tid] = probe ? S.cD[tid] : INFINITY;
+    }
+    if (tid == 0) {
+        M.g0x = g0x; M.g0y = g0y; M.g0z = g0z; M.inv_cell = inv_cell;
+        M.nc = nc;
+        M.npool = pool_ok ? S.npool : 0;
+        M.whole = pool_ok && S.whole != 0;
+        M.ok = pool_ok ? 1 : 0;
+    }
+}
+
+constexpr int KQ_WARPS = 4;
+constexpr int KQ_STACK = 8;    // qualifying points one lane holds before the warp folds them into its K best
+
+// One warp per chain of z-lines. The candidates of a query are the pool points of the 3-D cells within sqrt(thr):
+// the (x, y) columns of that window are dealt to the lanes, a lane walks the consecutive pool entries of its
+// column's z-range (the pool is sorted by cell) and pushes the points with d2 <= thr onto its own little stack in
+// shared memory; when a stack is full, and at the end, the stacks are compacted (one warp prefix sum), sorted in
+// chunks of 32 and merged into the K best so far, whose K-th distance tightens thr for what is still to scan.
+template <int T, bool BIG>
+__global__ void __launch_bounds__(KQ_WARPS * 32, 8)
+knn_pool_query_kernel(const float *__restrict__ query, int64_t Q, int K, int gsz, int zline, int chain_lines,
+                      int groups_per_item, int pool_cap, const float4 *__restrict__ pools,
+                      const unsigned short *__restrict__ starts_g, const KpMeta *__restrict__ metas,
+                      float *__restrict__ dist, int64_t *__restrict__ idx64, int32_t *__restrict__ idx32,
+                      unsigned long long *__restrict__ stats, KpWork *__restrict__ work,
+                      unsigned int *__restrict__ work_count, int64_t nchains_total, int chains_per_group) {
+    __shared__ unsigned long long s_stack[KQ_WARPS][KQ_STACK * 32];
+    __shared__ unsigned long long s_comp[KQ_WARPS][KQ_STACK * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long INF = 0xffffffffffffffffull;
+    unsigned long long *stack = s_stack[warp], *comp = s_comp[warp];
+    unsigned st_cert = 0, st_unc = 0, st_ovf = 0, st_cold = 0, st_adm = 0, st_scan = 0;
+    const int csz = chain_lines * zline;   // queries per chain
+    for (int64_t ch = (int64_t)blockIdx.x * KQ_WARPS + warp; ch < nchains_total; ch += (int64_t)gridDim.x * KQ_WARPS) {
+        const int gid = (int)(ch / chains_per_group);          // group over the whole batch
+        const int cig = (int)(ch - (int64_t)gid * chains_per_group);
+        const int b = gid / groups_per_item;
+        const int64_t q_begin = (int64_t)(gid - b * groups_per_item) * gsz;
+        const int nq = (int)min((int64_t)gsz, Q - q_begin);
+        const int u0 = cig * csz, u1 = min(u0 + csz, nq);
+        if (u0 >= nq) continue;
+        const int64_t qbase = (int64_t)b * Q + q_begin;
+        const float *qg = query + qbase * 3;
+        const KpMeta &M = metas[gid];
+        const float4 *pool = pools + (int64_t)gid * pool_cap;
+        const unsigned short *starts = starts_g + (int64_t)gid * KP_STARTS;
+        const int nc = M.nc;
+        const bool usable = M.ok != 0 && M.npool >= K, whole = M.whole != 0;
+        const float g0x = M.g0x, g0y = M.g0y, g0z = M.g0z, inv_cell = M.inv_cell;
+        // this lane's pool plane (certificate) and corner probe (a bound that always holds)
+        float pvx = 0.f, pvy = 0.f, pvz = 0.f, pinv = 0.f, poff = INFINITY;
+        if (lane < 26) {
+            kp_dir(lane, pvx, pvy, pvz);
+            pinv = rsqrtf(pvx * pvx + pvy * pvy + pvz * pvz) * 0.99999f;
+            poff = M.off[lane];
+        }
+        const float ccx = M.cx[lane & 7], ccy = M.cy[lane & 7], ccz = M.cz[lane & 7], ccD = M.cD[lane & 7];
+        unsigned long long list = INF;
+        int line_k = 0, line_dir = 1;   // position inside the current z-line, walking direction (boustrophedon)
+        for (int qi = u0; qi < u1; ++qi) {
+            const int line0 = qi - line_k;                    // first query of this line (walk order)
+            const int line_len = min(zline, u1 - line0);
+            const int ql = line_dir > 0 ? qi : line0 + (line_len - 1 - line_k);
+            if (++line_k == line_len) {
+                line_k = 0;
+                line_dir = -line_dir;
+            }
+            const float qx = __ldg(qg + 3 * ql), qy = __ldg(qg + 3 * ql + 1), qz = __ldg(qg + 3 * ql + 2);
+            float thr;
+            {   // nearest probed corner: d_K is 1-Lipschitz (+inf when the pool holds the whole cloud unprobed)
+                const float dq = sqrtf((ccx - qx) * (ccx - qx) + (ccy - qy) * (ccy - qy) + (ccz - qz) * (ccz - qz));
+                float bsum = fmaf(ccD + dq, 1.0001f, 1e-5f * (fabsf(qx) + fabsf(qy) + fabsf(qz)) + 1e-6f);
+                bsum = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(bsum)));
+                thr = bsum * bsum;
+            }
+            unsigned long long res = INF;
+            bool done = false;
+            if (usable) {
+                if (__any_sync(0xffffffffu, list != INF)) {   // the previous query's K neighbours, re-evaluated
+                    float d2 = 0.f;
+                    if (lane < K) {
+                        const float4 P = __ldg(pool + ((unsigned)list & ((1u << KP_POSBITS) - 1u)));
+                        d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+                    }
+                    thr = fminf(thr, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(d2))));
+                } else {
+                    ++st_cold;
+                }
+                int cnt = 0;   // entries on my stack
+                // fold the stacks into the K best so far; their K-th distance becomes the bound
+                auto fold = [&]() {
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+                    for (int j = 0; j < cnt; ++j) comp[off + j] = stack[j * 32 + lane];
+                    __syncwarp();
+                    for (int g = 0; g < total; g += 32) {
+                        unsigned long long k = g + lane < total ? comp[g + lane] : INF;
+                        k = bitonic_sort32(k, lane);
+                        if (__all_sync(0xffffffffu, res == INF)) {
+                            res = k;
+                        } else {
+                            const unsigned long long r = __shfl_sync(0xffffffffu, k, 31 - lane);
+                            res = u64min(res, r);
+#pragma unroll
+                            for (int j = 16; j > 0; j >>= 1) res = cmpx64(res, j, (lane & j) == 0);
+                        }
+                    }
+                    __syncwarp();
+                    st_adm += total;
+                    cnt = 0;
+                    const unsigned long long w = __shfl_sync(0xffffffffu, res, K - 1);
+                    if (w != INF) thr = fminf(thr, __uint_as_float((unsigned)(w >> 32)));
+                };
+                // window of cells
+                int cx0 = 0, cx1 = nc - 1, cy0 = 0, cy1 = nc - 1, cz0 = 0, cz1 = nc - 1;
+                if (thr < INFINITY) {
+                    const float r0 = sqrtf(thr);
+                    const float rho = fmaf(r0, 1.00002f, 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + r0) + 1e-30f);
+                    cx0 = kp_cell(qx - rho, g0x, inv_cell, nc); cx1 = kp_cell(qx + rho, g0x, inv_cell, nc);
+                    cy0 = kp_cell(qy - rho, g0y, inv_cell, nc); cy1 = kp_cell(qy + rho, g0y, inv_cell, nc);
+                    cz0 = kp_cell(qz - rho, g0z, inv_cell, nc); cz1 = kp_cell(qz + rho, g0z, inv_cell, nc);
+                }
+                const int wy = cy1 - cy0 + 1, ncols = (cx1 - cx0 + 1) * wy;
+                const float inv_wy = 1.0f / (float)wy;
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    const int c = c0 + lane;
+                    int i = 0, i1 = 0;
+                    if (c < ncols) {
+                        const int cxi = (int)(((float)c + 0.5f) * inv_wy), cyi = c - cxi * wy;   // exact for c < 2^20
+                        const int base = ((cx0 + cxi) * nc + (cy0 + cyi)) * nc;
+                        i = __ldg(starts + base + cz0);
+                        i1 = __ldg(starts + base + cz1 + 1);
+                    }
+                    st_scan += i1 - i;
+                    // short runs (the usual case: a few points per column): every lane walks its own
+#pragma unroll 1
+                    for (int it = 0; it < 3 && __any_sync(0xffffffffu, i < i1); ++it) {
+                        if (i < i1) {
+                            const float4 P = __ldg(pool + i);
+                            const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+                            if (d2 <= thr) {
+                                stack[cnt * 32 + lane] = kp_key(d2, __float_as_int(P.w), i);
+                                ++cnt;
+                            }
+                            ++i;
+                        }
+                        if (__any_sync(0xffffffffu, cnt == KQ_STACK)) {
+                            fold();
+                            ++st_ovf;
+                        }
+                    }
+                    // what is left of long runs (wide windows far from the cloud): the whole warp walks one run at a time
+                    unsigned rem = __ballot_sync(0xffffffffu, i < i1);
+                    while (rem) {
+                        const int srcl = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        const int a = __shfl_sync(0xffffffffu, i, srcl), bnd = __shfl_sync(0xffffffffu, i1, srcl);
+                        for (int j = a + lane; j < bnd + ((a - bnd) & 31); j += 32) {
+                            if (j < bnd) {
+                                const float4 P = __ldg(pool + j);
+                                const float d2 = sqdist_direct(P.x - qx, P.y - qy, P.z - qz);
+                                if (d2 <= thr) {
+                                    stack[cnt * 32 + lane] = kp_key(d2, __float_as_int(P.w), j);
+                                    ++cnt;
+                                }
+                            }
+                            if (__any_sync(0xffffffffu, cnt == KQ_STACK)) {
+                                fold();
+                                ++st_ovf;
+                            }
+                        }
+                    }
+                }
+                fold();
+                if (lane >= K) res = INF;
+                const unsigned long long wk = __shfl_sync(0xffffffffu, res, K - 1);
+                if (wk != INF) {   // the pool had K points within the bound
+                    const float kth = __uint_as_float((unsigned)(wk >> 32));
+                    float m = (poff - (pvx * qx + pvy * qy + pvz * qz)) * pinv;
+                    m = m - 4e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(m));
+                    if (!(poff < INFINITY)) m = INFINITY;
+                    m = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(fmaxf(m, 0.f))));
+                    done = whole || kth * 1.00001f < m * m;
+                } else {
+                    res = INF;
+                }
+            }
+            if (done) {
+                if (lane < K) {
+                    const int64_t o = (qbase + ql) * K + lane;
+                    dist[o] = __fsqrt_rn(__uint_as_float((unsigned)(res >> 32)));
+                    const unsigned id = (unsigned)res >> KP_POSBITS;
+                    if (idx64) idx64[o] = id;
+                    if (idx32) idx32[o] = (int32_t)id;
+                }
+                list = res;
+                ++st_cert;
+            } else {
+                ++st_unc;
+                if (lane == 0) {   // thr: the best bound at hand (the pool's K-th distance if it had K points)
+                    const unsigned at = atomicAdd(work_count, 1u);
+                    work[at] = KpWork{qbase + ql, thr};
+                }
+                list = res;   // the pool's K best (if it had them) still seed the next query
+                if (!__all_sync(0xffffffffu, lane >= K || list != INF)) list = INF;
+            }
+        }
+    }
+    st_scan = __reduce_add_sync(0xffffffffu, st_scan);
+    kp_flush_stats(stats, lane, 1, 0, st_cert, st_unc, st_ovf, st_cold, 0u, st_adm, st_scan);
+}
+
 template <int T, bool BIG = false>
 static int launch_knn_pool(dvcp_cloud_index_t index, const float *query, int B, int N, int64_t Q, int K, int gsz,
                            int zline, float cell, int pool_cap, float *dist, int64_t *idx64, int32_t *idx32,
                            unsigned long long *stats, void *workspace, cudaStream_t st) {
-    auto k = knn_pool_kernel<T, BIG>;
-    if (pool_cap <= 0) {
-        static const int def = [] {   // DVCP_KNN_POOL: development override of the default pool capacity
-            const char *e = getenv("DVCP_KNN_POOL");
-            return e ? atoi(e) : KP_POOL_DEFAULT;
-        }();
-        pool_cap = def;
-    }
-    static const float halo_scale = [] {   // DVCP_KNN_HALO: development override (halo = scale x the corners' K-th distance)
+    static const float halo_scale = [] {   // DVCP_KNN_HALO: development override (allowance over the corners' K-th distance)
         const char *e = getenv("DVCP_KNN_HALO");
         return e ? (float)atof(e) : KP_HALO_SCALE;
     }();
-    pool_cap = pool_cap < 64 ? 64 : (pool_cap > KP_POOL_MAX ? KP_POOL_MAX : (pool_cap & ~31));
-    const int smem = (int)(sizeof(KpShared) + (size_t)pool_cap * sizeof(float4));
-    DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    dim3 grid((unsigned)((Q + gsz - 1) / gsz), B);
-    unsigned int *work_count = reinterpret_cast<unsigned int *>(workspace);
-    KpWork *work = reinterpret_cast<KpWork *>(reinterpret_cast<unsigned char *>(workspace) + 16);
+    static const int chain_lines_env = [] {   // DVCP_KNN_CHAIN: z-lines per chain of the query kernel
+        const char *e = getenv("DVCP_KNN_CHAIN");
+        return e ? atoi(e) : 0;
+    }();
+    static const int mono = [] {   // DVCP_KNN_MONO=1: the monolithic shared-memory kernel
+        const char *e = getenv("DVCP_KNN_MONO");
+        return e ? atoi(e) : 0;
+    }();
+    const int64_t groups = (Q + gsz - 1) / gsz;
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    unsigned int *work_count = reinterpret_cast<unsigned int *>(ws);
+    KpWork *work = reinterpret_cast<KpWork *>(ws + 16);
     DVCP_CUDA(cudaMemsetAsync(work_count, 0, 16, st));
-    k<<<grid, KP_THREADS, smem, st>>>(index, query, Q, K, gsz, zline, cell, N, pool_cap, halo_scale, dist, idx64, idx32, stats,
-                                      work, work_count);
-    DVCP_CHECK_LAUNCH();
+    if (mono) {
+        int cap = pool_cap <= 0 ? KP_POOL_DEFAULT : pool_cap;
+        cap = cap < 64 ? 64 : (cap > KP_POOL_MAX ? KP_POOL_MAX : (cap & ~31));
+        auto k = knn_pool_kernel<T, BIG>;
+        const int smem = (int)(sizeof(KpShared) + (size_t)cap * sizeof(float4));
+        DVCP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dim3 grid((unsigned)groups, B);
+        k<<<grid, KP_THREADS, smem, st>>>(index, query, Q, K, gsz, zline, cell, N, cap, halo_scale, dist, idx64, idx32, stats,
+                                          work, work_count);
+        DVCP_CHECK_LAUNCH();
+    } else {
+        int cap = pool_cap <= 0 ? KP_POOL_MAX : pool_cap;
+        cap = cap < 64 ? 64 : (cap > KP_POOL_MAX ? KP_POOL_MAX : (cap & ~31));
+        size_t off = 16 + (size_t)B * Q * sizeof(KpWork);
+        off = (off + 255) & ~(size_t)255;
+        KpMeta *metas = reinterpret_cast<KpMeta *>(ws + off);
+        off += (size_t)B * groups * sizeof(KpMeta);
+        off = (off + 255) & ~(size_t)255;
+        unsigned short *starts = reinterpret_cast<unsigned short *>(ws + off);
+        off += (size_t)B * groups * KP_STARTS * sizeof(unsigned short);
+        off = (off + 255) & ~(size_t)255;
+        float4 *pools = reinterpret_cast<float4 *>(ws + off);
+        dim3 bgrid((unsigned)groups, B);
+        knn_pool_build_kernel<T, BIG><<<bgrid, KP_THREADS, 0, st>>>(index, query, Q, K, gsz, cell, N, cap, halo_scale, pools,
+                                                                    starts, metas);
+        DVCP_CHECK_LAUNCH();
+        const int lines_per_group = (gsz + zline - 1) / zline;
+        int chain_lines = chain_lines_env > 0 ? chain_lines_env : 1;
+        if (chain_lines > lines_per_group) chain_lines = lines_per_group;
+        const int chains_per_group = (lines_per_group + chain_lines - 1) / chain_lines;
+        const int64_t nchains = (int64_t)B * groups * chains_per_group;
+        int64_t qgrid = (nchains + KQ_WARPS - 1) / KQ_WARPS;
+        if (qgrid > (int64_t)DVCP_NUM_SMS * 64) qgrid = (int64_t)DVCP_NUM_SMS * 64;
+        knn_pool_query_kernel<T, BIG><<<(unsigned)qgrid, KQ_WARPS * 32, 0, st>>>(
+            query, Q, K, gsz, zline, chain_lines, (int)groups, cap, pools, starts, metas, dist, idx64, idx32, stats, work,
+            work_count, nchains, chains_per_group);
+        DVCP_CHECK_LAUNCH();
+    }
     knn_deferred_kernel<T, BIG><<<DVCP_NUM_SMS * 4, KNI_WARPS * 32, 0, st>>>(index, query, Q, K, work, work_count, dist, idx64, idx32);
     DVCP_CHECK_LAUNCH();
     return 0;
@@ -587,9 +1080,12 @@ static int launch_knn_pool(dvcp_cloud_index_t index, const float *query, int B, 
 
 using namespace dvcp;
 
-extern "C" int64_t dvcp_knn_groups_workspace_bytes(int B, int64_t Q) {
-    if (B <= 0 || Q <= 0) return 0;
-    return 16 + (int64_t)B * Q * (int64_t)sizeof(KpWork);   // worst case: every query deferred
+extern "C" int64_t dvcp_knn_groups_workspace_bytes(int B, int64_t Q, int group) {
+    if (B <= 0 || Q <= 0 || group <= 0) return 0;
+    const int64_t groups = (Q + group - 1) / group;
+    // work list (worst case: every query deferred) + per group: meta data, cell starts, pool of KP_POOL_MAX points
+    return 16 + (int64_t)B * Q * (int64_t)sizeof(KpWork) + 3 * 256 +
+           (int64_t)B * groups * ((int64_t)sizeof(KpMeta) + KP_STARTS * 2 + (int64_t)KP_POOL_MAX * 16);
 }
 
 extern "C" int dvcp_knn_groups(dvcp_cloud_index_t index, const float *query, int B, int N, int64_t Q, int K,
@@ -602,7 +1098,7 @@ extern "C" int dvcp_knn_groups(dvcp_cloud_index_t index, const float *query, int
     if (K < 1 || K > 32 || K > N || B > 65535 || index.cap < N || (Q + group - 1) / group > 0x7fffffff)
         return DVCP_E_UNSUPPORTED;
     if (!workspace) return DVCP_E_ARG;
-    if (workspace_bytes < dvcp_knn_groups_workspace_bytes(B, Q)) return DVCP_E_WORKSPACE;
+    if (workspace_bytes < dvcp_knn_groups_workspace_bytes(B, Q, group)) return DVCP_E_WORKSPACE;
     if (zline > group) zline = group;
     cudaStream_t st = (cudaStream_t)stream;
     switch (index.cap / 1024) {

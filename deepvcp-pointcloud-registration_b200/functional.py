@@ -373,11 +373,11 @@ def knn_groups(index, lo, device, B, N, query, K, group, zline, cell, pool_cap=0
     dist = torch.empty(B, Q, K, dtype=torch.float32, device=device)
     i64 = torch.empty(B, Q, K, dtype=torch.int64, device=device) if want64 else None
     i32 = torch.empty(B, Q, K, dtype=torch.int32, device=device) if want32 else None
-    nbytes = lib().dvcp_knn_groups_workspace_bytes(B, Q)
+    nbytes = lib().dvcp_knn_groups_workspace_bytes(B, Q, group)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
     check(lib().dvcp_knn_groups(index.c(lo), ptr(query), B, N, Q, K, group, zline, float(cell), pool_cap, ptr(dist),
                                 ptr(i64), ptr(i32), ptr(stats), ptr(ws), nbytes, stream_ptr(device)), "dvcp_knn_groups")
-    _count(2)   # pool kernel + the deferred index searches
+    _count(3)   # pool build + query kernel + the deferred index searches
     return dist, i64, i32
 
 

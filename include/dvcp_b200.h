@@ -233,9 +233,10 @@ DVCP_API int dvcp_knn_indexed(dvcp_cloud_index_t ref_index, const float *query, 
  * dvcp_knn. pool_cap: shared-memory pool capacity in points (0 = default; 64..8192). Clouds of up to
  * 65536 points. stats (nullable): 8 device counters ADDED to, for profiling -- queries certified by the pool,
  * uncertified, list overflows, cold starts, queries of groups without a pool, pool points, points admitted
- * by the bound, points scanned. workspace: dvcp_knn_groups_workspace_bytes(B, Q) bytes (the list of queries
- * the pools could not certify; a second kernel answers them through the index, one warp per query). */
-DVCP_API int64_t dvcp_knn_groups_workspace_bytes(int B, int64_t Q);
+ * by the bound, points scanned. workspace: dvcp_knn_groups_workspace_bytes(B, Q, group) bytes (the pools, their
+ * cell tables, and the list of queries the pools could not certify: a last kernel answers those through the
+ * index, one warp per query). */
+DVCP_API int64_t dvcp_knn_groups_workspace_bytes(int B, int64_t Q, int group);
 DVCP_API int dvcp_knn_groups(dvcp_cloud_index_t index, const float *query, int B, int N, int64_t Q, int K,
                     int group, int zline, float cell, int pool_cap, float *dist, int64_t *idx64,
                     int32_t *idx32, uint64_t *stats, void *workspace, int64_t workspace_bytes,
