@@ -114,6 +114,8 @@ class GraphedRegistration:
         from . import functional as F_
         self.model, self.dev, self.depth = model, dev, max(1, depth)
         self.B, self.C_in, self.N = B, C_in, N
+        import os
+        self.small_sampling_ctas = os.environ.get("DVCP_FPS_SMALL") == "1"   # development: 8-warp sampling CTAs
         self.fe_stream = torch.cuda.Stream(device=dev)
         self.match_stream = torch.cuda.Stream(device=dev) if self.depth > 1 else self.fe_stream
         self.copy_stream = torch.cuda.Stream(device=dev)   # input copies run ahead of the (in-order) feature stream
@@ -139,7 +141,8 @@ class GraphedRegistration:
             self._capture(s, F_)
 
     def _run_fe(self, s):
-        return self.model.extract_features(s["src"], s["tgt"], (s["st"][0], s["st"][1], s["st"][2]))
+        return self.model.extract_features(s["src"], s["tgt"], (s["st"][0], s["st"][1], s["st"][2]),
+                                           concurrent=self.small_sampling_ctas)
 
     def _run_match(self, s, fe):
         kp, vcp = self.model.match(fe, s["Ri"])
