@@ -58,6 +58,47 @@ __device__ __forceinline__ float sqdist_direct(float dx, float dy, float dz) {
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// ---- key of the spatial index: position of a 10-bit-per-axis cell on a space-filling curve ----
+// The consumers only need "32 consecutive points of the order form a compact box"; the order itself never
+// changes a result (members are always decided by the exact arithmetic). The Hilbert curve has no jumps, so
+// the boxes of consecutive runs are tighter than along the Z-order (Morton) curve, whose runs straddle
+// octant boundaries: fewer buckets pass the box tests of the KNN / ball-query / sampling kernels.
+__device__ __forceinline__ unsigned spread_bits10(unsigned v) {   // bit i -> bit 3 i
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned spatial_key(unsigned x, unsigned y, unsigned z) {
+#ifndef DVCP_MORTON_INDEX
+    // Skilling's axes -> transposed Hilbert index (3 axes, 10 bits), then interleaved
+    unsigned X[3] = {x, y, z};
+#pragma unroll
+    for (unsigned Q = 512u; Q > 1u; Q >>= 1) {
+        const unsigned P = Q - 1u;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const unsigned t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    unsigned t = 0u;
+#pragma unroll
+    for (unsigned Q = 512u; Q > 1u; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1u;
+    x = X[0] ^ t; y = X[1] ^ t; z = X[2] ^ t;
+#endif
+    return (spread_bits10(x) << 2) | (spread_bits10(y) << 1) | spread_bits10(z);
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 // argmax over a warp of (value bits, tie -> smaller `lo` payload wins is encoded

@@ -5,45 +5,52 @@
 // Linear layers have no activation between them (deep_feat_embedding.py:48-50), so
 // they are one affine map 35 -> 32; the host collapses them in float64
 // (Wc = W3 W2 W1, bc = W3 (W2 b1 + b2) + b3) and this kernel evaluates
-//     Y^T[32 x 128] = Bm[32 x 40] * A^T[40 x 128]
+//     Y[128 x 32] = X[128 x 40] * Wc^T[40 x 32]
 // per tile of 4 candidates x 32 neighbours, K = 32 weighted features + 3 local
 // coordinates + 1 (bias) + 4 zero columns, as a TF32 tensor-core GEMM with the
-// 3xTF32 split (A = Ah + Al, B = Bh + Bl; Bh*Ah + Bh*Al + Bl*Ah, FP32 accumulate
+// 3xTF32 split (X = Xh + Xl, W = Wh + Wl; Xh*Wh + Xh*Wl + Xl*Wh, FP32 accumulate
 // in TMEM), which keeps FP32-level accuracy (error ~2^-21 relative).
 //
-// The WEIGHTS are the M-side operand (rows 32..127 of its 128-row image are zero) and the gathered
-// neighbour rows the N-side operand, so the accumulator is channel-major: TMEM lane = output channel,
-// column = neighbour. The max-pool over a candidate's 32 neighbours is then 31 FMNMX over the 32
-// registers one tcgen05.ld returns -- no shuffles (the row-major form needed a 63-shuffle butterfly per
-// warp and tile). The tensor pipe does 4x the useful work for it; it has the headroom (14 % busy before).
+// The kernel is bound by shared-memory bandwidth (the producers' operand stores, the gathered lines
+// coming through L1, and the tensor core's operand reads share one 128 B/clk pipe), so the MMA shapes are
+// chosen for the fewest operand bytes per tile: the GATHERED ROWS are the M-side operand (M = 128, read
+// once per MMA) and the N-side operand is the 64-row image [Wh ; Wl]: ONE N = 64 MMA forms Xh*Wh (TMEM
+// columns 0..31) and Xh*Wl (columns 32..63) from a single read of Xh, a second N = 32 MMA adds Xl*Wh to
+// columns 0..31. 10 MMAs and 55 KB of operand reads per tile (the channel-major form this replaces, weights
+// as a zero-padded 128-row M operand and N = 128: 15 MMAs, 120 KB, tensor pipe 61 % busy on 4x the useful work).
+// The accumulator is row-major (TMEM lane = neighbour, column = channel): an epilogue warp per candidate
+// adds the two column halves in registers and takes the max over its 32 lanes with a transposing butterfly
+// (16 shuffles per 16 channels).
 //
-// Roles in a CTA (14 warps, one persistent CTA per SM, 4 operand stages + 4 TMEM accumulators of 128 columns):
-//   warp 0      epilogue: per candidate one tcgen05.ld of its 32 TMEM lanes (channels) x 32 columns
-//               (neighbours), max in registers, one coalesced 128-byte store;
-//   warps 1-12  producers, 3 groups of 4 (group g builds tiles g, g+3, ...): gather the
+// Roles in a CTA (21 warps, one persistent CTA per SM, 4 operand stages + 4 TMEM accumulators of 64 columns):
+//   warps 0-3   epilogue: warp w owns TMEM lanes 32w..32w+31 = candidate w of the tile: tcgen05.ld of
+//               16 + 16 columns at a time, add, max over the lanes, one coalesced 128-byte store;
+//   warps 4-19  producers, 4 groups of 4 (group g builds tiles g, g+4, ...): gather the
 //               neighbours' feature rows into registers (next tile's indices are already
 //               in flight), scale by the float64 distance weights carried as float pairs,
-//               split hi/lo, store into shared memory in the UMMA K-major core-matrix layout;
-//   warp 13     allocates TMEM, waits for the operand, issues the 15 tcgen05.mma of a tile from
+//               split hi/lo, store into shared memory in the UMMA K-major SWIZZLE_128B layout;
+//   warp 20     allocates TMEM, waits for the operand, issues the 10 tcgen05.mma of a tile from
 //               one lane and commits to the mbarriers.
-// A is gathered (index-driven) and cannot be described by a TMA tensor map; the
-// operands reach the tensor core through shared-memory matrix descriptors.
+// The rows are gathered (index-driven) AND scaled by a per-candidate, per-feature weight before the
+// contraction (quirk Q7), so they pass through registers; a bulk / TMA copy could only land them in a
+// staging buffer that the same warps would have to read again (more shared-memory traffic, the binding
+// resource). The operands reach the tensor core through shared-memory matrix descriptors.
 #include "common.cuh"
 
 namespace dvcp {
 
-constexpr unsigned TC_M = 128;                   // UMMA M (32 channels used; M = 64 has another TMEM lane mapping and is no faster: measured)
+constexpr unsigned TC_M = 128;                   // UMMA M = rows of a tile
 constexpr int TC_K = 40;                       // padded reduction length
 constexpr int TC_ROWS = 128;                   // rows per tile = 4 candidates x 32 neighbours
 constexpr int TC_A_SW_BYTES = TC_ROWS * 128;    // A plane, columns 0..31: 128-byte rows, SWIZZLE_128B (K-major)
 constexpr int TC_A_TAIL_BYTES = TC_ROWS * 32;   // A plane, columns 32..39: no-swizzle core matrices, K = 8
 constexpr int TC_A_BYTES = TC_A_SW_BYTES + TC_A_TAIL_BYTES;   // one A plane (hi or lo)
 constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one weight plane as the host lays it out (32 channels)
-constexpr int TC_BW_BYTES = 128 * TC_K * 4;     // the same plane as the 128-row M-side operand (rows 32..127 zero)
-constexpr int TC_ACC_COLS = 128;                // TMEM columns per accumulator (= rows of a tile)
+constexpr int TC_BW_BYTES = TC_B_BYTES;         // the N-side operand is [hi plane ; lo plane]: a 64-row image
+constexpr int TC_ACC_COLS = 64;                 // TMEM columns per accumulator: Xh*Wh + Xl*Wh | Xh*Wl
 constexpr int TC_STAGES = 4;                   // shared-memory A stages == TMEM accumulators
 constexpr int TC_GROUPS = 4;                   // producer groups of 4 warps (one candidate per warp)
-constexpr int TC_EPI_WARPS = 1;                // warp 0 reads TMEM lanes 0..31 = the 32 output channels
+constexpr int TC_EPI_WARPS = 4;                // warp w reads TMEM lanes 32w..32w+31 = the neighbours of candidate w
 constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS - 1
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
 constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
@@ -85,8 +92,8 @@ __device__ __forceinline__ uint64_t make_desc_tail(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
            (1ull << 46);
 }
-// kind::tf32, FP32 accumulate, A and B K-major, M = 128 (channels, 32 used), N = 128 (rows of the tile)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((TC_M >> 4) << 24);
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128 (rows of the tile), N = 64 ([Wh ; Wl]) or 32 (Wh)
+__host__ __device__ constexpr uint32_t tc_idesc(unsigned n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((TC_M >> 4) << 24); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -105,12 +112,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+template <unsigned NCOLS>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(tc_idesc(NCOLS)), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -134,10 +142,10 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [32][33]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // rows 0..31 of the 128-row operand are the host's 32-row image (the layout is row-block major), the rest zero
+    // the layout is row-block major, so the host's two 32-row images back to back are the 64-row image [Wh ; Wl]
     for (int i = threadIdx.x; i < TC_BW_BYTES / 4; i += blockDim.x) {
-        reinterpret_cast<float *>(sB)[i] = i < TC_B_BYTES / 4 ? Bhi[i] : 0.f;
-        reinterpret_cast<float *>(sB + TC_BW_BYTES)[i] = i < TC_B_BYTES / 4 ? Blo[i] : 0.f;
+        reinterpret_cast<float *>(sB)[i] = Bhi[i];
+        reinterpret_cast<float *>(sB + TC_BW_BYTES)[i] = Blo[i];
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -168,7 +176,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
 
     if (warp == TC_MMA_WARP) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t a_base = smem_u32(sA), b_hi = smem_u32(sB), b_lo = smem_u32(sB + TC_BW_BYTES);
+        const uint32_t a_base = smem_u32(sA), b_w = smem_u32(sB);   // [Wh ; Wl], 64 rows
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
@@ -176,21 +184,19 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             mbar_wait(&tempty[s], ph ^ 1);      // accumulator s drained (tile i - TC_STAGES)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-                const uint32_t d = tmem_base + (uint32_t)s * TC_ACC_COLS;   // 128 FP32 columns per accumulator
+                const uint32_t d = tmem_base + (uint32_t)s * TC_ACC_COLS;   // 64 FP32 columns per accumulator
                 const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_SW_BYTES;
                 const uint32_t t_hi = a_hi + 2 * TC_A_SW_BYTES, t_lo = t_hi + TC_A_TAIL_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t ka = (uint32_t)ks * 32;          // 8 floats inside the 128-byte swizzled row
-                    const uint32_t kb = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks of B per MMA (K = 8)
-                    // M-side operand: the weights; N-side operand: the gathered rows
-                    umma_tf32(d, make_desc(b_hi + kb), make_desc_sw128(a_hi + ka), ks > 0);
-                    umma_tf32(d, make_desc(b_hi + kb), make_desc_sw128(a_lo + ka), 1u);
-                    umma_tf32(d, make_desc(b_lo + kb), make_desc_sw128(a_hi + ka), 1u);
+                    const uint32_t kb = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks of W per MMA (K = 8)
+                    // M side: the gathered rows; N side: [Wh ; Wl] (columns 0..31 | 32..63), then Wh alone for Xl
+                    umma_tf32<64>(d, make_desc_sw128(a_hi + ka), make_desc(b_w + kb), ks > 0);
+                    umma_tf32<32>(d, make_desc_sw128(a_lo + ka), make_desc(b_w + kb), 1u);
                 }
-                umma_tf32(d, make_desc(b_hi + 4 * 2 * 128), make_desc_tail(t_hi), 1u);
-                umma_tf32(d, make_desc(b_hi + 4 * 2 * 128), make_desc_tail(t_lo), 1u);
-                umma_tf32(d, make_desc(b_lo + 4 * 2 * 128), make_desc_tail(t_hi), 1u);
+                umma_tf32<64>(d, make_desc_tail(t_hi), make_desc(b_w + 4 * 2 * 128), 1u);
+                umma_tf32<32>(d, make_desc_tail(t_lo), make_desc(b_w + 4 * 2 * 128), 1u);
                 umma_commit(&empty[s]);   // shared-memory stage may be rewritten
                 umma_commit(&tfull[s]);   // accumulator is complete
             }
@@ -198,59 +204,73 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         }
     } else if (warp < TC_EPI_WARPS) {
         // ------------------ epilogue: TMEM -> max over the 32 neighbours -> global ------------------
-        // lane = output channel; the 32 registers of one load are that channel's values for the 32 neighbours
+        // warp = candidate of the tile, lane = neighbour (TMEM lane 32 * warp + lane); columns c and 32 + c are
+        // the two partial sums of channel c. After the butterfly lane o holds channel o's max.
+        const uint32_t lane_base = ((uint32_t)warp * 32u) << 16;
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
-            const int64_t gq0 = tc_tile_cand(i);
+            const int64_t gq = tc_tile_cand(i) + warp;
             mbar_wait(&tfull[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float best[4];
+            float best = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + (uint32_t)s * TC_ACC_COLS + (uint32_t)c * 32u;   // lanes 0..31
+            for (int h = 0; h < 2; ++h) {
+                uint32_t u[16], v[16];
+                const uint32_t taddr = tmem_base + lane_base + (uint32_t)s * TC_ACC_COLS + (uint32_t)h * 16u;
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]),
+                      "=r"(u[15])
+                    : "r"(taddr));
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                      "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                      "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                      "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
+                      "=r"(v[15])
+                    : "r"(taddr + 32u));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float m = __uint_as_float(v[0]);
+                float y[16];
 #pragma unroll
-                for (int o = 1; o < 32; ++o) m = fmaxf(m, __uint_as_float(v[o]));
-                best[c] = m;
+                for (int o = 0; o < 16; ++o) y[o] = __uint_as_float(u[o]) + __uint_as_float(v[o]);
+                // transposing butterfly: 16 values x 32 lanes -> lane l holds the max of value l & 15
+#pragma unroll
+                for (int st = 8; st >= 1; st >>= 1) {
+                    const bool up = (lane & st) != 0;
+#pragma unroll
+                    for (int o = 0; o < st; ++o) {
+                        const float send = up ? y[o] : y[o + st];
+                        const float keep = up ? y[o + st] : y[o];
+                        y[o] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, st));
+                    }
+                }
+                const float m = fmaxf(y[0], __shfl_xor_sync(0xffffffffu, y[0], 16));
+                if ((lane >> 4) == h) best = m;   // channels 16h .. 16h + 15 live in lanes of the same half
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[s]);
             if (fm_C == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (gq0 + c < total_cand) out[(gq0 + c) * 32 + lane] = best[c];
+                if (gq < total_cand) out[gq * 32 + lane] = best;
             } else {
                 // feature-major inside every block of fm_C candidates (one key-point): the logical [32, C] order
                 // cpg.py:34 re-reads (quirk Q4), so that the CPG kernel finds a voxel's 32 values contiguous.
                 // The 8 tiles of a run are 32 consecutive candidates: transposed through shared memory, every
                 // store instruction then writes one feature of 32 consecutive candidates (coalesced).
-                const int col = (int)(i % TC_RUN) * 4;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) sT[lane * 33 + col + c] = best[c];
+                sT[lane * 33 + (int)(i % TC_RUN) * 4 + warp] = best;
                 if (i % TC_RUN == TC_RUN - 1) {
-                    __syncwarp();
-                    const int64_t gq = gq0 - (TC_RUN - 1) * 4 + lane;   // lane = candidate of the run
-                    if (gq < total_cand) {
-                        const int64_t kp = gq / fm_C;
-                        float *o = out + kp * 32 * fm_C + (gq - kp * fm_C);
-#pragma unroll 8
-                        for (int f = 0; f < 32; ++f) o[(int64_t)f * fm_C] = sT[f * 33 + lane];
+                    asm volatile("bar.sync 2, %0;" ::"r"(TC_EPI_WARPS * 32) : "memory");
+                    const int64_t gl = tc_tile_cand(i) - (TC_RUN - 1) * 4 + lane;   // lane = candidate of the run
+                    if (gl < total_cand) {
+                        const int64_t kp = gl / fm_C;
+                        float *o = out + kp * 32 * fm_C + (gl - kp * fm_C);
+#pragma unroll
+                        for (int f = warp * 8; f < warp * 8 + 8; ++f) o[(int64_t)f * fm_C] = sT[f * 33 + lane];
                     }
-                    __syncwarp();
+                    asm volatile("bar.sync 2, %0;" ::"r"(TC_EPI_WARPS * 32) : "memory");
                 }
             }
         }

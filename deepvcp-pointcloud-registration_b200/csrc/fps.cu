@@ -85,13 +85,6 @@ fps_generic_kernel(const T *__restrict__ base, int64_t bs, int64_t ps, int64_t c
 }
 
 // ----------------------------------------------------------------- bucketed --
-__device__ __forceinline__ unsigned expand_bits10(unsigned v) {
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
-}
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -173,7 +166,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
                 float v = (__ldg(p + (int64_t)n * ps + c * cs) - mn[c]) * scale;
                 q[c] = (unsigned)fminf(fmaxf(v, 0.0f), 1023.0f);
             }
-            keys[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+            keys[i] = spatial_key(q[0], q[1], q[2]);
             vals[i] = (unsigned)n;
         } else {
             keys[i] = 0xffffffffu;   // sentinels sort last

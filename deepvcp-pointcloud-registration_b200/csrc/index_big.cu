@@ -96,7 +96,7 @@ ib_run_sort_kernel(Cloud c, int N, int cap, const unsigned *__restrict__ bbox, u
                 const float t = (c.at(b, n, a) - mn[a]) * scale;
                 q[a] = (unsigned)fminf(fmaxf(t, 0.0f), 1023.0f);
             }
-            k[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+            k[i] = spatial_key(q[0], q[1], q[2]);
             v[i] = (unsigned)n;
         } else {
             k[i] = 0xffffffffu;   // unused slots sort behind every point
