@@ -48,8 +48,12 @@ constexpr int TC_A_BYTES = TC_A_SW_BYTES + TC_A_TAIL_BYTES;   // one A plane (hi
 constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one weight plane as the host lays it out (32 channels)
 constexpr int TC_BW_BYTES = TC_B_BYTES;         // the N-side operand is [hi plane ; lo plane]: a 64-row image
 constexpr int TC_ACC_COLS = 64;                 // TMEM columns per accumulator: Xh*Wh + Xl*Wh | Xh*Wl
-constexpr int TC_STAGES = 4;                   // shared-memory A stages == TMEM accumulators
-constexpr int TC_GROUPS = 4;                   // producer groups of 4 warps (one candidate per warp)
+#ifndef DVCP_DFE_GROUPS
+#define DVCP_DFE_GROUPS 3
+#endif
+constexpr int TC_STAGES = DVCP_DFE_GROUPS;     // shared-memory A stages == TMEM accumulators
+constexpr int TC_GROUPS = DVCP_DFE_GROUPS;     // producer groups of 4 warps (one candidate per warp); group g owns stage g
+constexpr unsigned TC_TMEM_COLS = TC_STAGES * 64 <= 256 ? 256u : 512u;   // allocation: a power of two
 constexpr int TC_EPI_WARPS = 4;                // warp w reads TMEM lanes 32w..32w+31 = the neighbours of candidate w
 constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS - 1
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
@@ -60,8 +64,9 @@ constexpr int TC_T_BYTES = 32 * 33 * 4;        // epilogue transposition tile (f
 constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + TC_T_BYTES + 1024;   // + alignment slack
 
 // first candidate of this CTA's i-th tile: runs of TC_RUN consecutive tiles, the runs dealt round-robin to the CTAs
-__device__ __forceinline__ int64_t tc_tile_cand(int64_t i) {
-    return (((i / TC_RUN) * gridDim.x + blockIdx.x) * TC_RUN + (i % TC_RUN)) * 4;
+__device__ __forceinline__ int64_t tc_tile_cand(int i) {   // (tile counts fit 32 bits: checked by the launcher)
+    const unsigned t = ((unsigned)i / TC_RUN * gridDim.x + blockIdx.x) * TC_RUN + ((unsigned)i % TC_RUN);
+    return (int64_t)t * 4;
 }
 
 // byte offset of element (row r, column k) in the K-major, no-swizzle canonical layout:
@@ -126,10 +131,11 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                  : "memory");
 }
 
+template <bool PF>   // PF: weights indexed by feature (quirk Q7), else by neighbour
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__restrict__ tfeat,
                   const float *__restrict__ kdist, const int32_t *__restrict__ kidx, int N, int64_t total_cand,
-                  int64_t Q, const float *__restrict__ Bhi, const float *__restrict__ Blo, int per_feature_weight,
+                  int64_t Q, const float *__restrict__ Bhi, const float *__restrict__ Blo, float inv_Q,
                   int fm_C, float *__restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
@@ -158,7 +164,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     }
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((unsigned)(TC_ACC_COLS * TC_STAGES))
+                     "r"(TC_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -172,12 +178,12 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     const int64_t ntiles = (total_cand + 3) / 4;
     const int64_t nruns = (ntiles + TC_RUN - 1) / TC_RUN;
     // (the tiles of a last, partial run beyond ntiles are dead: every role skips candidates >= total_cand)
-    const int64_t my_tiles = blockIdx.x < nruns ? (nruns - blockIdx.x + gridDim.x - 1) / gridDim.x * TC_RUN : 0;
+    const int my_tiles = blockIdx.x < nruns ? (int)((nruns - blockIdx.x + gridDim.x - 1) / gridDim.x * TC_RUN) : 0;
 
     if (warp == TC_MMA_WARP) {
         // ------------------------------ MMA issuer ------------------------------
         const uint32_t a_base = smem_u32(sA), b_w = smem_u32(sB);   // [Wh ; Wl], 64 rows
-        for (int64_t i = 0; i < my_tiles; ++i) {
+        for (int i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
             mbar_wait(&full[s], ph);            // A(i) is in shared memory
@@ -207,7 +213,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         // warp = candidate of the tile, lane = neighbour (TMEM lane 32 * warp + lane); columns c and 32 + c are
         // the two partial sums of channel c. After the butterfly lane o holds channel o's max.
         const uint32_t lane_base = ((uint32_t)warp * 32u) << 16;
-        for (int64_t i = 0; i < my_tiles; ++i) {
+        for (int i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
             const int64_t gq = tc_tile_cand(i) + warp;
@@ -281,22 +287,21 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         // 4g + rsub, so a quarter-warp reads one whole 128-byte line (4 wavefronts per LDG.128) and
         // writes the 8 chunks of one swizzled 128-byte row (conflict-free STS.128).
         const int pw = warp - TC_EPI_WARPS, group = pw >> 2, cw = pw & 3;   // cw: candidate of the tile
-        float2 *myw = sW + pw * 32;
+        float *wsh = reinterpret_cast<float *>(sW + pw * 32), *wsl = wsh + 32;
         const int rsub = lane >> 3, chunk = lane & 7;
-        const bool small = total_cand < (1ll << 31);
         const bool xyz4 = txyz.ps == 4 && txyz.cs == 1 && txyz.bs % 4 == 0 && (reinterpret_cast<uintptr_t>(txyz.p) & 15) == 0;
-        // columns 36..39 are zero padding: written once per stage, never touched again
-        for (int s = group; s < TC_STAGES; s += TC_GROUPS) {
-            unsigned char *thi = sA + (size_t)s * 2 * TC_A_BYTES + 2 * TC_A_SW_BYTES, *tlo = thi + TC_A_TAIL_BYTES;
-            const int r0 = cw * 32 + lane;
-            *reinterpret_cast<float4 *>(thi + tc_tail_off(r0, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(tlo + tc_tail_off(r0, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // the zero columns of stage s are written by warps of different groups than the one that later
-        // arrives on full[s]: order them before any arrive with a barrier among the producer warps
-        asm volatile("bar.sync 1, %0;" ::"r"(TC_PROD_WARPS * 32) : "memory");
+        // stage s == group: a group always rebuilds its own stage
+        unsigned char *const ahi = sA + (size_t)group * 2 * TC_A_BYTES;
+        unsigned char *const thi = ahi + 2 * TC_A_SW_BYTES + tc_tail_off(cw * 32 + lane, 0);
+        // columns 36..39 are zero padding: written once, never touched again
+        *reinterpret_cast<float4 *>(thi + 128) = make_float4(0.f, 0.f, 0.f, 0.f);                     // tc_tail_off(r, 4)
+        *reinterpret_cast<float4 *>(thi + TC_A_TAIL_BYTES + 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+        // row 4 g + rsub of candidate cw: 128-byte rows, the 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+        // (SWIZZLE_128B); r & 7 alternates between rsub and rsub + 4, so two bases + immediates address all rows
+        unsigned char *const row0 = ahi + (cw * 32 + rsub) * 128 + ((chunk ^ rsub) << 4);
+        unsigned char *const row1 = ahi + (cw * 32 + rsub) * 128 + ((chunk ^ (rsub + 4)) << 4);
         // idx / dist of the first tile; the next tile's are fetched while this one is built
-        int64_t i = group;
+        int i = group;
         int id_n = 0;
         float dj_n = 0.f;
         if (i < my_tiles) {
@@ -306,30 +311,33 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 dj_n = __ldg(kdist + gq * 32 + lane);
             }
         }
-        for (; i < my_tiles; i += TC_GROUPS) {
-            const int s = (int)(i % TC_STAGES);
-            const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
+        for (unsigned it = 0; i < my_tiles; i += TC_GROUPS, ++it) {
             const int64_t gq = tc_tile_cand(i) + cw;   // this warp's candidate
             const bool live = gq < total_cand;
             const int id = id_n;
             const float djf = dj_n;
             {
-                const int64_t i2 = i + TC_GROUPS;
+                const int i2 = i + TC_GROUPS;
                 const int64_t gq2 = tc_tile_cand(i2) + cw;
                 if (i2 < my_tiles && gq2 < total_cand) {
                     id_n = __ldg(kidx + gq2 * 32 + lane);
                     dj_n = __ldg(kdist + gq2 * 32 + lane);
                 }
             }
-            const int b = live ? (small ? (int)((unsigned)gq / (unsigned)Q) : (int)(gq / Q)) : 0;
+            // cloud of the candidate: gq / Q from the float quotient, corrected by at most one either way
+            int b = 0;
+            if (live) {
+                b = (int)((float)gq * inv_Q);
+                const int64_t lo = (int64_t)b * Q;
+                b += (gq - lo >= Q) - (gq < lo);
+            }
             // ---- gather first (long latency) ----
             float4 f[8];
-            const float *fbase = tfeat + (int64_t)b * N * 32;
+            const float4 *fbase = reinterpret_cast<const float4 *>(tfeat + (int64_t)b * N * 32) + chunk;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int rid = __shfl_sync(0xffffffffu, id, 4 * g + rsub);
-                f[g] = live ? __ldg(reinterpret_cast<const float4 *>(fbase + (int64_t)rid * 32 + chunk * 4))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                f[g] = live ? __ldg(fbase + rid * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             // raw coordinate loads are issued here, consumed after the weight arithmetic below
             float px = 0.f, py = 0.f, pz = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
@@ -351,10 +359,9 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             const double wl = live ? dj / sum : 0.0;
             const float whi = (float)wl, wlo = (float)(wl - (double)whi);
             // per-feature mode: the weights of my 4 channels 4 * chunk .. 4 * chunk + 3, high parts and low parts as
-            // two float4 (pairs of adjacent channels feed the packed FMUL2 / FFMA2 below without moves)
+            // two float4 (pairs of adjacent channels feed the packed FMUL2 / FFMA2 below)
             float4 wqh = make_float4(0.f, 0.f, 0.f, 0.f), wql = wqh;
-            if (per_feature_weight) {
-                float *wsh = reinterpret_cast<float *>(myw), *wsl = wsh + 32;
+            if (PF) {
                 __syncwarp();
                 wsh[lane] = whi;
                 wsl[lane] = wlo;
@@ -364,18 +371,15 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             }
             // my neighbour's local coordinates + bias column
             const float4 loc = live ? make_float4(px - cx, py - cy, pz - cz, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mbar_wait(&empty[s], ph ^ 1);   // MMAs of tile i - TC_STAGES have finished reading stage s
-            unsigned char *ahi = sA + (size_t)s * 2 * TC_A_BYTES, *alo = ahi + TC_A_SW_BYTES;
-            unsigned char *thi = ahi + 2 * TC_A_SW_BYTES, *tlo = thi + TC_A_TAIL_BYTES;
+            mbar_wait(&empty[group], (it & 1) ^ 1);   // the MMAs of this group's previous tile have read the stage
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const int row = 4 * g + rsub, trow = cw * 32 + row;
                 float2 h01, h23, l01, l23;   // weight pairs
-                if (per_feature_weight) {
+                if (PF) {
                     h01 = make_float2(wqh.x, wqh.y); h23 = make_float2(wqh.z, wqh.w);
                     l01 = make_float2(wql.x, wql.y); l23 = make_float2(wql.z, wql.w);
                 } else {
-                    const float rhi = __shfl_sync(0xffffffffu, whi, row), rlo = __shfl_sync(0xffffffffu, wlo, row);
+                    const float rhi = __shfl_sync(0xffffffffu, whi, 4 * g + rsub), rlo = __shfl_sync(0xffffffffu, wlo, 4 * g + rsub);
                     h01 = h23 = make_float2(rhi, rhi);
                     l01 = l23 = make_float2(rlo, rlo);
                 }
@@ -393,9 +397,9 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 const float2 d01 = __ffma2_rn(make_float2(hv.x, hv.y), m1, v01);   // v - hi, exact
                 const float2 d23 = __ffma2_rn(make_float2(hv.z, hv.w), m1, v23);
                 lv = make_float4(d01.x, d01.y, d23.x, d23.y);
-                const int off = trow * 128 + ((chunk ^ (trow & 7)) << 4);   // SWIZZLE_128B
-                *reinterpret_cast<float4 *>(ahi + off) = hv;
-                *reinterpret_cast<float4 *>(alo + off) = lv;
+                unsigned char *const dst = ((g & 1) ? row1 : row0) + g * 512;
+                *reinterpret_cast<float4 *>(dst) = hv;
+                *reinterpret_cast<float4 *>(dst + TC_A_SW_BYTES) = lv;
             }
             {
                 float4 hv, lv;
@@ -407,20 +411,19 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                     hp[e] = t;
                     lp[e] = le[e] - t;
                 }
-                const int off = tc_tail_off(cw * 32 + lane, 0);
-                *reinterpret_cast<float4 *>(thi + off) = hv;
-                *reinterpret_cast<float4 *>(tlo + off) = lv;
+                *reinterpret_cast<float4 *>(thi) = hv;
+                *reinterpret_cast<float4 *>(thi + TC_A_TAIL_BYTES) = lv;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
+            if (lane == 0) mbar_arrive(&full[group]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((unsigned)(TC_ACC_COLS * TC_STAGES))
+                     "r"(TC_TMEM_COLS)
                      : "memory");
     }
 }
@@ -445,12 +448,19 @@ extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const fl
         return DVCP_E_ARG;
     const int64_t total = (int64_t)B * Q;
     const int64_t ntiles = (total + 3) / 4;
-    DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    if (ntiles + TC_RUN * DVCP_NUM_SMS >= (1ll << 29) || (int64_t)N * 8 >= (1ll << 31)) return DVCP_E_UNSUPPORTED;   // 32-bit tile / row arithmetic
+    DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     int64_t grid = DVCP_NUM_SMS;   // persistent: one CTA per SM
     if (grid > ntiles) grid = ntiles;
     // one cloud stride for the whole batch: tgt_xyz is addressed with b = candidate / Q
-    dfe_tgt_tc_kernel<<<(unsigned)grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
-        cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, (quirks >> 1) & 1, feature_major_c, out);
+    const float inv_Q = 1.0f / (float)Q;
+    if ((quirks >> 1) & 1)
+        dfe_tgt_tc_kernel<true><<<(unsigned)grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
+            cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, inv_Q, feature_major_c, out);
+    else
+        dfe_tgt_tc_kernel<false><<<(unsigned)grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(
+            cand, as_cloud(tgt_xyz), tgt_feat, knn_dist, knn_idx, N, total, Q, b_hi, b_lo, inv_Q, feature_major_c, out);
     DVCP_CHECK_LAUNCH();
     return 0;
 }
