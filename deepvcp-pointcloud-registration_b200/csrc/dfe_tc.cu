@@ -255,6 +255,8 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 }
                 const float m = fmaxf(y[0], __shfl_xor_sync(0xffffffffu, y[0], 16));
                 if ((lane >> 4) == h) best = m;   // channels 16h .. 16h + 15 live in lanes of the same half
+                // (one CREDUX.MAX.F32 per channel instead of the butterfly: fewer instructions, measured slower,
+                //  0.852 against 0.824 ms)
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -331,33 +333,57 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 const int64_t lo = (int64_t)b * Q;
                 b += (gq - lo >= Q) - (gq < lo);
             }
-            // ---- gather first (long latency) ----
+            // ---- gather first (long latency). Every load is unconditional: a dead candidate (beyond total_cand)
+            //      has id = 0, b = 0 and reads row 0 -- its rows are built from finite garbage and never stored.
+            //      (Predicated loads made the compiler copy every result out of a temporary before the next load
+            //      was issued: the eight gathers of a candidate were serialised on their latency.) ----
             float4 f[8];
             const float4 *fbase = reinterpret_cast<const float4 *>(tfeat + (int64_t)b * N * 32) + chunk;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int rid = __shfl_sync(0xffffffffu, id, 4 * g + rsub);
-                f[g] = live ? __ldg(fbase + rid * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+                f[g] = __ldg(fbase + rid * 8);
             }
             // raw coordinate loads are issued here, consumed after the weight arithmetic below
-            float px = 0.f, py = 0.f, pz = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
-            if (live) {
-                if (xyz4) {
-                    const float4 pp = __ldg(reinterpret_cast<const float4 *>(txyz.p + (int64_t)b * txyz.bs) + id);
-                    px = pp.x; py = pp.y; pz = pp.z;
-                } else {
-                    px = txyz.at(b, id, 0); py = txyz.at(b, id, 1); pz = txyz.at(b, id, 2);
-                }
-                cx = __ldg(cand + gq * 3); cy = __ldg(cand + gq * 3 + 1); cz = __ldg(cand + gq * 3 + 2);
+            float px, py, pz;
+            if (xyz4) {
+                const float4 pp = __ldg(reinterpret_cast<const float4 *>(txyz.p + (int64_t)b * txyz.bs) + id);
+                px = pp.x; py = pp.y; pz = pp.z;
+            } else {
+                px = txyz.at(b, id, 0); py = txyz.at(b, id, 1); pz = txyz.at(b, id, 2);
             }
-            // ---- w = dist / sum(dist) in float64 (get_cat_feat_tgt.py:57-58), carried as a float pair: the
-            //      product with a float32 feature is then float32(double(f) * w) up to one rounding in 2^-48 ----
+            const float *cp = cand + (live ? gq : 0) * 3;
+            const float cx = __ldg(cp), cy = __ldg(cp + 1), cz = __ldg(cp + 2);
+            // ---- w = dist / sum(dist), float64 in the reference (get_cat_feat_tgt.py:57-58), carried as a float
+            //      pair (whi + wlo = w to ~2^-43): the product with a float32 feature is then
+            //      float32(double(f) * w) up to one rounding far below float32. Formed with error-free float32
+            //      transformations: the FP64 unit of this part is a slow shared pipe (ncu: 'math pipe throttle' on
+            //      every DADD / DFMA of the float64 form, a fifth of the producers' time) ----
+#ifdef DVCP_DFE_W64
             const double dj = (double)djf;
             double sum = dj;
 #pragma unroll
             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             const double wl = live ? dj / sum : 0.0;
             const float whi = (float)wl, wlo = (float)(wl - (double)whi);
+#else
+            float sh = djf, sl = 0.f;   // sum of the 32 distances as sh + sl (TwoSum per butterfly round: symmetric, so
+#pragma unroll                      // every lane ends with the same pair)
+            for (int o = 16; o; o >>= 1) {
+                const float oh = __shfl_xor_sync(0xffffffffu, sh, o), ol = __shfl_xor_sync(0xffffffffu, sl, o);
+                const float t = __fadd_rn(sh, oh), bb = __fsub_rn(t, sh);
+                const float e = __fadd_rn(__fsub_rn(sh, __fsub_rn(t, bb)), __fsub_rn(oh, bb));
+                sl = __fadd_rn(__fadd_rn(sl, ol), e);
+                sh = t;
+            }
+            const float S = __fadd_rn(sh, sl), Sl = __fsub_rn(sl, __fsub_rn(S, sh));
+            const float rcp = __fdividef(1.0f, S);
+            const float qh = __fmul_rn(djf, rcp);
+            const float rem = __fmaf_rn(-qh, Sl, __fmaf_rn(-qh, S, djf));   // d - qh (S + Sl)
+            const float ql = __fmul_rn(rem, rcp);
+            float whi = __fadd_rn(qh, ql), wlo = __fsub_rn(ql, __fsub_rn(whi, qh));
+            if (!live) whi = wlo = 0.f;
+#endif
             // per-feature mode: the weights of my 4 channels 4 * chunk .. 4 * chunk + 3, high parts and low parts as
             // two float4 (pairs of adjacent channels feed the packed FMUL2 / FFMA2 below)
             float4 wqh = make_float4(0.f, 0.f, 0.f, 0.f), wql = wqh;
@@ -370,7 +396,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 wql = *reinterpret_cast<const float4 *>(wsl + chunk * 4);
             }
             // my neighbour's local coordinates + bias column
-            const float4 loc = live ? make_float4(px - cx, py - cy, pz - cz, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 loc = make_float4(px - cx, py - cy, pz - cz, 1.0f);
             mbar_wait(&empty[group], (it & 1) ^ 1);   // the MMAs of this group's previous tile have read the stage
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
