@@ -83,6 +83,11 @@ class DeepVCP(nn.Module):
     def forward(self, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=False, topk_override=None):
         """src_pts, tgt_pts [B,C_in,N]; R_init [B,3,3] float64; t_init [1,3] (unused by
         the reference, quirk Q6) -> (src_keypts [B,K,3], tgt_vcp [B,K,3])."""
+        if self.training:
+            # train.py:93-105: batch statistics in the BatchNorm layers and an autograd graph (training.py)
+            from . import training
+            return training.forward(self, src_pts, tgt_pts, R_init, t_init, starts=starts, keep_stages=keep_stages,
+                                    topk_override=topk_override)
         fe = self.extract_features(src_pts, tgt_pts, starts)
         return self.match(fe, R_init, keep_stages=keep_stages, topk_override=topk_override, t_init=t_init)
 
@@ -97,7 +102,8 @@ class DeepVCP(nn.Module):
         state match() continues from. Split out so that a stream of batches can run this half (few SMs,
         long) beside the second half of the previous batch (pipeline.StreamedRegistration)."""
         if self.training:
-            raise RuntimeError("DeepVCP (b200) is the inference path: call .eval() first")
+            raise RuntimeError("extract_features / match are the inference kernels: call .eval() first (train mode goes "
+                               "through forward(), see training.py)")
         for x in (src_pts, tgt_pts):
             if x.dtype not in (torch.float32, torch.float64):
                 raise RuntimeError("clouds must be float32 or float64, got %s" % x.dtype)

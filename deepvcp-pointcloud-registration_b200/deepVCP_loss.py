@@ -1,5 +1,5 @@
-"""Pose solve -- deepVCP_loss.py:13-90 of the reference (loss value itself is
-training-only and out of scope)."""
+"""Pose solve and loss -- deepVCP_loss.py:13-121 of the reference. The kernels compute values; a prediction
+that carries a gradient goes through the autograd form of training.py."""
 import torch
 
 from . import functional as F_
@@ -27,8 +27,11 @@ def svd_optimization(x, y_pred, R_true, t_true, quirks=QUIRKS_REFERENCE):
 
 
 def deepVCP_loss(x, y_pred, R_true, t_true, alpha):
-    """Reference :105-121 (value only: the CUDA path has no backward). x, y_pred [B,N,3]; returns
+    """Reference :105-121 (a y_pred with requires_grad takes the differentiable path of training.py). x, y_pred [B,N,3]; returns
     (loss, R [B,3,3], t [B,3,1]): alpha * L1(y_true_inliers, y_pred2) + (1 - alpha) * |mean(y_pred2 - y_true_inliers)|."""
+    if y_pred.requires_grad:
+        from . import training
+        return training.loss(x, y_pred, R_true, t_true, alpha)
     xx = x.permute(0, 2, 1).double()
     yy = y_pred.permute(0, 2, 1).double()
     R, t, x_inl, y_opt = svd_optimization(xx, yy, R_true, t_true)

@@ -107,7 +107,12 @@ class PointNetSetAbstraction(nn.Module):
         if self.group_all:
             raise NotImplementedError("group_all=True is not on the DeepVCP path")
         if self.training:
-            raise RuntimeError("train-mode BatchNorm statistics are out of scope: call .eval()")
+            # batch statistics + autograd graph: sampling and ball query on the kernels, the shared MLP with
+            # torch operators (training.py; reference :176-202 in train mode)
+            from . import training
+            new_xyz, feats, fps = training.set_abstraction(self, xyz, points, start)
+            out = (new_xyz.permute(0, 2, 1), feats.permute(0, 2, 1))
+            return out + (fps.int(),) if return_fps else out
         require_cuda(xyz, points)
         _float_cloud(xyz)
         B, _, N = xyz.shape

@@ -139,10 +139,11 @@ def make_model(use_normal: bool, n_points: int, seed: int = 0):
     return model
 
 
-def forward(model, src, tgt, R_init, t_init, r: float, s: float, record: dict = None):
+def forward(model, src, tgt, R_init, t_init, r: float, s: float, record: dict = None, grad: bool = False):
     """Reference DeepVCP.forward under S5 (and S6 for 3-channel clouds).
 
-    `record`, if given, is filled with the stage-boundary tensors.
+    `record`, if given, is filled with the stage-boundary tensors. grad=True keeps the autograd graph
+    (training fixtures: train.py:105-123).
     """
     m = load()
     dv = m.deepVCP
@@ -212,7 +213,7 @@ def forward(model, src, tgt, R_init, t_init, r: float, s: float, record: dict = 
     model.WL.forward = wl
     model.FE1.forward = fe
     try:
-        with torch.no_grad(), quiet():
+        with (contextlib.nullcontext() if grad else torch.no_grad()), quiet():
             if src.shape[1] == 6:
                 kp, vcp = model(src, tgt, R_init, t_init)
             else:

@@ -252,12 +252,74 @@ def dtype_cases():
                  pair_id=4, stride=32, dtype="mixed")
 
 
+def train_case(name, kind, n_points, r, s, model_seed, rng_seed, pair_id=0, dtype="f32", lr=0.001):
+    """One training step of the UNMODIFIED reference exactly as train.py:93-123 drives it: model.train(),
+    forward, deepVCP_loss(alpha=0.5), backward, Adam(lr).step(). Stored: the inputs, the initial state_dict,
+    the indices the forward drew / chose (FPS starts, top-k), the loss, R / t, the gradient of every parameter
+    that received one, and the state_dict after the step (BatchNorm running statistics included)."""
+    use_normal = kind == "modelnet"
+    src, tgt, R, t = syn.make_batch(kind, [pair_id], n_points, dtype=dtype)
+    model = rs.make_model(use_normal, n_points, seed=model_seed)
+    model.train()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    m = rs.load()
+    pu = m.pointnet2_utils
+    fps_log = []
+    orig_fps = pu.farthest_point_sample
+
+    def fps(xyz, npoint):
+        out = orig_fps(xyz, npoint)
+        fps_log.append(out.clone())
+        return out
+
+    pu.farthest_point_sample = fps
+    rec = {}
+    optim = torch.optim.Adam(model.parameters(), lr=lr)
+    try:
+        torch.manual_seed(rng_seed)
+        kp, vcp = rs.forward(model, src, tgt, R, torch.zeros(1, 3), r, s, rec, grad=True)
+    finally:
+        pu.farthest_point_sample = orig_fps
+    optim.zero_grad()
+    with rs.quiet():
+        loss, Rp, tp = m.deepVCP_loss.deepVCP_loss(kp, vcp, R, t.view(1, 3, 1), alpha=0.5)
+    loss.backward()
+    out = {
+        "kind": kind, "r": r, "s": s, "n_points": n_points, "dtype": dtype, "pair_id": pair_id, "lr": lr,
+        "src": npy(src), "tgt": npy(tgt), "R": npy(R), "t": npy(t),
+        "starts": np.array([int(fps_log[0][0, 0]), int(fps_log[1][0, 0]), int(fps_log[2][0, 0])]),
+        "topk_idx": npy(rec["topk_idx"]).astype(np.int32),
+        "src_fe_feat": npy(rec["src_fe_feat"]), "vcp": npy(vcp), "src_keypts": npy(kp),
+        "loss": npy(loss), "R_pred": npy(Rp), "t_pred": npy(tp),
+    }
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            out["grad/" + k] = npy(p.grad)
+    optim.step()
+    for k, v in sd0.items():
+        out["sd/" + k] = npy(v)
+    for k, v in model.state_dict().items():
+        out["sd_after/" + k] = npy(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024),
+          "loss %.6f, %d parameters with a gradient" % (float(loss), sum(k.startswith("grad/") for k in out)))
+
+
+def train_cases():
+    train_case("train_modelnet_n512_g5", "modelnet", 512, 0.8, 0.4, model_seed=7, rng_seed=31, pair_id=2)
+    train_case("train_modelnet_f64_n512_g5", "modelnet", 512, 0.8, 0.4, model_seed=8, rng_seed=32, pair_id=6, dtype="f64")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "native":
         native_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dtypes":
         dtype_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_cases()
         sys.exit(0)
     primitives_case()
     native_case()
@@ -266,3 +328,4 @@ if __name__ == "__main__":
     forward_case("fwd_kitti_n2048_g7", "kitti", 2048, syn.grid_radius(7), 0.4, model_seed=2, rng_seed=9,
                  pair_id=1, stride=32)
     dtype_cases()
+    train_cases()
