@@ -77,8 +77,11 @@ def test_no_cpu_fallback(dv):
         model(x, x, torch.eye(3, dtype=torch.float64)[None], torch.zeros(1, 3))
     with pytest.raises(RuntimeError, match="CUDA"):
         dv.farthest_point_sample(torch.rand(1, 10, 3), 4)
+    # train mode (training.py) has no CPU path either, and the inference halves refuse a module in train mode
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dv.DeepVCP(use_normal=True, npoint=64)(x, x, torch.eye(3, dtype=torch.float64)[None], torch.zeros(1, 3))
     with pytest.raises(RuntimeError, match="eval"):
-        dv.DeepVCP(use_normal=True)(x, x, torch.eye(3, dtype=torch.float64)[None], torch.zeros(1, 3))
+        dv.DeepVCP(use_normal=True, npoint=64).extract_features(x, x)
 
 
 def test_product_does_not_import_oracle():
