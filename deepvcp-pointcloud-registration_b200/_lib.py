@@ -102,7 +102,9 @@ QUIRK_PER_FEATURE_WEIGHT = 2    # Q7: distance weight indexed by feature (get_ca
 QUIRK_COST_VOLUME_RESHAPE = 4   # Q4: (feature, candidate) axes scrambled by the reshape (deepVCP.py:106, cpg.py:34)
 QUIRK_IGNORE_T_INIT = 8         # Q6: t_init never added (deepVCP.py:86-91)
 QUIRK_NO_REFLECTION_FIX = 16    # Q10: R = V U^T may have det = -1 (deepVCP_loss.py:36-40)
-QUIRKS_REFERENCE = 31
+QUIRK_FPS_ORDER_MISMATCH = 32   # Q5: rows of the FPS-ordered feature tables addressed with original-order / key-point-local indices
+                                #     (deepVCP.py:35,46,61; get_cat_feat_tgt.py:85) -- host-side wiring, no kernel reads this bit
+QUIRKS_REFERENCE = 63
 QUIRKS_INTENDED = 0
 
 

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
-from ._lib import QUIRK_COST_VOLUME_RESHAPE, QUIRKS_REFERENCE, cloud_cm, cloud_pm, require_cuda
+from ._lib import QUIRK_COST_VOLUME_RESHAPE, QUIRK_FPS_ORDER_MISMATCH, QUIRKS_REFERENCE, cloud_cm, cloud_pm, require_cuda
 from .cpg import cpg
 from .deep_feat_embedding import feat_embedding_layer
 from .deep_feat_extraction import feat_extraction_layer
@@ -232,8 +232,20 @@ class DeepVCP(nn.Module):
             topk = F_.topk(scores, K) if topk_override is None else topk_override.to(dev).view(B, K)
             mark("weighting_topk")
             dfe = self.DFE.params()
+            kp_rows, kp_feat = topk, sfeat
+            if not (self.quirks & QUIRK_FPS_ORDER_MISMATCH):
+                # intended wiring (Q5): row k of the feature table belongs to point fps[k], so the key-point
+                # coordinates are those of fps[topk] (the reference gathers src_pts[:, topk], deepVCP.py:35,46), the
+                # key-points' neighbourhood features are the key-points' own rows (the reference reads rows 0..63 of
+                # the whole table with key-point-local indices, :61), and the target features are addressed by
+                # original point index like the KNN result that indexes them (get_cat_feat_tgt.py:85)
+                kp_rows = torch.gather(sfps.long(), 1, topk)
+                kp_feat = F_.gather_rows(sfeat, topk.int())
+                t_orig = torch.empty_like(tfeat)
+                t_orig.scatter_(1, tfps.long().unsqueeze(-1).expand(-1, -1, tfeat.shape[-1]), tfeat)
+                tfeat = t_orig
             keypts, picked, cat, src_dfe, centres = F_.keypoint_stage(
-                src, topk, starts[1], sfeat, R, self.group_radius, ns, dfe, self.quirks,
+                src, kp_rows, starts[1], kp_feat, R, self.group_radius, ns, dfe, self.quirks,
                 want_cat=keep_stages, want_picked=keep_stages, t_init=t_init)
             # candidates, KNN, target-side embedding
             G = F_.grid_size(self.r, self.s)

@@ -25,7 +25,7 @@ import contextlib
 import torch
 import torch.nn.functional as F
 
-from ._lib import QUIRK_COST_VOLUME_RESHAPE, QUIRK_IGNORE_T_INIT, QUIRK_KEYPOINT_VIEW, QUIRK_PER_FEATURE_WEIGHT, require_cuda
+from ._lib import QUIRK_COST_VOLUME_RESHAPE, QUIRK_FPS_ORDER_MISMATCH, QUIRK_IGNORE_T_INIT, QUIRK_KEYPOINT_VIEW, QUIRK_PER_FEATURE_WEIGHT, require_cuda
 from .get_cat_feat_src import Get_Cat_Feat_Src
 from .knn_cuda import KNN
 from .pointnet2_utils import farthest_point_sample, query_ball_point, sample_and_group
@@ -120,12 +120,14 @@ def forward(model, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=Fa
         scores = model.WL.fc3(model.WL.fc2(model.WL.fc1(sfeat)))
         topk = (torch.topk(scores, K, dim=1).indices.view(B, K) if topk_override is None
                 else topk_override.to(dev).view(B, K))
-        g = torch.gather(src, 2, topk.view(B, 1, K).expand(-1, C_in, -1))               # [B,C_in,K]
+        intended_order = not (q & QUIRK_FPS_ORDER_MISMATCH)                             # Q5, see DeepVCP.match
+        rows = torch.gather(sfps, 1, topk) if intended_order else topk
+        g = torch.gather(src, 2, rows.view(B, 1, K).expand(-1, C_in, -1))               # [B,C_in,K]
         keypts = g.reshape(B, K, C_in) if q & QUIRK_KEYPOINT_VIEW else g.permute(0, 2, 1).contiguous()   # Q3
         # grouping among the key-points (deepVCP.py:54-56)
         _, grouped, picked = sample_and_group(K, model.group_radius, ns, keypts[:, :, :3].contiguous(), None,
                                               returnidx=True, start=starts[1])
-    src_keyfeats = _gather_rows(sfeat, picked)                                          # deepVCP.py:61 (Q5)
+    src_keyfeats = _gather_rows(_gather_rows(sfeat, topk) if intended_order else sfeat, picked)   # deepVCP.py:61 (Q5)
     src_cat = Get_Cat_Feat_Src()(keypts, grouped, src_keyfeats)
     # target side
     tgt_xyz = tgt[:, :3, :].permute(0, 2, 1).contiguous()
@@ -140,6 +142,8 @@ def forward(model, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=Fa
         dist, idx = KNN(k=ns, transpose_mode=True)(tgt_xyz, cand.view(B, K * C, 3))     # get_cat_feat_tgt.py:45-52
         w = dist / torch.sum(dist, dim=2, keepdim=True, dtype=torch.float64)            # :57-58, float64
         local = _gather_rows(tgt_xyz, idx).view(B, K, C, ns, 3) - cand.unsqueeze(3)     # :86-89
+    if intended_order:   # feature rows by original point index, like the KNN indices that address them
+        tfeat = torch.zeros_like(tfeat).scatter(1, tfps.unsqueeze(-1).expand(-1, -1, 32), tfeat)
     picked_feat = _gather_rows(tfeat, idx).view(B, K, C, ns, 32)                        # :85
     if q & QUIRK_PER_FEATURE_WEIGHT:                                                    # :65,92 (Q7): weight by feature
         wmap = w.view(B, K, C, 1, ns)

@@ -54,7 +54,10 @@ extern "C" {
                                              host-side: selects `layout` of dvcp_cpg                                  */
 #define DVCP_QUIRK_IGNORE_T_INIT       8  /* Q6  deepVCP.py:86-91     t_init never added to the transformed key-points */
 #define DVCP_QUIRK_NO_REFLECTION_FIX  16  /* Q10 deepVCP_loss.py:36-40 R = V U^T may have det = -1                     */
-#define DVCP_QUIRKS_REFERENCE         31
+#define DVCP_QUIRK_FPS_ORDER_MISMATCH 32  /* Q5  deepVCP.py:35,46,61; get_cat_feat_tgt.py:85  feature rows (FPS order) addressed with
+                                              original-order / key-point-local indices. Wiring above the kernels: the caller
+                                              passes the tables / indices of the mode it wants; no entry point reads this bit */
+#define DVCP_QUIRKS_REFERENCE         63
 
 typedef void *dvcp_stream_t;
 

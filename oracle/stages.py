@@ -266,8 +266,8 @@ def grid_size(r, s):
 
 
 QUIRK_KEYPOINT_VIEW, QUIRK_PER_FEATURE_WEIGHT, QUIRK_COST_VOLUME_RESHAPE, QUIRK_IGNORE_T_INIT, \
-    QUIRK_NO_REFLECTION_FIX = 1, 2, 4, 8, 16
-QUIRKS_REFERENCE = 31
+    QUIRK_NO_REFLECTION_FIX, QUIRK_FPS_ORDER_MISMATCH = 1, 2, 4, 8, 16, 32
+QUIRKS_REFERENCE = 63
 
 
 def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsample=32,
@@ -288,12 +288,17 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
         sd, src_pts, starts[0], radius=fe_radius, nsample=fe_nsample, chained=chained_fe)
     o["scores"] = weighting_scores(sd, o["src_fe_feat"])
     o["topk_idx"] = topk_indices(o["scores"], k_topk) if topk_override is None else topk_override
-    kp = gather_keypoints(src_pts, o["topk_idx"], bool(quirks & QUIRK_KEYPOINT_VIEW))   # [B,64,C_in]
+    # Q5 (deepVCP.py:35,46,61; get_cat_feat_tgt.py:85): the feature tables are in FPS order, the reference addresses them
+    # with original-order / key-point-local indices. Clear bit: key-point k is point fps[topk[k]], its neighbourhood
+    # features are the key-points' own rows, the target features are addressed by original point index.
+    mismatch = bool(quirks & QUIRK_FPS_ORDER_MISMATCH)
+    rows = o["topk_idx"] if mismatch else torch.gather(o["src_fps"], 1, o["topk_idx"])
+    kp = gather_keypoints(src_pts, rows, bool(quirks & QUIRK_KEYPOINT_VIEW))   # [B,64,C_in]
     o["src_keypts_full"] = kp
     kp_xyz = kp[:, :, :3].contiguous()
     new_xyz, grouped, picked, kp_fps = sample_and_group(k_topk, 1, nsample, kp_xyz, None, starts[1])
     o["picked_idx"], o["kp_fps"], o["src_grouped"] = picked, kp_fps, grouped
-    keyfeats = index_points(o["src_fe_feat"], picked)                 # Q5
+    keyfeats = index_points(o["src_fe_feat"] if mismatch else index_points(o["src_fe_feat"], o["topk_idx"]), picked)
     o["src_cat"] = cat_feat_src(kp, grouped, keyfeats)
     tgt_xyz = tgt_pts[:, :3, :].permute(0, 2, 1).contiguous()
     o["tgt_fe_xyz"], o["tgt_fe_feat"], o["tgt_fps"] = feat_extraction(
@@ -308,7 +313,10 @@ def deepvcp_forward(sd, src_pts, tgt_pts, R_init, r, s, starts, k_topk=64, nsamp
     Q = cand.shape[1] * cand.shape[2]
     dist, idx = knn(tgt_xyz, cand.reshape(B, Q, 3), nsample)
     o["knn_dist"], o["knn_idx"] = dist, idx
-    tgt_cat = cat_feat_tgt(cand, tgt_xyz, o["tgt_fe_feat"], dist, idx, bool(quirks & QUIRK_PER_FEATURE_WEIGHT))
+    tfeat = o["tgt_fe_feat"]
+    if not mismatch:
+        tfeat = torch.zeros_like(tfeat).scatter(1, o["tgt_fps"].unsqueeze(-1).expand(-1, -1, tfeat.shape[-1]), tfeat)
+    tgt_cat = cat_feat_tgt(cand, tgt_xyz, tfeat, dist, idx, bool(quirks & QUIRK_PER_FEATURE_WEIGHT))
     o["src_dfe"] = feat_embedding(sd, o["src_cat"])                   # [B,64,32]
     o["tgt_dfe"] = feat_embedding(sd, tgt_cat)                        # [B,64,C,32]
     del tgt_cat

@@ -836,10 +836,11 @@ def test_forward_vs_reference_record_at_native_operating_point(dv, synthetic):
 
 
 # ---------------------------------------- intended-semantics mode ------
-@pytest.mark.parametrize("quirks", [0, 31 - 4, 31 - 8, 31 - 1, 31 - 2, 31 - 16, 4 + 16])
+@pytest.mark.parametrize("quirks", [0, 63 - 4, 63 - 8, 63 - 1, 63 - 2, 63 - 16, 63 - 32, 32, 4 + 16])
 def test_forward_with_quirk_switches_vs_oracle(dv, synthetic, quirks):
     """Every quirk bit cleared on its own and all of them cleared ("intended" mode: proper key-point
-    permute, per-neighbour weights, un-scrambled cost volume, t_init applied, reflection fix): CUDA
+    permute, per-neighbour weights, un-scrambled cost volume, t_init applied, reflection fix, feature rows
+    addressed in their own order -- Q3, Q7, Q4, Q6, Q10, Q5): CUDA
     path against the oracle with the same switches. Indices bit-exact, features 1e-5, pose north-star."""
     N = 1024
     src, tgt, R, t = synthetic.make_batch("modelnet", [31, 32], N)

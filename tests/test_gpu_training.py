@@ -140,3 +140,29 @@ def test_training_batch_of_pairs_runs_and_reduces_the_loss(dv, synthetic):
     with torch.no_grad():
         kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts)
     assert torch.isfinite(vcp).all()
+
+
+@pytest.mark.parametrize("quirks", [63, 0, 63 - 32, 63 - 2 - 4])
+def test_autograd_forward_equals_the_inference_kernels_in_eval_mode(dv, synthetic, quirks):
+    """training.forward follows the module's mode: with eval-mode BatchNorm it must reproduce the fused inference
+    kernels (reference mode and the intended-semantics switches alike), stage by stage."""
+    N = 1024
+    src, tgt, R, t = synthetic.make_batch("modelnet", [41, 42], N)
+    torch.manual_seed(13)
+    model = dv.DeepVCP(use_normal=True, npoint=N, r=0.8, s=0.4, quirks=quirks).to(DEV).eval()
+    starts = (torch.tensor([1, 2]), torch.tensor([3, 4]), torch.tensor([5, 6]))
+    t_init = torch.tensor([[0.25, -0.5, 0.125]])
+    kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), t_init, starts=starts, keep_stages=True)
+    A = dict(model.last)
+    with dv.training.fp32_math():
+        kp2, vcp2 = dv.training.forward(model, src.to(DEV), tgt.to(DEV), R.to(DEV), t_init, starts=starts,
+                                        keep_stages=True, topk_override=A["topk_idx"])
+    Bm = model.last
+    assert vcp2.requires_grad
+    assert torch.equal(A["src_fps"].long(), Bm["src_fps"]) and torch.equal(A["tgt_fps"].long(), Bm["tgt_fps"])
+    assert rel_err(Bm["src_fe_feat"], A["src_fe_feat"]) < 1e-5
+    assert torch.equal(kp, kp2) and torch.equal(A["picked_idx"], Bm["picked_idx"])
+    assert torch.equal(A["candidates"], Bm["candidates"]) and torch.equal(A["knn_idx"], Bm["knn_idx"])
+    assert rel_err(Bm["src_dfe"], A["src_dfe"]) < 1e-5
+    assert rel_err(Bm["tgt_dfe"], A["tgt_dfe"]) < 2e-5
+    assert (vcp2 - vcp).abs().max() < 5e-5
