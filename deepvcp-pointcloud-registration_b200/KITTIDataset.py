@@ -57,3 +57,32 @@ def ingest(scans, idx, R=None, t=None, device="cuda", want_reflectance=False):
                                   ptr(refl), stream_ptr(dev)), "dvcp_ingest_kitti")
     F_._count(1)
     return src, tgt, refl
+
+
+def voxel_grid_filter(points, cell, origin=(0.0, 0.0, 0.0), mode="centroid", capacity=None, want_counts=False):
+    """Voxel-grid filter on the GPU (the alternative to the random down-sample of
+    KITTIDataset.py:11-16 that the paper's KITTI pipeline uses). points [M, 3 or 4] float32 (host or device):
+    one output row per occupied cell of edge `cell` -- the centroid of the cell's points (mode "centroid",
+    float64 sums in point order) or its first point (mode "first"); cells come out in (ix, iy, iz) order.
+    Returns a device tensor [n_cells, C] (and the points per cell, int32, if want_counts)."""
+    pts = torch.as_tensor(points, dtype=torch.float32)
+    if pts.dim() != 2 or pts.shape[1] not in (3, 4):
+        raise RuntimeError("voxel_grid_filter: [M,3] or [M,4] float32 points expected")
+    if not pts.is_cuda:
+        pts = pts.to("cuda") if torch.cuda.is_available() else pts
+    if not pts.is_cuda:
+        raise RuntimeError("voxel_grid_filter runs on a CUDA device; there is no CPU fallback")
+    pts = pts.contiguous()
+    dev = pts.device
+    M, C = pts.shape
+    cap = int(capacity) if capacity else M
+    ws = torch.empty(int(lib().dvcp_voxel_filter_workspace_bytes(M)), dtype=torch.uint8, device=dev)
+    out = torch.empty(cap, C, dtype=torch.float32, device=dev)
+    cnt = torch.empty(cap, dtype=torch.int32, device=dev) if want_counts else None
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().dvcp_voxel_grid_filter(ptr(pts), C, C, M, float(origin[0]), float(origin[1]), float(origin[2]), float(cell),
+                                       {"centroid": 0, "first": 1}[mode], ptr(ws), cap, ptr(out), ptr(cnt), ptr(n_out),
+                                       stream_ptr(dev)), "dvcp_voxel_grid_filter")
+    F_._count(5)
+    n = min(int(n_out.item()), cap)
+    return (out[:n], cnt[:n]) if want_counts else out[:n]

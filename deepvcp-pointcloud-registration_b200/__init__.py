@@ -8,7 +8,7 @@
 
 Everything numeric runs in libdvcp_b200.so (include/dvcp_b200.h); see DESIGN.md.
 """
-from . import KITTIDataset, functional, metrics, pipeline, sharding, synthetic, training              # noqa: F401
+from . import KITTIDataset, ModelNet40Dataset, functional, metrics, pipeline, sharding, synthetic, training              # noqa: F401
 from ._lib import (QUIRK_COST_VOLUME_RESHAPE, QUIRK_FPS_ORDER_MISMATCH, QUIRK_IGNORE_T_INIT, QUIRK_KEYPOINT_VIEW,  # noqa: F401
                    QUIRK_NO_REFLECTION_FIX, QUIRK_PER_FEATURE_WEIGHT, QUIRKS_INTENDED, QUIRKS_REFERENCE, lib, lib_path)
 from .build import build                                               # noqa: F401

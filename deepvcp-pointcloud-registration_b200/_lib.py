@@ -91,6 +91,10 @@ SIGNATURES = {
     "dvcp_pose_from_forward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_pack_xyz4": (c_i32, [Cloud, c_i32, c_i32, c_vp, c_vp]),
     "dvcp_ingest_kitti": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dvcp_ingest_modelnet": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dvcp_voxel_filter_workspace_bytes": (c_i64, [c_i64]),
+    "dvcp_voxel_grid_filter": (c_i32, [c_vp, c_i32, c_i32, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_i64, c_vp, c_vp,
+                                       c_vp, c_vp]),
     "dvcp_kabsch": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dvcp_kabsch_refine": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_vp]),

@@ -366,6 +366,26 @@ DVCP_API int dvcp_ingest_kitti(const float *raw, const int64_t *scan_offset, con
                       const double *t, int B, int N, float *src, float *tgt, float *reflectance,
                       dvcp_stream_t stream);
 
+/* ModelNet40Dataset.py:38-41,62-92: B clouds of M rows (x, y, z, nx, ny, nz) float64 as np.loadtxt returns them
+ * (raw [B,M,6]); the first N rows of each -> src [B,6,N] and (tgt non-null) tgt [B,6,N] = (R_b xyz + t_b,
+ * R_b normals), channel-major, float64 (out_f64 != 0: what the reference's loader yields) or float32.
+ * R [B,9], t [B,3] float64. */
+DVCP_API int dvcp_ingest_modelnet(const double *raw, const double *R, const double *t, int B, int M, int N, int out_f64,
+                         void *src, void *tgt, dvcp_stream_t stream);
+
+/* Voxel-grid filter (the preprocessing of the paper's KITTI pipeline -- the reference's loader
+ * only has the random down-sample of KITTIDataset.py:11-16): one output point per occupied cell of the cubic
+ * lattice of edge `cell` anchored at (ox, oy, oz). pts: M rows of `stride` floats, the first `channels` (3 or 4:
+ * x, y, z[, reflectance]) are reduced. Cell of a point = floor((p - o) / cell) per axis in float32. mode 0: centroid
+ * of the cell's points (float64 sums in ascending point index, rounded to float32); mode 1: the cell's first point.
+ * Cells come out in ascending (ix, iy, iz) order: out [capacity, channels], out_count [capacity] (nullable: points
+ * per cell), n_out (device int64): occupied cells (may exceed capacity; only the first `capacity` are written).
+ * workspace: dvcp_voxel_filter_workspace_bytes(M) bytes, 256-byte aligned. */
+DVCP_API int64_t dvcp_voxel_filter_workspace_bytes(int64_t M);
+DVCP_API int dvcp_voxel_grid_filter(const float *pts, int stride, int channels, int64_t M, float ox, float oy, float oz,
+                           float cell, int mode, void *workspace, int64_t capacity, float *out, int32_t *out_count,
+                           int64_t *n_out, dvcp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

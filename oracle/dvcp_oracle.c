@@ -284,3 +284,56 @@ int64_t orc_grid_size(double c, double r, double s)
     const double start = lo - s / 2;
     return (int64_t)ceil((hi - start) / s);
 }
+
+/* ---------------------------------------------------------------------------
+ * Voxel-grid filter (no counterpart in the reference's loader, which only has the
+ * random down-sample of KITTIDataset.py:11-16): cell = floor((p - o) / cell) per axis in float32, one
+ * output row per occupied cell in ascending (ix, iy, iz) order, centroid (mode 0: float64 sums in
+ * ascending point index) or first point (mode 1). pts [M, stride] float32, the first `channels` are
+ * reduced. Returns the number of cells; out [>= cells, channels], cnt [>= cells] (nullable).
+ * ------------------------------------------------------------------------- */
+typedef struct { unsigned long long key; int64_t idx; } orc_vk_t;
+static int orc_vk_cmp(const void *a, const void *b)
+{
+    const orc_vk_t *x = (const orc_vk_t *)a, *y = (const orc_vk_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+int64_t orc_voxel_filter(const float *pts, int64_t M, int64_t stride, int64_t channels, float ox, float oy, float oz,
+                         float cell, int64_t mode, float *out, int32_t *cnt)
+{
+    orc_vk_t *v = (orc_vk_t *)malloc(sizeof(orc_vk_t) * (size_t)M);
+    const float o[3] = {ox, oy, oz};
+    for (int64_t i = 0; i < M; ++i) {
+        unsigned long long k = 0;
+        int ok = 1;
+        for (int a = 0; a < 3; ++a) {
+            const float d = pts[i * stride + a] - o[a];
+            const float q = d / cell;
+            const float f = floorf(q);
+            if (!(fabsf(f) <= 1048575.0f)) ok = 0;
+            else k = (k << 21) | (unsigned long long)((long long)f + 1048576ll);
+        }
+        v[i].key = ok ? k : 0xffffffffffffffffull;
+        v[i].idx = i;
+    }
+    qsort(v, (size_t)M, sizeof(orc_vk_t), orc_vk_cmp);
+    int64_t n = 0;
+    for (int64_t i = 0; i < M;) {
+        if (v[i].key == 0xffffffffffffffffull) break;
+        int64_t j = i;
+        double acc[4] = {0, 0, 0, 0};
+        while (j < M && v[j].key == v[i].key) {
+            if (mode == 0 || j == i)
+                for (int64_t c = 0; c < channels; ++c) acc[c] += (double)pts[v[j].idx * stride + c];
+            ++j;
+        }
+        const double div = mode == 0 ? (double)(j - i) : 1.0;
+        for (int64_t c = 0; c < channels; ++c) out[n * channels + c] = (float)(acc[c] / div);
+        if (cnt) cnt[n] = (int32_t)(j - i);
+        ++n;
+        i = j;
+    }
+    free(v);
+    return n;
+}

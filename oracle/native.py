@@ -34,6 +34,8 @@ def lib():
         L.orc_candidates.argtypes = [vp, i64, f64, f64, i64, vp]
         L.orc_grid_size.argtypes = [f64, f64, f64]
         L.orc_grid_size.restype = i64
+        L.orc_voxel_filter.argtypes = [vp, i64, i64, i64, f32, f32, f32, f32, i64, vp, vp]
+        L.orc_voxel_filter.restype = i64
         for fn in (L.orc_fps_f32, L.orc_fps_f64, L.orc_square_distance_f32,
                    L.orc_ball_query_f32, L.orc_knn_f32, L.orc_candidates, L.orc_ball_query_f64,
                    L.orc_square_distance_f64):
@@ -120,3 +122,14 @@ def candidates(centres: torch.Tensor, r: float, s: float, G: int = None) -> torc
     out = torch.empty(B, M, G * G * G, 3, dtype=torch.float32)
     lib().orc_candidates(c.data_ptr(), B * M, float(r), float(s), G, out.data_ptr())
     return out
+
+
+def voxel_filter(pts: torch.Tensor, cell: float, origin=(0.0, 0.0, 0.0), mode: str = "centroid"):
+    """pts [M, 3 or 4] float32 -> (out [n, C] float32, counts [n] int32): see orc_voxel_filter."""
+    x = _c(pts, torch.float32)
+    M, C = x.shape
+    out = torch.empty(M, C, dtype=torch.float32)
+    cnt = torch.empty(M, dtype=torch.int32)
+    n = lib().orc_voxel_filter(x.data_ptr(), M, C, C, float(origin[0]), float(origin[1]), float(origin[2]), float(cell),
+                               {"centroid": 0, "first": 1}[mode], out.data_ptr(), cnt.data_ptr())
+    return out[:n].clone(), cnt[:n].clone()

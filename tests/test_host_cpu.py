@@ -168,3 +168,32 @@ def test_registration_error_metrics_follow_train_py(pkg):
         pd = torch.nn.PairwiseDistance(p=2)
         assert abs(float(rot[b]) - float((a - c).norm())) < 1e-9
         assert abs(float(tr[b]) - float(pd(tp[b].reshape(1, 3), tg[b].reshape(1, 3)))) < 1e-9
+
+
+def test_modelnet_loader_host_logic(pkg, tmp_path):
+    """ModelNet40Dataset.py:34-46,62-75: text rows parsed as float64 [M,6]; R = RotX RotY RotZ of utils.py:8-26;
+    draws in the reference's order (three np.random.uniform, then torch.rand(3,1))."""
+    import numpy as np
+    mn = pkg.ModelNet40Dataset
+    f = tmp_path / "a.txt"
+    f.write_text("0.5,-0.25,1.0,0.0,0.0,1.0\n-1.5,2.0,0.125,1.0,0.0,0.0\n")
+    a = mn.read_txt(str(f))
+    assert a.dtype == np.float64 and a.shape == (2, 6) and a[1, 0] == -1.5
+    np.random.seed(3)
+    torch.manual_seed(4)
+    R, t = mn.draw_transform()
+    np.random.seed(3)
+    torch.manual_seed(4)
+    th = [np.random.uniform(0, np.pi * 2) for _ in range(3)]
+    t_ref = (1.0 - -1.0) * torch.rand(3, 1) + -1.0
+    assert torch.equal(t, t_ref)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(R) - 1) < 1e-14
+    if os.path.isfile("/root/reference/utils.py"):   # the reference's own matrices, build container only
+        sys.path.insert(0, "/root/reference")
+        import utils as ref_utils
+        R_ref = np.asarray(ref_utils.RotX(th[0]) @ ref_utils.RotY(th[1]) @ ref_utils.RotZ(th[2]))
+        assert np.array_equal(R, R_ref)
+    with pytest.raises(RuntimeError):
+        mn.ingest([a], device="cpu")
+    with pytest.raises(RuntimeError):
+        pkg.KITTIDataset.voxel_grid_filter(torch.zeros(8, 5), 0.1)
