@@ -332,16 +332,34 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             }
             break;
         }
-        // descending key order; beyond FC_CAP candidates the (FC_CAP+1)-th key is the threshold T
-        for (int t = tid; t < n; t += FC_THREADS) {
-            const unsigned long long key = sh.c_key[t];
+        // descending key order (rank = number of larger keys; keys are distinct); beyond FC_CAP candidates the
+        // (FC_CAP+1)-th key is the threshold T. P adjacent lanes share one key and count a slice of the list each
+        // (n <= FC_C * FC_LCAP = 256 <= FC_THREADS / 2): the phase is a serial scan per thread, so its length is n / P
+        {
+            const int P = n * 4 <= FC_THREADS ? 4 : (n * 2 <= FC_THREADS ? 2 : 1);   // n <= 256 <= FC_THREADS
+            const int sh_p = P == 4 ? 2 : (P == 2 ? 1 : 0);
+            const int t = tid >> sh_p, part = tid & (P - 1);
+            const unsigned long long key = t < n ? sh.c_key[t] : 0ull;
+            // my slice of the list: a contiguous run, four independent loads in flight per trip
+            const int len = (n + P - 1) >> sh_p, u0 = part * len, u1 = min(u0 + len, n);
             int rk = 0;
-            for (int u = 0; u < n; ++u) rk += sh.c_key[u] > key;
-            if (rk < FC_CAP) {
-                sh.s_key[rk] = key;
-                sh.s_xyz[rk] = sh.c_xyz[t];
+            if (t < n) {
+                int u = u0;
+                for (; u + 4 <= u1; u += 4) {
+                    const unsigned long long a = sh.c_key[u], b = sh.c_key[u + 1], c = sh.c_key[u + 2], d = sh.c_key[u + 3];
+                    rk += (int)(a > key) + (int)(b > key) + (int)(c > key) + (int)(d > key);
+                }
+                for (; u < u1; ++u) rk += sh.c_key[u] > key;
             }
-            if (rk == FC_CAP) sh.T = key;
+            if (P >= 2) rk += __shfl_xor_sync(0xffffffffu, rk, 1);
+            if (P == 4) rk += __shfl_xor_sync(0xffffffffu, rk, 2);
+            if (t < n && part == 0) {
+                if (rk < FC_CAP) {
+                    sh.s_key[rk] = key;
+                    sh.s_xyz[rk] = sh.c_xyz[t];
+                }
+                if (rk == FC_CAP) sh.T = key;
+            }
         }
         FC_TICK(9);
         __syncthreads();
