@@ -22,19 +22,24 @@
 // adds the two column halves in registers and takes the max over its 32 lanes with a transposing butterfly
 // (16 shuffles per 16 channels).
 //
-// Roles in a CTA (21 warps, one persistent CTA per SM, 4 operand stages + 4 TMEM accumulators of 64 columns):
+// Roles in a CTA (18 warps, one persistent CTA per SM, 3 operand stages + 3 TMEM accumulators of 64 columns):
 //   warps 0-3   epilogue: warp w owns TMEM lanes 32w..32w+31 = candidate w of the tile: tcgen05.ld of
 //               16 + 16 columns at a time, add, max over the lanes, one coalesced 128-byte store;
-//   warps 4-19  producers, 4 groups of 4 (group g builds tiles g, g+4, ...): gather the
-//               neighbours' feature rows into registers (next tile's indices are already
-//               in flight), scale by the float64 distance weights carried as float pairs,
-//               split hi/lo, store into shared memory in the UMMA K-major SWIZZLE_128B layout;
-//   warp 20     allocates TMEM, waits for the operand, issues the 10 tcgen05.mma of a tile from
-//               one lane and commits to the mbarriers.
-// The rows are gathered (index-driven) AND scaled by a per-candidate, per-feature weight before the
-// contraction (quirk Q7), so they pass through registers; a bulk / TMA copy could only land them in a
-// staging buffer that the same warps would have to read again (more shared-memory traffic, the binding
-// resource). The operands reach the tensor core through shared-memory matrix descriptors.
+//   warps 4-15  producers, 3 groups of 4 (group g builds tiles g, g+3, ... into stage g): gather the
+//               neighbours' feature rows into registers, scale by the distance weights (float64 in the
+//               reference, carried as float pairs), split hi/lo, store into shared memory in the UMMA
+//               K-major SWIZZLE_128B layout;
+//   warp 16     allocates TMEM, waits for the operand, issues the 10 tcgen05.mma of a tile from
+//               one lane and commits to the mbarriers;
+//   warp 17     loader: the KNN indices / distances of the next run of 8 tiles (two contiguous 4 KB pieces)
+//               come in by cp.async.bulk (TMA) into a double buffer, completion counted on an mbarrier.
+// TMA feeds what is contiguous: the index / distance stream. The feature rows are gathered (index-driven) AND
+// scaled by a per-candidate, per-feature weight before the contraction (quirk Q7), so they pass through
+// registers: a bulk copy (UBLKCP takes its addresses from uniform registers: one 128-byte row per
+// instruction, 32 per candidate) or a tile::gather4 tensor copy could only land them in a staging buffer that
+// the same warps would have to read again -- more traffic on the shared-memory / L1 data pipe, which is the
+// binding resource of this kernel (ncu: LSU + tensor-core wavefronts fill 91 % of its cycles).
+// The operands reach the tensor core through shared-memory matrix descriptors.
 #include "common.cuh"
 
 namespace dvcp {
@@ -57,11 +62,13 @@ constexpr unsigned TC_TMEM_COLS = TC_STAGES * 64 <= 256 ? 256u : 512u;   // allo
 constexpr int TC_EPI_WARPS = 4;                // warp w reads TMEM lanes 32w..32w+31 = the neighbours of candidate w
 constexpr int TC_PROD_WARPS = 4 * TC_GROUPS;   // warps 4 .. 4 + TC_PROD_WARPS - 1
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
-constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
+constexpr int TC_LOAD_WARP = TC_MMA_WARP + 1;   // issues the bulk (TMA) copies of the neighbour index / distance stream
+constexpr int TC_THREADS = (TC_LOAD_WARP + 1) * 32;
 constexpr int TC_W_BYTES = TC_PROD_WARPS * 32 * 8;   // per producer warp: (hi, lo) distance weight of each feature
 constexpr int TC_RUN = 8;                      // a CTA takes its tiles in runs of 8 consecutive tiles = 32 consecutive candidates
 constexpr int TC_T_BYTES = 32 * 33 * 4;        // epilogue transposition tile (feature-major output)
-constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + TC_T_BYTES + 1024;   // + alignment slack
+constexpr int TC_RUN_BYTES = TC_RUN * 4 * 32 * 4;   // the idx (or dist) rows of one run of tiles: 32 candidates x 32 neighbours
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + TC_T_BYTES + 4 * TC_RUN_BYTES + 1024;   // + alignment slack
 
 // first candidate of this CTA's i-th tile: runs of TC_RUN consecutive tiles, the runs dealt round-robin to the CTAs
 __device__ __forceinline__ int64_t tc_tile_cand(int i) {   // (tile counts fit 32 bits: checked by the launcher)
@@ -146,6 +153,9 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 3 * TC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * TC_STAGES);
     float *sT = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [32][33]
+    // neighbour indices / distances of a run of tiles, double-buffered, filled by cp.async.bulk (16-byte aligned)
+    unsigned char *sRun = reinterpret_cast<unsigned char *>(sT) + TC_T_BYTES + ((16u - ((TC_T_BYTES) & 15u)) & 15u);
+    uint64_t *rfull = bars + 4 * TC_STAGES + 1, *rempty = rfull + 2;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the layout is row-block major, so the host's two 32-row images back to back are the 64-row image [Wh ; Wl]
@@ -159,6 +169,10 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             mbar_init(&empty[s], 1);    // tcgen05.commit
             mbar_init(&tfull[s], 1);    // tcgen05.commit
             mbar_init(&tempty[s], TC_EPI_WARPS);
+        }
+        for (int r = 0; r < 2; ++r) {
+            mbar_init(&rfull[r], 1);               // the loader's arrive.expect_tx; the copies complete the bytes
+            mbar_init(&rempty[r], TC_PROD_WARPS);  // every producer warp has read its rows of the run
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -207,6 +221,29 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 umma_commit(&tfull[s]);   // accumulator is complete
             }
             __syncwarp();
+        }
+    } else if (warp == TC_LOAD_WARP) {
+        // ---------- loader: the neighbour indices / distances of a run of 8 tiles (32 candidates) are two
+        // contiguous 4 KB pieces of the KNN result: one thread brings them in with cp.async.bulk (TMA, completion
+        // counted in bytes on an mbarrier), one run ahead of the producers ----------
+        if (lane == 0) {
+            const int my_runs = my_tiles / TC_RUN;
+            for (int r = 0; r < my_runs; ++r) {
+                const int buf = r & 1, use = r >> 1;
+                if (use > 0) mbar_wait(&rempty[buf], (unsigned)((use - 1) & 1));   // the producers are done with the buffer
+                const int64_t c0 = tc_tile_cand(r * TC_RUN);
+                const int64_t left = total_cand - c0;
+                const uint32_t bytes = left <= 0 ? 0u : (uint32_t)(left < TC_RUN * 4 ? left : TC_RUN * 4) * 128u;
+                const uint32_t bar = smem_u32(&rfull[buf]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+                if (bytes) {
+                    const uint32_t dst = smem_u32(sRun + (size_t)buf * 2 * TC_RUN_BYTES);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(kidx + c0 * 32), "r"(bytes), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst + TC_RUN_BYTES), "l"(kdist + c0 * 32), "r"(bytes), "r"(bar) : "memory");
+                }
+            }
         }
     } else if (warp < TC_EPI_WARPS) {
         // ------------------ epilogue: TMEM -> max over the 32 neighbours -> global ------------------
@@ -302,29 +339,19 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         // (SWIZZLE_128B); r & 7 alternates between rsub and rsub + 4, so two bases + immediates address all rows
         unsigned char *const row0 = ahi + (cw * 32 + rsub) * 128 + ((chunk ^ rsub) << 4);
         unsigned char *const row1 = ahi + (cw * 32 + rsub) * 128 + ((chunk ^ (rsub + 4)) << 4);
-        // idx / dist of the first tile; the next tile's are fetched while this one is built
         int i = group;
-        int id_n = 0;
-        float dj_n = 0.f;
-        if (i < my_tiles) {
-            const int64_t gq = tc_tile_cand(i) + cw;
-            if (gq < total_cand) {
-                id_n = __ldg(kidx + gq * 32 + lane);
-                dj_n = __ldg(kdist + gq * 32 + lane);
-            }
-        }
         for (unsigned it = 0; i < my_tiles; i += TC_GROUPS, ++it) {
             const int64_t gq = tc_tile_cand(i) + cw;   // this warp's candidate
             const bool live = gq < total_cand;
-            const int id = id_n;
-            const float djf = dj_n;
-            {
-                const int i2 = i + TC_GROUPS;
-                const int64_t gq2 = tc_tile_cand(i2) + cw;
-                if (i2 < my_tiles && gq2 < total_cand) {
-                    id_n = __ldg(kidx + gq2 * 32 + lane);
-                    dj_n = __ldg(kdist + gq2 * 32 + lane);
-                }
+            // my neighbour's index and distance: from the run buffer the loader filled (a dead candidate reads row 0)
+            const int run = i / TC_RUN, buf = run & 1;
+            mbar_wait(&rfull[buf], (unsigned)((run >> 1) & 1));
+            const unsigned char *rb = sRun + (size_t)buf * 2 * TC_RUN_BYTES + ((i % TC_RUN) * 4 + cw) * 128 + lane * 4;
+            const int id = live ? *reinterpret_cast<const int *>(rb) : 0;
+            const float djf = live ? *reinterpret_cast<const float *>(rb + TC_RUN_BYTES) : 0.f;
+            if ((i + TC_GROUPS) / TC_RUN != run || i + TC_GROUPS >= my_tiles) {   // my last tile of this run
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rempty[buf]);
             }
             // cloud of the candidate: gq / Q from the float quotient, corrected by at most one either way
             int b = 0;
@@ -475,6 +502,7 @@ extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const fl
     const int64_t total = (int64_t)B * Q;
     const int64_t ntiles = (total + 3) / 4;
     if (ntiles + TC_RUN * DVCP_NUM_SMS >= (1ll << 29) || (int64_t)N * 8 >= (1ll << 31)) return DVCP_E_UNSUPPORTED;   // 32-bit tile / row arithmetic
+    if (((uintptr_t)knn_idx | (uintptr_t)knn_dist) & 15) return DVCP_E_UNSUPPORTED;   // bulk copies: 16-byte aligned sources
     DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     int64_t grid = DVCP_NUM_SMS;   // persistent: one CTA per SM

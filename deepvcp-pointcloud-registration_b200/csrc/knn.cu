@@ -144,12 +144,18 @@ knn_indexed_kernel(dvcp_cloud_index_t index, const float *__restrict__ query, in
     for (int64_t ch = (int64_t)blockIdx.x * KNI_WARPS + warp; ch < nchains; ch += (int64_t)gridDim.x * KNI_WARPS) {
         const int64_t q0 = ch * chain, q1 = min(q0 + chain, Q);
         unsigned long long list = INF;   // result of the previous query of the chain (lane j: j-th neighbour)
+        // boustrophedon over the z-lines of the chain (consecutive queries stay adjacent): line / position kept as
+        // counters (a division per query was 3 % of the kernel's instructions)
+        int line = 0, k = 0;
+        int64_t line0 = q0;                       // first query of the current line
+        bool rev = false;                         // odd, complete line: walked backwards
         for (int64_t qi = q0; qi < q1; ++qi) {
-            // boustrophedon over the z-lines of the chain: consecutive queries stay adjacent
-            int64_t q = qi;
-            {
-                const int i = (int)(qi - q0), line = i / zline, k = i - line * zline;
-                if ((line & 1) && q0 + (int64_t)(line + 1) * zline <= q1) q = q0 + (int64_t)line * zline + (zline - 1 - k);
+            const int64_t q = rev ? line0 + (zline - 1 - k) : line0 + k;
+            if (++k == zline) {
+                k = 0;
+                ++line;
+                line0 += zline;
+                rev = (line & 1) && line0 + zline <= q1;
             }
             const float *qp = query + ((int64_t)b * Q + q) * 3;
             const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
