@@ -80,6 +80,8 @@ SIGNATURES = {
     "dvcp_knn_groups_workspace_bytes": (c_i64, [c_i32, c_i64, c_i32]),
     "dvcp_dfe_tgt_fused": (c_i32, [c_vp, Cloud, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, DfeParams, c_i32, c_vp,
                                    c_vp]),
+    "dvcp_dfe_tgt_backward": (c_i32, [c_vp, Cloud, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, DfeParams, c_vp, c_i32, c_vp, c_vp,
+                                      c_vp, c_vp, c_vp]),
     "dvcp_dfe_tc_b_floats": (c_i32, []),
     "dvcp_dfe_tc_b_offset": (c_i32, [c_i32, c_i32]),
     "dvcp_dfe_tgt_tc": (c_i32, [c_vp, Cloud, c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),

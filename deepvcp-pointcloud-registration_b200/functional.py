@@ -391,6 +391,22 @@ def dfe_tgt_fused(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, dfe, qui
     return out
 
 
+def dfe_tgt_backward(cand, tgt_cloud, tgt_feat, knn_dist, knn_idx32, B, N, dfe, w_collapsed, quirks, grad_out):
+    """Gradient of dfe_tgt_fused (training): -> (grad of the collapsed map [32,35], grad of its bias [32],
+    grad of tgt_feat [B,N,32])."""
+    require_cuda(cand, tgt_feat, knn_dist, knn_idx32, grad_out)
+    dev = cand.device
+    Q = knn_dist.shape[1]
+    gw = torch.zeros(32, 35, dtype=torch.float32, device=dev)
+    gb = torch.zeros(32, dtype=torch.float32, device=dev)
+    gf = torch.zeros(B, N, 32, dtype=torch.float32, device=dev)
+    check(lib().dvcp_dfe_tgt_backward(ptr(_f32c(cand)), tgt_cloud, ptr(_f32c(tgt_feat)), ptr(knn_dist), ptr(knn_idx32), B, N, Q,
+                                      dfe, ptr(_f32c(w_collapsed)), quirks, ptr(_f32c(grad_out)), ptr(gw), ptr(gb), ptr(gf),
+                                      stream_ptr(dev)), "dvcp_dfe_tgt_backward")
+    _count(1)
+    return gw, gb, gf
+
+
 def dfe_tc_operand(W1, b1, W2, b2, W3, b3, device):
     """Collapse the three un-activated Linear layers (float64) and lay the 32 x 40
     operand out for the tensor-core kernel; returns (b_hi, b_lo) device tensors."""

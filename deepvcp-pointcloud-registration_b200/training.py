@@ -13,8 +13,13 @@ What the reference differentiates and what it does not decides the split:
 * The differentiable stages are the reference's own tensor algebra written with torch
   operators on the device, so autograd returns the reference's gradients and BatchNorm in
   train mode uses and updates batch statistics exactly as nn.BatchNorm2d does
-  (pointnet2_utils.py:196-198). There is no hand-written backward kernel: the fused
-  inference kernels (folded BatchNorm, collapsed embedding, fused CPG) are not used here.
+  (pointnet2_utils.py:196-198).
+* One stage has a hand-written forward AND backward: the target-side embedding, whose input in the reference is
+  a float64 [B,64,C,32,35] tensor (763 MB per pair at the KITTI shape, twice that with its autograd graph).
+  `TargetEmbedding` evaluates it with the fused gather + embedding kernel and differentiates it with
+  dvcp_dfe_tgt_backward (arg-max neighbours recomputed, gradients to the collapsed 32 x 35 map and to the target
+  feature table); autograd carries the collapsed map's gradient on to fc1 / fc2 / fc3. `fused_embedding=False`
+  selects the plain autograd form of the same stage.
 
 `DeepVCP.forward` routes here when the module is in train mode; `deepVCP_loss` routes to
 `loss()` when its prediction carries a gradient. Parameters that receive no gradient in the
@@ -25,6 +30,8 @@ import contextlib
 import torch
 import torch.nn.functional as F
 
+from . import functional as F_
+from ._lib import cloud_pm
 from ._lib import QUIRK_COST_VOLUME_RESHAPE, QUIRK_FPS_ORDER_MISMATCH, QUIRK_IGNORE_T_INIT, QUIRK_KEYPOINT_VIEW, QUIRK_PER_FEATURE_WEIGHT, require_cuda
 from .get_cat_feat_src import Get_Cat_Feat_Src
 from .knn_cuda import KNN
@@ -81,6 +88,34 @@ def embedding(dfe, X):
     return torch.max(X, dim=-2)[0]
 
 
+class TargetEmbedding(torch.autograd.Function):
+    """out[b,q,c] = max_j (Wc x_j + bc)[c] over the 32 neighbours of candidate q (get_cat_feat_tgt.py:53-96 +
+    deep_feat_embedding.py:46-60) as ONE kernel forward and ONE kernel backward. Differentiable inputs: the
+    collapsed map Wc [32,35], its bias bc [32] (functions of fc1 / fc2 / fc3 on the autograd tape) and the target
+    feature table [B,N,32]; everything else is data (knn_cuda runs under no_grad, :45-52)."""
+
+    @staticmethod
+    def forward(ctx, Wc, bc, tfeat, cand, tgt_xyz, dist, idx32, dfe_mod, quirks):
+        B, N, _ = tfeat.shape
+        ctx.save_for_backward(Wc, tfeat, cand, tgt_xyz, dist, idx32)
+        ctx.dfe_mod, ctx.quirks = dfe_mod, quirks
+        return F_.dfe_tgt_fused(cand, cloud_pm(tgt_xyz), tfeat, dist, idx32, B, N, dfe_mod.params(), quirks)
+
+    @staticmethod
+    def backward(ctx, gout):
+        Wc, tfeat, cand, tgt_xyz, dist, idx32 = ctx.saved_tensors
+        B, N, _ = tfeat.shape
+        gw, gb, gf = F_.dfe_tgt_backward(cand, cloud_pm(tgt_xyz), tfeat, dist, idx32, B, N, ctx.dfe_mod.params(),
+                                         Wc.detach(), ctx.quirks, gout.contiguous())
+        return gw, gb, gf, None, None, None, None, None, None
+
+
+def collapsed_embedding(dfe):
+    """Wc = W3 W2 W1, bc = W3 (W2 b1 + b2) + b3 on the autograd tape (no activation between the layers)."""
+    W1, W2, W3 = dfe.fc1.weight, dfe.fc2.weight, dfe.fc3.weight
+    return W3 @ W2 @ W1, W3 @ (W2 @ dfe.fc1.bias + dfe.fc2.bias) + dfe.fc3.bias
+
+
 def corresponding_points(cpg_mod, src_dfe, tgt_dfe, candidates, G, reshape_quirk):
     """cpg.forward (cpg.py:27-60). src_dfe [B,K,32], tgt_dfe [B,K,C,32], candidates [B,K,C,3] -> vcp [B,K,3]."""
     B, K, C, _ = candidates.shape
@@ -95,7 +130,8 @@ def corresponding_points(cpg_mod, src_dfe, tgt_dfe, candidates, G, reshape_quirk
     return torch.sum(w * candidates, -2) / torch.sum(w.expand(-1, -1, -1, 3), -2)
 
 
-def forward(model, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=False, topk_override=None):
+def forward(model, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=False, topk_override=None,
+            fused_embedding=True):
     """DeepVCP.forward (deepVCP.py:24-110) with a gradient. Same arguments and results as the inference
     forward; B > 1 = B independent pairs (BatchNorm statistics are taken over the batch, as torch does)."""
     dev = model.cpg.conv1.weight.device
@@ -140,18 +176,27 @@ def forward(model, src_pts, tgt_pts, R_init, t_init, starts=None, keep_stages=Fa
         C = cand.shape[2]
         G = round(C ** (1.0 / 3.0))
         dist, idx = KNN(k=ns, transpose_mode=True)(tgt_xyz, cand.view(B, K * C, 3))     # get_cat_feat_tgt.py:45-52
-        w = dist / torch.sum(dist, dim=2, keepdim=True, dtype=torch.float64)            # :57-58, float64
-        local = _gather_rows(tgt_xyz, idx).view(B, K, C, ns, 3) - cand.unsqueeze(3)     # :86-89
     if intended_order:   # feature rows by original point index, like the KNN indices that address them
-        tfeat = torch.zeros_like(tfeat).scatter(1, tfps.unsqueeze(-1).expand(-1, -1, 32), tfeat)
-    picked_feat = _gather_rows(tfeat, idx).view(B, K, C, ns, 32)                        # :85
-    if q & QUIRK_PER_FEATURE_WEIGHT:                                                    # :65,92 (Q7): weight by feature
-        wmap = w.view(B, K, C, 1, ns)
+        tfeat_used = torch.zeros_like(tfeat).scatter(1, tfps.unsqueeze(-1).expand(-1, -1, 32), tfeat)
     else:
-        wmap = w.view(B, K, C, ns, 1)
-    tgt_cat = torch.cat((local, picked_feat * wmap), dim=4)                             # float64, :93-96
+        tfeat_used = tfeat
     src_dfe = embedding(model.DFE, src_cat)
-    tgt_dfe = embedding(model.DFE, tgt_cat)
+    if fused_embedding:
+        # gather + weights + embedding + max in one kernel each way; the float64 [B,K,C,32,35] tensor is never built
+        Wc, bc = collapsed_embedding(model.DFE)
+        tgt_dfe = TargetEmbedding.apply(Wc, bc, tfeat_used, cand.view(B, K * C, 3), tgt_xyz.float().contiguous(), dist,
+                                        idx.int(), model.DFE, q).view(B, K, C, 32)
+    else:
+        with torch.no_grad():
+            w = dist / torch.sum(dist, dim=2, keepdim=True, dtype=torch.float64)        # :57-58, float64
+            local = _gather_rows(tgt_xyz, idx).view(B, K, C, ns, 3) - cand.unsqueeze(3)  # :86-89
+        picked_feat = _gather_rows(tfeat_used, idx).view(B, K, C, ns, 32)               # :85
+        if q & QUIRK_PER_FEATURE_WEIGHT:                                                # :65,92 (Q7): weight by feature
+            wmap = w.view(B, K, C, 1, ns)
+        else:
+            wmap = w.view(B, K, C, ns, 1)
+        tgt_cat = torch.cat((local, picked_feat * wmap), dim=4)                         # float64, :93-96
+        tgt_dfe = embedding(model.DFE, tgt_cat)
     vcp = corresponding_points(model.cpg, src_dfe, tgt_dfe, cand, G, bool(q & QUIRK_COST_VOLUME_RESHAPE))
     if keep_stages:
         model.last = dict(src_fps=sfps, tgt_fps=tfps, src_fe_feat=sfeat, tgt_fe_feat=tfeat, scores=scores, topk_idx=topk,

@@ -366,6 +366,16 @@ DVCP_API int dvcp_ingest_kitti(const float *raw, const int64_t *scan_offset, con
                       const double *t, int B, int N, float *src, float *tgt, float *reflectance,
                       dvcp_stream_t stream);
 
+/* Training: gradient of dvcp_dfe_tgt_fused. Inputs as the forward's; w_collapsed [32,35] = W3 W2 W1
+ * (row-major); grad_out [B,Q,32]. The arg-max neighbour of every (candidate, channel) is recomputed with the forward's
+ * arithmetic. ACCUMULATES into grad_w [32,35] (gradient w.r.t. the collapsed map), grad_b [32] and grad_feat [B,N,32]
+ * (gradient w.r.t. tgt_feat): the caller zeroes them. Distances, coordinates and candidates receive no gradient
+ * (get_cat_feat_tgt.py:45-58: knn_cuda runs under no_grad). */
+DVCP_API int dvcp_dfe_tgt_backward(const float *cand, dvcp_cloud_t tgt_xyz, const float *tgt_feat, const float *knn_dist,
+                          const int32_t *knn_idx, int B, int N, int64_t Q, dvcp_dfe_params_t dfe,
+                          const float *w_collapsed, int quirks, const float *grad_out, float *grad_w, float *grad_b,
+                          float *grad_feat, dvcp_stream_t stream);
+
 /* ModelNet40Dataset.py:38-41,62-92: B clouds of M rows (x, y, z, nx, ny, nz) float64 as np.loadtxt returns them
  * (raw [B,M,6]); the first N rows of each -> src [B,6,N] and (tgt non-null) tgt [B,6,N] = (R_b xyz + t_b,
  * R_b normals), channel-major, float64 (out_f64 != 0: what the reference's loader yields) or float32.

@@ -35,8 +35,11 @@ def build(dv, g):
     return model, src.to(DEV), tgt.to(DEV), R.to(DEV), t.to(DEV), starts
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", ["train_modelnet_n512_g5", "train_modelnet_f64_n512_g5"])
-def test_training_step_vs_reference_record(dv, name):
+def test_training_step_vs_reference_record(dv, name, fused):
+    """fused=True: the target-side embedding runs as one kernel forward (dvcp_dfe_tgt_fused) and one kernel backward
+    (dvcp_dfe_tgt_backward); False: the same stage through autograd on the materialised float64 tensor."""
     g = load_golden(name)
     model, src, tgt, R, t, starts = build(dv, g)
     model.train()
@@ -44,8 +47,8 @@ def test_training_step_vs_reference_record(dv, name):
     optim = torch.optim.Adam(model.parameters(), lr=lr)
     with dv.training.fp32_math():
         # the key-point choice is the reference's own draw from its scores (top-k ties are unspecified)
-        kp, vcp = model(src, tgt, R, torch.zeros(1, 3), starts=starts, keep_stages=True,
-                        topk_override=T(g["topk_idx"]).long().view(1, -1))
+        kp, vcp = dv.training.forward(model, src, tgt, R, torch.zeros(1, 3), starts=starts, keep_stages=True,
+                                      topk_override=T(g["topk_idx"]).long().view(1, -1), fused_embedding=fused)
         assert vcp.requires_grad and kp.dtype == src.dtype and vcp.dtype == torch.float32
         # train-mode features (batch statistics) and the forward outputs
         assert rel_err(model.last["src_fe_feat"], T(g["src_fe_feat"])) < 1e-5
