@@ -519,11 +519,11 @@ def run_reference(args):
 
 
 def main():
-    # stdout carries exactly ONE JSON line. At NCCL_DEBUG=VERSION (and only then) NCCL prints its version banner to
-    # stdout, which would be a second line: that one level is lowered to WARN; INFO / TRACE / anything else the
-    # caller set is left alone (their output goes where NCCL_DEBUG_FILE says, stdout by default)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly ONE JSON line. NCCL writes its debug output (the version banner at VERSION / WARN, the
+    # ring and rank lines at INFO) to stdout unless NCCL_DEBUG_FILE names a file: the LEVEL the caller set is left
+    # alone, the output is sent to stderr when the caller has not chosen a destination itself
+    if os.environ.get("NCCL_DEBUG") and "NCCL_DEBUG_FILE" not in os.environ:
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
