@@ -13,6 +13,10 @@
 //     largest second-best key, (3) pushes them, with coordinates, into the shared
 //     memory of all 8 CTAs (DSMEM stores), (4) cluster barrier, (5) every CTA
 //     resolves the same candidate list redundantly (so no second exchange is needed).
+//     Which buckets a centroid can reach is found AHEAD of its acceptance: while warp 0
+//     resolves the candidate list, the other warps box-test EVERY candidate against the
+//     CTA's buckets (the bucket maxima do not change in between); the next step masks
+//     the result with the accepted set. The box tests leave the critical path.
 // Exactness argument: as for the batched rounds of fps.cu, generalised to FC_E exposed
 // keys per bucket: with S = the largest (FC_E+1)-th best key of any bucket, every point
 // whose key exceeds S is among the FC_E best of its bucket, so the exposed keys above S
@@ -69,11 +73,11 @@ struct FcShared {
     unsigned long long s_key[FC_CAP];
     float4 s_xyz[FC_CAP];
     unsigned K[FC_CAP][4], L[FC_CAP][4];   // row r, bit i: earlier candidate i lowers r / lowers r to a key <= T
-    float4 acc[FC_CAP];                    // centroids accepted in this step, in FPS order
     unsigned long long top[FC_MAXNBL][FC_E + 1];   // per bucket: its FC_E + 1 largest keys, descending
-    unsigned F[FC_MAXNBL][4];              // per bucket: accepted centroids that can reach it
+    unsigned F[FC_MAXNBL][4];              // per bucket: candidates (rows of s_xyz) that can reach it
     float box[6][FC_MAXNBL];
     unsigned long long T, l_S;
+    unsigned accmask[4];                   // bit r: candidate r (row of s_xyz) was accepted in the last resolution
     unsigned l_cnt, n_cand, n_acc;
 };
 
@@ -134,7 +138,10 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     }
     const unsigned startidx = (unsigned)start[b];
     if (tid == 0) {
-        sh.acc[0] = make_float4(xyz.at(b, (int)startidx, 0), xyz.at(b, (int)startidx, 1), xyz.at(b, (int)startidx, 2), 0.f);
+        // the start point is "candidate 0, accepted" of a step that happened before the loop
+        sh.s_xyz[0] = make_float4(xyz.at(b, (int)startidx, 0), xyz.at(b, (int)startidx, 1), xyz.at(b, (int)startidx, 2), 0.f);
+        sh.accmask[0] = 1u;
+        sh.accmask[1] = sh.accmask[2] = sh.accmask[3] = 0u;
         sh.n_acc = 1u;
         sh.n_cand = 0u;
         sh.l_cnt = 0u;
@@ -145,6 +152,29 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     }
     cluster.sync();   // peers exist and are initialised before anyone writes into them
 
+    // Box tests: which of my buckets can candidate a (row a of s_xyz) reach? lane = bucket (its box stays in
+    // registers while the candidates stream by), the warps first .. first + nw - 1 stride over the candidates.
+    auto box_tests = [&](int m_cand, int first, int nw) {
+        for (int h = 0; h < H2; ++h) {
+            const int jl = h * 32 + lane;
+            if (jl < NBL) {
+                const float nx = sh.box[0][jl], ny = sh.box[1][jl], nz = sh.box[2][jl];
+                const float xx = sh.box[3][jl], xy = sh.box[4][jl], xz = sh.box[5][jl];
+                const float bestval = __uint_as_float((unsigned)(sh.top[jl][0] >> 32));
+#pragma unroll 4
+                for (int a = warp - first; a < m_cand; a += nw) {
+                    const float4 c = sh.s_xyz[a];
+                    const float ex = fmaxf(fmaxf(__fsub_rn(nx, c.x), __fsub_rn(c.x, xx)), 0.0f);
+                    const float ey = fmaxf(fmaxf(__fsub_rn(ny, c.y), __fsub_rn(c.y, xy)), 0.0f);
+                    const float ez = fmaxf(fmaxf(__fsub_rn(nz, c.z), __fsub_rn(c.z, xz)), 0.0f);
+                    if (sq3_nofma(ex, ey, ez) < bestval) atomicOr(&sh.F[jl][a >> 5], 1u << (a & 31));
+                }
+            }
+        }
+    };
+    __syncthreads();
+    box_tests(1, 0, FC_WARPS);   // the start point
+
     int produced = 0;
 #ifdef DVCP_FPS_TIMING
     long long t_last__ = clock64();
@@ -154,30 +184,19 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
     for (int step = 0;; ++step) {
         const int buf = step & 1;
         FC_TICK(15);
-        // ---- (1) which of my buckets can each accepted centroid reach? ----
         const int A = (int)sh.n_acc;
-        for (int h = 0; h < H2; ++h) {
-            const int jl = h * 32 + lane;
-            if (jl < NBL) {   // lane = bucket: its box stays in registers while the centroids stream by
-                const float nx = sh.box[0][jl], ny = sh.box[1][jl], nz = sh.box[2][jl];
-                const float xx = sh.box[3][jl], xy = sh.box[4][jl], xz = sh.box[5][jl];
-                const float bestval = __uint_as_float((unsigned)(sh.top[jl][0] >> 32));
-#pragma unroll 4
-                for (int a = warp; a < A; a += FC_WARPS) {
-                    const float4 c = sh.acc[a];
-                    const float ex = fmaxf(fmaxf(__fsub_rn(nx, c.x), __fsub_rn(c.x, xx)), 0.0f);
-                    const float ey = fmaxf(fmaxf(__fsub_rn(ny, c.y), __fsub_rn(c.y, xy)), 0.0f);
-                    const float ez = fmaxf(fmaxf(__fsub_rn(nz, c.z), __fsub_rn(c.z, xz)), 0.0f);
-                    if (sq3_nofma(ex, ey, ez) < bestval) atomicOr(&sh.F[jl][a >> 5], 1u << (a & 31));
-                }
-            }
-        }
         FC_TICK(0);
         __syncthreads();
         FC_TICK(1);
         // ---- (2) lower the distances of the reached buckets, refresh their largest keys ----
         for (int jl = warp; jl < NBL; jl += FC_WARPS) {
-            const uint4 Fw = *reinterpret_cast<const uint4 *>(sh.F[jl]);
+            uint4 Fw = *reinterpret_cast<const uint4 *>(sh.F[jl]);
+            const bool any = (Fw.x | Fw.y | Fw.z | Fw.w) != 0u;
+            Fw.x &= sh.accmask[0]; Fw.y &= sh.accmask[1]; Fw.z &= sh.accmask[2]; Fw.w &= sh.accmask[3];   // accepted only
+            if (any) {
+                __syncwarp();
+                if (lane < 4) sh.F[jl][lane] = 0u;
+            }
             if (Fw.x | Fw.y | Fw.z | Fw.w) {
                 const int p = jl * 32 + lane;
                 const float x = s_x[p], y = s_y[p], z = s_z[p];
@@ -188,7 +207,7 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                     while (F) {
                         const int a = w * 32 + __ffs(F) - 1;
                         F &= F - 1;
-                        const float4 c = sh.acc[a];
+                        const float4 c = sh.s_xyz[a];
                         const float d = sq3_nofma(__fsub_rn(x, c.x), __fsub_rn(y, c.y), __fsub_rn(z, c.z));
                         dk = d < dk ? d : dk;
                     }
@@ -196,7 +215,6 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                 s_d[p] = dk;
                 fc_bucket_top(__float_as_uint(dk),
                               ((0xffffu - (unsigned)s_id[p]) << 16) | (unsigned)((jl * FC_C + rank) * 32 + lane), sh.top[jl], lane);
-                if (lane < 4) sh.F[jl][lane] = 0u;
             }
         }
         produced += A;
@@ -459,15 +477,14 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
             for (int q = 0; q < 4; ++q) {
                 const int r = q * 32 + lane;
                 const int rk = below + __popc(acc[q] & ((1u << lane) - 1u));
-                if (((acc[q] >> lane) & 1u) && rk < rem) {
-                    const float4 c = sh.s_xyz[r];
-                    sh.acc[rk] = c;
-                    if (rank == 0) {
-                        const unsigned idx = 0xffffu - ((unsigned)sh.s_key[r] >> 16);
-                        if (out64) out64[(int64_t)b * npoint + produced + rk] = idx;
-                        if (out32) out32[(int64_t)b * npoint + produced + rk] = (int32_t)idx;
-                    }
+                const bool take = ((acc[q] >> lane) & 1u) && rk < rem;
+                if (take && rank == 0) {
+                    const unsigned idx = 0xffffu - ((unsigned)sh.s_key[r] >> 16);
+                    if (out64) out64[(int64_t)b * npoint + produced + rk] = idx;
+                    if (out32) out32[(int64_t)b * npoint + produced + rk] = (int32_t)idx;
                 }
+                const unsigned tm = __ballot_sync(0xffffffffu, take);
+                if (lane == 0) sh.accmask[q] = tm;    // the next step applies rows tm of s_xyz
                 below += __popc(acc[q]);
             }
             if (lane == 0) {
@@ -475,6 +492,10 @@ fps_cluster_kernel(Cloud xyz, dvcp_cloud_index_t index, int N, int npoint, const
                 sh.n_cand = 0u;
                 sh.l_cnt = 0u;
             }
+        } else {
+            // meanwhile: which buckets can each CANDIDATE reach (the accepted ones are a subset; the bucket maxima the
+            // test reads do not change before the next step applies them)
+            box_tests(m, 1, FC_WARPS - 1);
         }
         FC_TICK(13);
         __syncthreads();
