@@ -339,6 +339,15 @@ def run_ours(args):
                              "algorithmic_mb": round(ab.get(name, 0) / 1e6, 3),
                              "achieved_gbs": None if gbs is None else round(gbs, 2),
                              "frac_hbm": None if gbs is None else round(gbs / peak, 5)}
+        if "fps" in kernels and kernels["fps"]["ms"] > 0:
+            # the sampling is a chain of dependent selections: picks per second and time per pick say more than a
+            # bandwidth fraction ("report rounds/s and time per round"). 2B clouds of N picks per step;
+            # a step of the cluster kernel yields ~81 picks per cloud
+            picks = 2 * B * N
+            kernels["fps"].update({"picks_per_s": round(picks / (kernels["fps"]["ms"] * 1e-3), 1),
+                                   "ns_per_pick_per_cloud": round(kernels["fps"]["ms"] * 1e6 / N, 2),
+                                   "clouds": 2 * B, "picks_per_cloud": N,
+                                   "note": "stage = index build + sampling (SA layer beside it on another stream)"})
         # The roofline object is for the KNN kernel: it is the kernel BASELINE.json's metric names and the
         # longest HBM-type kernel. The longest stage overall is the sampling ("fps", latency-bound: a chain of
         # dependent selections), which has no meaningful bandwidth roofline.
