@@ -97,10 +97,23 @@ class DeepVCP(nn.Module):
             e.record(torch.cuda.current_stream(dev))
             self._events.append((name, e))
 
-    def extract_features(self, src_pts, tgt_pts, starts=None, concurrent=False):
+    def prepare_index(self, src_pts, tgt_pts):
+        """The part of extract_features() that does not depend on the FPS starts: the two clouds side by side and
+        their spatial index (16 single-CTA sorts). A stream of batches builds it one batch further ahead, off the
+        critical path (pipeline.GraphedRegistration). Returns None when the forward takes another route."""
+        B, C_in, N = src_pts.shape
+        if (self.FE1.chained or src_pts.dtype != torch.float32 or tgt_pts.dtype != torch.float32 or
+                not (F_.SpatialIndex.indexable(N) and N > 2048 and 2 * self.FE1.sa1.npoint >= N)):
+            return None
+        with torch.no_grad():
+            both = torch.cat([src_pts, tgt_pts], dim=0)
+            return dict(both=both, index=F_.build_index(cloud_cm(both), both.device, 2 * B, N))
+
+    def extract_features(self, src_pts, tgt_pts, starts=None, concurrent=False, prepared=None):
         """First half of forward(): feature extraction of both clouds (deepVCP.py:29,72). Returns the
         state match() continues from. Split out so that a stream of batches can run this half (few SMs,
-        long) beside the second half of the previous batch (pipeline.StreamedRegistration)."""
+        long) beside the second half of the previous batch (pipeline.StreamedRegistration). prepared: the
+        result of prepare_index() on the same clouds."""
         if self.training:
             raise RuntimeError("extract_features / match are the inference kernels: call .eval() first (train mode goes "
                                "through forward(), see training.py)")
@@ -130,7 +143,7 @@ class DeepVCP(nn.Module):
             mark("begin")
             # feature extraction: source and target clouds go through each kernel in ONE
             # launch (2B independent clouds); features come out in FPS order
-            both = torch.cat([src, tgt], dim=0)
+            both = prepared["both"] if prepared else torch.cat([src, tgt], dim=0)
             if self.FE1.chained:
                 # three chained set-abstraction layers + fc through the module (one launch sequence for 2B clouds)
                 s0, s2 = torch.as_tensor(starts[0]), torch.as_tensor(starts[2])
@@ -148,7 +161,7 @@ class DeepVCP(nn.Module):
                 # features of a point do not depend on its FPS rank: build the index, then run the SA
                 # layer over the points in their ORIGINAL order beside the sampling, and put the rows
                 # into FPS order afterwards (feat_fps[s] = feat_orig[fps[s]]).
-                index = F_.build_index(cloud_cm(both), dev, 2 * B, N)
+                index = prepared["index"] if prepared else F_.build_index(cloud_cm(both), dev, 2 * B, N)
                 main = torch.cuda.current_stream(dev)
                 ev_index = torch.cuda.Event()
                 ev_index.record(main)
