@@ -230,6 +230,12 @@ class DeepVCP(nn.Module):
     def match(self, fe, R_init, keep_stages=False, topk_override=None, t_init=None):
         """Second half of forward(): key-point selection, candidates, KNN, embedding, CPG
         (deepVCP.py:33-110) on the state extract_features() returned."""
+        st = self.match_search(fe, R_init, keep_stages=keep_stages, topk_override=topk_override, t_init=t_init)
+        return self.match_finish(st, keep_stages=keep_stages)
+
+    def match_search(self, fe, R_init, keep_stages=False, topk_override=None, t_init=None):
+        """match() up to and including the KNN (many small CTAs: they share the GPU with the sampling of the next
+        batch); match_finish() continues with the persistent tensor-core kernels."""
         src, tgt, index, fps2, feat2, starts = fe["src"], fe["tgt"], fe["index"], fe["fps2"], fe["feat2"], fe["starts"]
         B, N, dev = fe["B"], fe["N"], fe["dev"]
         ilo = fe.get("index_lo", B)   # target clouds are batch items ilo..ilo+B-1 of the index
@@ -281,6 +287,20 @@ class DeepVCP(nn.Module):
                 kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
                                         want32=True)
             mark("knn")
+        return dict(fe=fe, tfeat=tfeat, sfps=sfps, tfps=tfps, sfeat=sfeat, scores=scores, topk=topk, keypts=keypts,
+                    picked=picked, cat=cat, src_dfe=src_dfe, centres=centres, cand=cand, kd=kd, ki64=ki64, ki32=ki32,
+                    G=G, C=C, dfe=dfe)
+
+    def match_finish(self, st, keep_stages=False):
+        """Embedding, CPG (deepVCP.py:93-110) on the state match_search() returned."""
+        fe = st["fe"]
+        tgt, B, N, dev = fe["tgt"], fe["B"], fe["N"], fe["dev"]
+        K = self.K_topk
+        tfeat, sfps, tfps, sfeat, scores, topk = st["tfeat"], st["sfps"], st["tfps"], st["sfeat"], st["scores"], st["topk"]
+        keypts, picked, cat, src_dfe, centres, cand = st["keypts"], st["picked"], st["cat"], st["src_dfe"], st["centres"], st["cand"]
+        kd, ki64, ki32, G, C, dfe = st["kd"], st["ki64"], st["ki32"], st["G"], st["C"], st["dfe"]
+        mark = lambda name: self._mark(name, dev)
+        with torch.no_grad():
             reshape_quirk = bool(self.quirks & QUIRK_COST_VOLUME_RESHAPE)
             fm = False   # tgt_dfe held feature-major per key-point ([B,K,32,C])?
             if self.dfe_tensor_cores:
