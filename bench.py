@@ -531,7 +531,8 @@ def main():
     # stdout carries exactly ONE JSON line. NCCL writes its debug output (the version banner at VERSION / WARN, the
     # ring and rank lines at INFO) to stdout unless NCCL_DEBUG_FILE names a file: the LEVEL the caller set is left
     # alone, the output is sent to stderr when the caller has not chosen a destination itself
-    if os.environ.get("NCCL_DEBUG") and "NCCL_DEBUG_FILE" not in os.environ:
+    # (the banner also appears with NCCL_DEBUG unset in this image, so the destination is set unconditionally)
+    if "NCCL_DEBUG_FILE" not in os.environ:
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
