@@ -7,17 +7,21 @@
 // (Wc = W3 W2 W1, bc = W3 (W2 b1 + b2) + b3) and this kernel evaluates
 //     Y[128 x 32] = X[128 x 40] * Wc^T[40 x 32]
 // per tile of 4 candidates x 32 neighbours, K = 32 weighted features + 3 local
-// coordinates + 1 (bias) + 4 zero columns, as a TF32 tensor-core GEMM with the
-// 3xTF32 split (X = Xh + Xl, W = Wh + Wl; Xh*Wh + Xh*Wl + Xl*Wh, FP32 accumulate
-// in TMEM), which keeps FP32-level accuracy (error ~2^-21 relative).
+// coordinates + 1 (bias) + 4 zero columns, on the tensor cores with a split that keeps FP32-level
+// accuracy: X = Xh + Xl with Xh the TF32 truncation and Xl the (13-bit) remainder, W = Wh + Wl;
+//     Y = Xh*Wh + Xh*Wl   (kind::tf32)   +   Xl*W   (kind::f16, Xl and W rounded to BF16)
+// all accumulated in FP32 in the same TMEM columns. Error: 2^-19 of |x||w| per product (BF16 rounding of Xl and
+// of W inside the small term Xl*W, itself 2^-11 of the product); measured
+// 4e-6 of the feature scale at the KITTI shape (bar: 1e-3).
 //
 // The kernel is bound by shared-memory bandwidth (the producers' operand stores, the gathered lines
-// coming through L1, and the tensor core's operand reads share one 128 B/clk pipe), so the MMA shapes are
-// chosen for the fewest operand bytes per tile: the GATHERED ROWS are the M-side operand (M = 128, read
-// once per MMA) and the N-side operand is the 64-row image [Wh ; Wl]: ONE N = 64 MMA forms Xh*Wh (TMEM
-// columns 0..31) and Xh*Wl (columns 32..63) from a single read of Xh, a second N = 32 MMA adds Xl*Wh to
-// columns 0..31. 10 MMAs and 55 KB of operand reads per tile (the channel-major form this replaces, weights
-// as a zero-padded 128-row M operand and N = 128: 15 MMAs, 120 KB, tensor pipe 61 % busy on 4x the useful work).
+// coming through L1, and the tensor core's operand reads share one 128 B/clk pipe), so the MMA shapes and
+// operand formats are chosen for the fewest operand bytes per tile: the GATHERED ROWS are the M-side operand
+// (M = 128, read once per MMA) and the N-side operand is the 64-row image [Wh ; Wl]: ONE N = 64 MMA forms
+// Xh*Wh (TMEM columns 0..31) and Xh*Wl (columns 32..63) from a single read of Xh; Xl is stored as BF16 (2
+// bytes per element on the store AND on the read side) and Xl*W takes three K = 16 MMAs (N = 32) into columns
+// 0..31. 8 MMAs and 45 KB of operand reads per tile (round 1's channel-major form: 15 MMAs, 120 KB, tensor pipe
+// 61 % busy on 4x the useful work; Xl as TF32: 10 MMAs, 55 KB, 0.83 ms against 0.77 ms now).
 // The accumulator is row-major (TMEM lane = neighbour, column = channel): an epilogue warp per candidate
 // adds the two column halves in registers and takes the max over its 32 lanes with a transposing butterfly
 // (16 shuffles per 16 channels).
@@ -29,7 +33,7 @@
 //               neighbours' feature rows into registers, scale by the distance weights (float64 in the
 //               reference, carried as float pairs), split hi/lo, store into shared memory in the UMMA
 //               K-major SWIZZLE_128B layout;
-//   warp 16     allocates TMEM, waits for the operand, issues the 10 tcgen05.mma of a tile from
+//   warp 16     allocates TMEM, waits for the operand, issues the 8 tcgen05.mma of a tile from
 //               one lane and commits to the mbarriers;
 //   warp 17     loader: the KNN indices / distances of the next run of 8 tiles (two contiguous 4 KB pieces)
 //               come in by cp.async.bulk (TMA) into a double buffer, completion counted on an mbarrier.
@@ -40,6 +44,8 @@
 // the same warps would have to read again -- more traffic on the shared-memory / L1 data pipe, which is the
 // binding resource of this kernel (ncu: LSU + tensor-core wavefronts fill 91 % of its cycles).
 // The operands reach the tensor core through shared-memory matrix descriptors.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dvcp {
@@ -53,6 +59,19 @@ constexpr int TC_A_BYTES = TC_A_SW_BYTES + TC_A_TAIL_BYTES;   // one A plane (hi
 constexpr int TC_B_BYTES = 32 * TC_K * 4;       // one weight plane as the host lays it out (32 channels)
 constexpr int TC_BW_BYTES = TC_B_BYTES;         // the N-side operand is [hi plane ; lo plane]: a 64-row image
 constexpr int TC_ACC_COLS = 64;                 // TMEM columns per accumulator: Xh*Wh + Xl*Wh | Xh*Wl
+// The low parts of the rows (X - Xh: 13 significant bits) are kept as BF16 (8 bits: the product's error stays at
+// 2^-19 of |x||w|, far inside the feature bar): 2 bytes per element instead of 4 on the operand stores and on the
+// tensor core's operand reads -- the resource that binds this kernel. Xl * W is then a kind::f16 MMA (K = 16 per
+// instruction) into the same accumulator. Layout: no-swizzle K-major core matrices (8 rows x 16 B) with the K
+// chunks 192 bytes apart (not 128: consecutive chunks then fall on different banks for the producers' 8-byte stores).
+constexpr int TC_L16_LBO = 192, TC_L16_KCHUNKS = 6;          // K = 48 = 32 features + 3 coordinates + 1 (bias) + zeros
+constexpr int TC_L16_SBO = TC_L16_KCHUNKS * TC_L16_LBO;      // 8-row groups 1152 bytes apart
+constexpr int TC_L16_BYTES = (TC_ROWS / 8) * TC_L16_SBO;     // 18 KB per stage
+constexpr int TC_W16_BYTES = 4 * TC_L16_SBO;                 // the 32 weight rows in the same layout
+__host__ __device__ constexpr int tc_l16_off(int r, int k) {
+    return (r >> 3) * TC_L16_SBO + (k >> 3) * TC_L16_LBO + (r & 7) * 16 + (k & 7) * 2;
+}
+static_assert(TC_A_SW_BYTES + TC_L16_BYTES + TC_A_TAIL_BYTES <= 2 * TC_A_BYTES, "stage layout");
 #ifndef DVCP_DFE_GROUPS
 #define DVCP_DFE_GROUPS 3
 #endif
@@ -68,7 +87,7 @@ constexpr int TC_W_BYTES = TC_PROD_WARPS * 32 * 8;   // per producer warp: (hi, 
 constexpr int TC_RUN = 8;                      // a CTA takes its tiles in runs of 8 consecutive tiles = 32 consecutive candidates
 constexpr int TC_T_BYTES = 32 * 33 * 4;        // epilogue transposition tile (feature-major output)
 constexpr int TC_RUN_BYTES = TC_RUN * 4 * 32 * 4;   // the idx (or dist) rows of one run of tiles: 32 candidates x 32 neighbours
-constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + TC_T_BYTES + 4 * TC_RUN_BYTES + 1024;   // + alignment slack
+constexpr int TC_SMEM = TC_STAGES * 2 * TC_A_BYTES + 2 * TC_BW_BYTES + TC_W_BYTES + 256 + TC_T_BYTES + 4 * TC_RUN_BYTES + TC_W16_BYTES + 1024;   // + alignment slack
 
 // first candidate of this CTA's i-th tile: runs of TC_RUN consecutive tiles, the runs dealt round-robin to the CTAs
 __device__ __forceinline__ int64_t tc_tile_cand(int i) {   // (tile counts fit 32 bits: checked by the launcher)
@@ -104,6 +123,12 @@ __device__ __forceinline__ uint64_t make_desc_tail(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
            (1ull << 46);
 }
+__device__ __forceinline__ uint64_t make_desc_l16(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((unsigned)TC_L16_LBO >> 4) << 16) |
+           ((uint64_t)((unsigned)TC_L16_SBO >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 with BF16 operands, FP32 accumulate, K-major, M = 128, N = 32
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((TC_M >> 4) << 24);
 // kind::tf32, FP32 accumulate, A and B K-major, M = 128 (rows of the tile), N = 64 ([Wh ; Wl]) or 32 (Wh)
 __host__ __device__ constexpr uint32_t tc_idesc(unsigned n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((TC_M >> 4) << 24); }
 
@@ -133,6 +158,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(tc_idesc(NCOLS)), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(TC_IDESC_BF16)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -156,12 +189,20 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     // neighbour indices / distances of a run of tiles, double-buffered, filled by cp.async.bulk (16-byte aligned)
     unsigned char *sRun = reinterpret_cast<unsigned char *>(sT) + TC_T_BYTES + ((16u - ((TC_T_BYTES) & 15u)) & 15u);
     uint64_t *rfull = bars + 4 * TC_STAGES + 1, *rempty = rfull + 2;
+    unsigned char *sW16 = sRun + 4 * TC_RUN_BYTES;   // the weights as BF16, N-side operand of the low-part MMAs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the layout is row-block major, so the host's two 32-row images back to back are the 64-row image [Wh ; Wl]
     for (int i = threadIdx.x; i < TC_BW_BYTES / 4; i += blockDim.x) {
         reinterpret_cast<float *>(sB)[i] = Bhi[i];
         reinterpret_cast<float *>(sB + TC_BW_BYTES)[i] = Blo[i];
+    }
+    for (int i = threadIdx.x; i < TC_W16_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(sW16)[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * TC_K; i += blockDim.x) {
+        const int n = i / TC_K, k = i - n * TC_K;
+        const float w = Bhi[tc_off(n, k) / 4] + Blo[tc_off(n, k) / 4];
+        *reinterpret_cast<__nv_bfloat16 *>(sW16 + tc_l16_off(n, k)) = __float2bfloat16_rn(w);
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -196,7 +237,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
 
     if (warp == TC_MMA_WARP) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t a_base = smem_u32(sA), b_w = smem_u32(sB);   // [Wh ; Wl], 64 rows
+        const uint32_t a_base = smem_u32(sA), b_w = smem_u32(sB), w16 = smem_u32(sW16);   // [Wh ; Wl], 64 rows; W as BF16
         for (int i = 0; i < my_tiles; ++i) {
             const int s = (int)(i % TC_STAGES);
             const unsigned ph = (unsigned)((i / TC_STAGES) & 1);
@@ -205,18 +246,21 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t d = tmem_base + (uint32_t)s * TC_ACC_COLS;   // 64 FP32 columns per accumulator
-                const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_lo = a_hi + TC_A_SW_BYTES;
-                const uint32_t t_hi = a_hi + 2 * TC_A_SW_BYTES, t_lo = t_hi + TC_A_TAIL_BYTES;
+                // stage: [Xh features, SWIZZLE_128B | Xl, BF16 | Xh coordinates + bias]
+                const uint32_t a_hi = a_base + (uint32_t)s * 2 * TC_A_BYTES, a_l16 = a_hi + TC_A_SW_BYTES;
+                const uint32_t t_hi = a_l16 + TC_L16_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t ka = (uint32_t)ks * 32;          // 8 floats inside the 128-byte swizzled row
                     const uint32_t kb = (uint32_t)ks * 2 * 128;     // two 16-byte K chunks of W per MMA (K = 8)
-                    // M side: the gathered rows; N side: [Wh ; Wl] (columns 0..31 | 32..63), then Wh alone for Xl
+                    // M side: the gathered rows; N side: [Wh ; Wl] (columns 0..31 | 32..63)
                     umma_tf32<64>(d, make_desc_sw128(a_hi + ka), make_desc(b_w + kb), ks > 0);
-                    umma_tf32<32>(d, make_desc_sw128(a_lo + ka), make_desc(b_w + kb), 1u);
                 }
                 umma_tf32<64>(d, make_desc_tail(t_hi), make_desc(b_w + 4 * 2 * 128), 1u);
-                umma_tf32<32>(d, make_desc_tail(t_lo), make_desc(b_w + 4 * 2 * 128), 1u);
+                // Xl (BF16) * W (BF16) into columns 0..31: three K = 16 steps
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    umma_bf16(d, make_desc_l16(a_l16 + (uint32_t)j * 2 * TC_L16_LBO), make_desc_l16(w16 + (uint32_t)j * 2 * TC_L16_LBO));
                 umma_commit(&empty[s]);   // shared-memory stage may be rewritten
                 umma_commit(&tfull[s]);   // accumulator is complete
             }
@@ -331,10 +375,15 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
         const bool xyz4 = txyz.ps == 4 && txyz.cs == 1 && txyz.bs % 4 == 0 && (reinterpret_cast<uintptr_t>(txyz.p) & 15) == 0;
         // stage s == group: a group always rebuilds its own stage
         unsigned char *const ahi = sA + (size_t)group * 2 * TC_A_BYTES;
-        unsigned char *const thi = ahi + 2 * TC_A_SW_BYTES + tc_tail_off(cw * 32 + lane, 0);
-        // columns 36..39 are zero padding: written once, never touched again
-        *reinterpret_cast<float4 *>(thi + 128) = make_float4(0.f, 0.f, 0.f, 0.f);                     // tc_tail_off(r, 4)
-        *reinterpret_cast<float4 *>(thi + TC_A_TAIL_BYTES + 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned char *const al16 = ahi + TC_A_SW_BYTES;                                   // Xl, BF16
+        unsigned char *const thi = al16 + TC_L16_BYTES + tc_tail_off(cw * 32 + lane, 0);     // Xh, coordinates + bias
+        unsigned char *const tl16 = al16 + tc_l16_off(cw * 32 + lane, 32);                   // Xl, coordinates (K chunk 4)
+        // zero padding, written once, never touched again: columns 36..39 of both parts, columns 40..47 of Xl
+        *reinterpret_cast<float4 *>(thi + 128) = make_float4(0.f, 0.f, 0.f, 0.f);            // tc_tail_off(r, 4)
+        *reinterpret_cast<uint2 *>(tl16 + 8) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint4 *>(tl16 + TC_L16_LBO) = make_uint4(0u, 0u, 0u, 0u);
+        // Xl feature rows: row r = cw * 32 + 4 g + rsub, my four columns 4 * chunk .. + 3 (8 bytes)
+        unsigned char *const lrow = al16 + (cw * 4) * TC_L16_SBO + (chunk >> 1) * TC_L16_LBO + rsub * 16 + (chunk & 1) * 8;
         // row 4 g + rsub of candidate cw: 128-byte rows, the 16-byte chunk c of row r sits at chunk c ^ (r & 7)
         // (SWIZZLE_128B); r & 7 alternates between rsub and rsub + 4, so two bases + immediates address all rows
         unsigned char *const row0 = ahi + (cw * 32 + rsub) * 128 + ((chunk ^ rsub) << 4);
@@ -441,7 +490,7 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 const float2 f01 = make_float2(f[g].x, f[g].y), f23 = make_float2(f[g].z, f[g].w);
                 const float2 v01 = __ffma2_rn(f01, h01, __fmul2_rn(f01, l01));
                 const float2 v23 = __ffma2_rn(f23, h23, __fmul2_rn(f23, l23));
-                float4 hv, lv;
+                float4 hv;
                 hv.x = __uint_as_float(__float_as_uint(v01.x) & 0xffffe000u);
                 hv.y = __uint_as_float(__float_as_uint(v01.y) & 0xffffe000u);
                 hv.z = __uint_as_float(__float_as_uint(v23.x) & 0xffffe000u);
@@ -449,10 +498,11 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                 const float2 m1 = make_float2(-1.f, -1.f);
                 const float2 d01 = __ffma2_rn(make_float2(hv.x, hv.y), m1, v01);   // v - hi, exact
                 const float2 d23 = __ffma2_rn(make_float2(hv.z, hv.w), m1, v23);
-                lv = make_float4(d01.x, d01.y, d23.x, d23.y);
                 unsigned char *const dst = ((g & 1) ? row1 : row0) + g * 512;
                 *reinterpret_cast<float4 *>(dst) = hv;
-                *reinterpret_cast<float4 *>(dst + TC_A_SW_BYTES) = lv;
+                const __nv_bfloat162 p01 = __floats2bfloat162_rn(d01.x, d01.y), p23 = __floats2bfloat162_rn(d23.x, d23.y);
+                *reinterpret_cast<uint2 *>(lrow + (g >> 1) * TC_L16_SBO + (g & 1) * 64) =
+                    make_uint2(*reinterpret_cast<const unsigned *>(&p01), *reinterpret_cast<const unsigned *>(&p23));
             }
             {
                 float4 hv, lv;
@@ -465,7 +515,9 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
                     lp[e] = le[e] - t;
                 }
                 *reinterpret_cast<float4 *>(thi) = hv;
-                *reinterpret_cast<float4 *>(thi + TC_A_TAIL_BYTES) = lv;
+                const __nv_bfloat162 q01 = __floats2bfloat162_rn(lv.x, lv.y), q23 = __floats2bfloat162_rn(lv.z, lv.w);
+                *reinterpret_cast<uint2 *>(tl16) =
+                    make_uint2(*reinterpret_cast<const unsigned *>(&q01), *reinterpret_cast<const unsigned *>(&q23));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
