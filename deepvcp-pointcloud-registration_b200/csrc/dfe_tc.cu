@@ -63,10 +63,11 @@ constexpr int TC_ACC_COLS = 64;                 // TMEM columns per accumulator:
 // 2^-19 of |x||w|, far inside the feature bar): 2 bytes per element instead of 4 on the operand stores and on the
 // tensor core's operand reads -- the resource that binds this kernel. Xl * W is then a kind::f16 MMA (K = 16 per
 // instruction) into the same accumulator. Layout: no-swizzle K-major core matrices (8 rows x 16 B) with the K
-// chunks 192 bytes apart (not 128: consecutive chunks then fall on different banks for the producers' 8-byte stores).
-constexpr int TC_L16_LBO = 192, TC_L16_KCHUNKS = 6;          // K = 48 = 32 features + 3 coordinates + 1 (bias) + zeros
-constexpr int TC_L16_SBO = TC_L16_KCHUNKS * TC_L16_LBO;      // 8-row groups 1152 bytes apart
-constexpr int TC_L16_BYTES = (TC_ROWS / 8) * TC_L16_SBO;     // 18 KB per stage
+// chunks 160 bytes apart (not 128): the four chunks a half-warp's 8-byte stores touch then start 8 banks apart and
+// the store is conflict-free (at 128 all four fall on the same banks, at 192 they collide in pairs: measured).
+constexpr int TC_L16_LBO = 160, TC_L16_KCHUNKS = 6;          // K = 48 = 32 features + 3 coordinates + 1 (bias) + zeros
+constexpr int TC_L16_SBO = TC_L16_KCHUNKS * TC_L16_LBO;      // 8-row groups 960 bytes apart
+constexpr int TC_L16_BYTES = (TC_ROWS / 8) * TC_L16_SBO;     // 15 KB per stage
 constexpr int TC_W16_BYTES = 4 * TC_L16_SBO;                 // the 32 weight rows in the same layout
 __host__ __device__ constexpr int tc_l16_off(int r, int k) {
     return (r >> 3) * TC_L16_SBO + (k >> 3) * TC_L16_LBO + (r & 7) * 16 + (k & 7) * 2;
