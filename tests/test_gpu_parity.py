@@ -978,3 +978,23 @@ def test_chained_feature_extraction_and_forward_vs_oracle(dv, F, synthetic):
     torch.manual_seed(99)
     a = model.draw_starts(2, N)
     assert a[0].shape == (3, 2) and a[1].shape == (2,) and a[2].shape == (3, 2)
+
+
+def test_dfe_tensor_core_kernel_ragged_batches(dv, F, synthetic):
+    """Several clouds with a candidate count that is no multiple of a tile (4), a run (32) or anything else: runs of
+    tiles cross cloud boundaries (the cloud index of a candidate comes from a float quotient + correction), the last
+    run is clipped (the bulk copies of the index stream too). Against the FP32 CUDA-core kernel, both weight modes."""
+    lib = importlib.import_module(PKG + "._lib")
+    torch.manual_seed(21)
+    dfe = dv.feat_embedding_layer().to(DEV)
+    for B, N, Q in ((3, 1024, 125 * 7 + 3), (5, 300, 37), (2, 4096, 32 * 41 + 31)):
+        g = torch.Generator().manual_seed(B * 1000 + Q)
+        tg = (torch.rand(B, 3, N, generator=g) * 4 - 2).to(DEV)
+        tfeat = torch.randn(B, N, 32, generator=g).to(DEV)
+        cq = (torch.rand(B, Q, 3, generator=g) * 4 - 2).to(DEV)
+        kd, _, ki = F.knn(lib.cloud_cm(tg), tg.device, B, N, cq, 32, want64=False, want32=True)
+        b_hi, b_lo = dfe.tc_operand()
+        for quirks in (lib.QUIRKS_REFERENCE, lib.QUIRKS_INTENDED):
+            ref = F.dfe_tgt_fused(cq, lib.cloud_cm(tg), tfeat, kd, ki, B, N, dfe.params(), quirks)
+            out = F.dfe_tgt_tc(cq, lib.cloud_cm(tg), tfeat, kd, ki, B, N, b_hi, b_lo, quirks)
+            assert rel_err(out, ref) < 2e-5, (B, N, Q, quirks)
