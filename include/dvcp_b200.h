@@ -75,13 +75,13 @@ typedef struct {
     int in_ch, out_ch;
 } dvcp_mlp_layer_t;
 
-/* Spatial index of a cloud (64 <= N <= 16384; up to 131072 through dvcp_build_index_ws): the points in Morton order, cut
+/* Spatial index of a cloud (64 <= N <= 16384; up to 131072 through dvcp_build_index_ws): the points in space-filling-curve (Hilbert) order, cut
  * into buckets of 32 consecutive points with their bounding boxes. Built by
  * dvcp_build_index, or as a by-product of dvcp_fps (which sorts the cloud
  * anyway); consumed by the pruned ball-query / SA / KNN kernels. Pruning never
  * changes results: members are always decided by the exact arithmetic. */
 typedef struct {
-    float *sorted_pt;    /* [B, cap, 4]  x, y, z, original index (int32 bits) in Morton order;
+    float *sorted_pt;    /* [B, cap, 4]  x, y, z, original index (int32 bits) in curve order;   
                             unused slots +inf, +inf, +inf, -1: one 16-byte load per point       */
     float *bucket_box;   /* [B, cap/32, 8] minx,miny,minz,maxx,maxy,maxz,count,0                */
     int cap;             /* dvcp_index_capacity(N)                                              */
