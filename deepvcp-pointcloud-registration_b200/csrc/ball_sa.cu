@@ -243,7 +243,7 @@ sa_layer_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict__ cidx,
     }
 }
 
-// Pruned variant: uses the spatial index (Morton buckets + boxes). A bucket can
+// Pruned variant: uses the spatial index (Hilbert buckets + boxes). A bucket can
 // hold a member only if its box is within sqrt(r^2 + E) of the centre, where E
 // bounds the rounding error of the expanded-form distance: |d2_fl - d2| <=
 // 12 * 2^-24 * (|q| + |p|)^2 (three roundings in the dot product and each squared
@@ -290,7 +290,7 @@ sa_layer_pruned_kernel(Cloud xyz, Cloud feats, int D, const int32_t *__restrict_
         const float E = 8e-7f * (qn + pn) * (qn + pn);
         return lb * 0.9999f <= r2 + E;
     };
-    // level 1: lane l tests the union box of its T Morton-consecutive buckets
+    // level 1: lane l tests the union box of its T Hilbert-consecutive buckets
     float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
     for (int t = 0; t < T; ++t) {
         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
@@ -405,7 +405,7 @@ sa_layer_fast_kernel(Cloud xyz, Cloud feats, const int32_t *__restrict__ cidx, i
     const int cap = index.cap, NB = cap / 32, T = NB / 32;
     const float *box = index.bucket_box + (int64_t)b * NB * 8;
     const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
-    // union box of this lane's T Morton-consecutive buckets
+    // union box of this lane's T Hilbert-consecutive buckets
     float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
     for (int t = 0; t < T; ++t) {
         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));
@@ -591,7 +591,7 @@ sa_layer_fast_kernel(Cloud xyz, Cloud feats, const int32_t *__restrict__ cidx, i
 
 // ------------------------------------------- SA layer of EVERY point, by bucket --
 // When every point of the cloud is a centroid (DeepVCP: npoint == N) the search can be
-// shared: a warp takes one Morton bucket, lane = centroid, finds the few buckets whose box
+// shared: a warp takes one Hilbert bucket, lane = centroid, finds the few buckets whose box
 // some lane's ball can reach, stages each in shared memory and lets every lane test the 32
 // staged points with the exact arithmetic. Members go to a per-lane list; the shared MLP is
 // then evaluated member after member with the 32 running maxima of the lane's centroid in
@@ -636,7 +636,7 @@ sa_layer_bucket_kernel(Cloud feats, int N, float r2, int nsample, SaParams P, dv
     const int cap = index.cap, NB = cap / 32, T = NB / 32;
     const float *box = index.bucket_box + (int64_t)b * NB * 8;
     const float4 *spt = reinterpret_cast<const float4 *>(index.sorted_pt) + (int64_t)b * cap;
-    // union box of this lane's T Morton-consecutive buckets
+    // union box of this lane's T Hilbert-consecutive buckets
     float snx = INFINITY, sny = INFINITY, snz = INFINITY, sxx = -INFINITY, sxy = -INFINITY, sxz = -INFINITY;
     for (int t = 0; t < T; ++t) {
         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(box + (int64_t)(lane * T + t) * 8));

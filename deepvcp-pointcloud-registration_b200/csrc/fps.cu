@@ -6,7 +6,7 @@
 //
 // Two kernels:
 //  * fps_bucketed_kernel  (float32, N <= 16384): exact spatially-pruned FPS. The
-//    cloud is Morton-sorted into buckets of 32 points (one warp lane per point),
+//    cloud is Hilbert-sorted into buckets of 32 points (one warp lane per point),
 //    each bucket keeps its bounding box and the (max dist, lowest index) of its
 //    members. A round only revisits buckets whose box lower bound -- evaluated
 //    with the same rounded arithmetic, hence never above any member's rounded
@@ -97,7 +97,7 @@ __device__ __forceinline__ float warp_max_f(float v) {
 }
 
 // WARPS warps; each warp owns BPW buckets of 32 points: capacity WARPS * BPW * 32.
-// Bucket j (32 consecutive points of the Morton order) belongs to warp j % WARPS,
+// Bucket j (32 consecutive points of the Hilbert order) belongs to warp j % WARPS,
 // slot j / WARPS: spatial neighbours are spread over the warps, so the few
 // buckets a round revisits are processed in parallel instead of by one warp.
 template <int WARPS, int BPW, bool BATCHED>
@@ -122,7 +122,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
     const float *p = base + (int64_t)b * bs;
     const unsigned startidx = start ? (unsigned)start[b] : 0u;
 
-    // ---- cloud bounding box -> Morton keys -> block sort (prologue, once) ----
+    // ---- cloud bounding box -> Hilbert keys -> block sort (prologue, once) ----
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int n = tid; n < N; n += THREADS) {
 #pragma unroll
@@ -153,7 +153,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         mn[c] = a;
         ext = fmaxf(ext, z - a);
     }
-    // one scale for all axes: Morton cells are cubes, buckets stay compact
+    // one scale for all axes: Hilbert cells are cubes, buckets stay compact
     const float scale = ext > 0.f ? 1023.0f / ext : 0.0f;
     unsigned keys[ITEMS], vals[ITEMS];
 #pragma unroll
@@ -194,7 +194,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         sidx[pos] = (unsigned short)n;
     }
     __syncthreads();
-    // optional: publish the Morton-ordered cloud as a spatial index (ball query / KNN reuse it)
+    // optional: publish the Hilbert-ordered cloud as a spatial index (ball query / KNN reuse it)
     if (index.sorted_pt) {
         float4 *op = reinterpret_cast<float4 *>(index.sorted_pt) + (int64_t)b * CAP;
         for (int i = tid; i < CAP; i += THREADS) {

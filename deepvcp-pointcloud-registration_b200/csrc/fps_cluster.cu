@@ -6,7 +6,7 @@
 // selections per block-wide step) leaves the per-step bucket updates as the bulk of
 // the work; this kernel spreads them over 8 SMs and keeps ONE cluster barrier per
 // step:
-//   * the cloud arrives Morton-sorted with bucket boxes (dvcp_build_index); bucket j
+//   * the cloud arrives Hilbert-sorted with bucket boxes (dvcp_build_index); bucket j
 //     belongs to CTA j % 8, so every centroid's neighbourhood is spread over the CTAs;
 //   * per step each CTA (1) applies the centroids accepted in the previous step to
 //     the buckets they can reach, (2) finds its buckets' best keys above its own

@@ -1,15 +1,15 @@
 // Spatial index of clouds larger than one CTA can sort (16384 < N <= 131072).
 //
-// Same product as the single-CTA builder in fps.cu (dvcp_cloud_index_t: points in Morton order as
+// Same product as the single-CTA builder in fps.cu (dvcp_cloud_index_t: points in Hilbert order as
 // float4 (x, y, z, index bits), buckets of 32 with boxes), built by several CTAs per cloud:
 //   1. bounding box: block reductions + 6 atomics per CTA on order-preserving integer images;
-//   2. runs: each CTA sorts 16384 (key = 30-bit Morton code, value = point index) pairs in shared
+//   2. runs: each CTA sorts 16384 (key = 30-bit Hilbert code, value = point index) pairs in shared
 //      memory (CUB block radix sort, the same primitive the single-CTA builder uses);
 //   3. merges: log2(cap / 16384) passes; every element finds its output slot by its own offset plus
 //      its rank in the partner run (binary search; lower bound for the left run, upper bound for
 //      the right one, so equal keys give a permutation). No shared memory, all reads hit L2;
 //   4. publish: a warp per bucket writes the float4 points and the bucket's box.
-// The order among equal Morton codes is irrelevant to every consumer: pruning by boxes never changes
+// The order among equal Hilbert codes is irrelevant to every consumer: pruning by boxes never changes
 // results (members are always decided by the exact arithmetic).
 //
 // Consumer: dvcp_knn_indexed (knn.cu) -- SURVEY 8(d) SWEEP row, KNN at N = 32k..128k. The sampling /
@@ -71,7 +71,7 @@ ib_bbox_kernel(Cloud c, int N, unsigned *__restrict__ bbox) {
     if (threadIdx.x < 6) atomicMin(&bbox[b * 6 + threadIdx.x], s[threadIdx.x]);
 }
 
-// one CTA per run of IB_RUN slots of one cloud: Morton keys -> sorted (key, value) run
+// one CTA per run of IB_RUN slots of one cloud: Hilbert keys -> sorted (key, value) run
 __global__ void __launch_bounds__(IB_THREADS, 1)
 ib_run_sort_kernel(Cloud c, int N, int cap, const unsigned *__restrict__ bbox, unsigned *__restrict__ keys,
                    unsigned *__restrict__ vals) {

@@ -8,7 +8,7 @@
 namespace dvcp {
 
 // ------------------------------------------------------ indexed KNN ---------
-// Same contract, but the reference cloud comes with its spatial index (Morton
+// Same contract, but the reference cloud comes with its spatial index (Hilbert
 // buckets of 32 points + boxes). Per query:
 //   * lb[j] = fma-chain squared distance from the query to bucket j's box,
 //     evaluated on the clamped offsets with the SAME rounded arithmetic as the
@@ -99,7 +99,7 @@ struct KnnKey {
     }
 };
 
-// Two-level pruning. Level 1 "super-buckets" of TT = min(T, 32) Morton-consecutive buckets; lane l owns
+// Two-level pruning. Level 1 "super-buckets" of TT = min(T, 32) Hilbert-consecutive buckets; lane l owns
 // the SB = max(T / 32, 1) super-buckets s * 32 + l (T = buckets / 32 = cap / 1024).
 struct Box6 {
     float nx, ny, nz, xx, xy, xz;   // min, max
@@ -131,7 +131,7 @@ constexpr float KNI_LOOSE = 3.0f;   // measured: K8 unchanged for >= 3, ModelNet
 // What one warp needs to search one cloud.
 struct KnnCtx {
     const float *box;          // bucket boxes of the cloud
-    const float4 *spt;         // points in Morton order
+    const float4 *spt;         // points in Hilbert order
     const float4 *spt_lane;    // spt + lane: slot `lane` of bucket j is spt_lane[j * 32] (one IMAD.WIDE per visit)
     const float4 *box_lane;    // box of bucket (g * TT + lane): box_lane[g * TT * 2]
     unsigned long long *buf;   // this warp's KNI_BUF-entry scratch list in shared memory
