@@ -26,9 +26,7 @@
 
 namespace dvcp {
 
-constexpr int CT_THREADS = 512;
 constexpr int CT_MAXG = 11;
-constexpr int CT_TMEM_COLS = 512;
 constexpr int CT_B_FLOATS_Q = 27 * 2 * 32 * 4;   // per channel octet: [tap][k half][hi cout 0..15 | lo cout 0..15][4]
 constexpr int CT_B_FLOATS = 4 * CT_B_FLOATS_Q;
 
@@ -85,6 +83,7 @@ __global__ void cpg_tc_prepare_kernel(const float *__restrict__ w1, float *__res
     image[i] = h == 0 ? hi : w - hi;
 }
 
+template <int TH>
 __device__ __forceinline__ float ct_block_sum(float v, float *red, int tid) {
 #pragma unroll
     for (int s = 16; s; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
@@ -93,16 +92,19 @@ __device__ __forceinline__ float ct_block_sum(float v, float *red, int tid) {
     __syncthreads();
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < CT_THREADS / 32; ++w) t += red[w];
+    for (int w = 0; w < TH / 32; ++w) t += red[w];
     return t;
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 1)
+// TH threads per CTA: 512 with one CTA per SM for the large volumes; 256 with TWO CTAs per SM for small grids (G <= 6),
+// whose volumes are a chain of short phases separated by barriers -- two co-resident CTAs fill each other's gaps.
+template <int TH>
+__global__ void __launch_bounds__(TH, TH == 512 ? 1 : 2)
 cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, const float *__restrict__ cand, int64_t M,
-              int G, int R, const float *__restrict__ bimage, dvcp_cpg_params_t p, float *__restrict__ vcp,
-              float *__restrict__ logits_out) {
+              int G, int R, unsigned tmem_cols, const float *__restrict__ bimage, dvcp_cpg_params_t p,
+              float *__restrict__ vcp, float *__restrict__ logits_out) {
     extern __shared__ __align__(128) unsigned char ct_smem[];
-    __shared__ float red[CT_THREADS / 32];
+    __shared__ float red[TH / 32];
     __shared__ __align__(16) float s_src[32];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -110,7 +112,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
     const int Gp = G + 2, Gp2 = Gp * Gp, C = G * G * G, Cp = (C + 3) & ~3;
     const int m_lo = Gp2 + Gp + 1;                             // first interior row of the padded volume
     const int ntiles = ((G - 1) * m_lo + 1 + 127) >> 7;        // M tiles of 128 padded rows over the interior span
-    const int nissue = ntiles < CT_THREADS / 32 ? ntiles : CT_THREADS / 32;   // warps that issue MMAs (one commit each)
+    const int nissue = ntiles < TH / 32 ? ntiles : TH / 32;   // warps that issue MMAs (one commit each)
     // shared memory: A planes [hi k0 | hi k1 | lo k0 | lo k1][R rows][16 B]; B image of the current octet; W2; W3
     float4 *sA = reinterpret_cast<float4 *>(ct_smem);
     float *sB = reinterpret_cast<float *>(ct_smem + (size_t)4 * R * 16);
@@ -119,18 +121,18 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
     // after conv1 the A region is dead and holds conv1 out [16][Cp], conv2 out [4][Cp], logits [Cp]
     float *A1 = reinterpret_cast<float *>(ct_smem), *O2 = A1 + 16 * Cp, *LG = O2 + 4 * Cp;
 
-    for (int i = tid; i < 27 * 16 * 4; i += CT_THREADS) {
+    for (int i = tid; i < 27 * 16 * 4; i += TH) {
         const int co = i & 3, ci = (i >> 2) & 15, tap = i >> 6;
         W2[i] = __ldg(p.w2 + (co * 16 + ci) * 27 + tap);
     }
-    for (int i = tid; i < 27 * 4; i += CT_THREADS) W3[i] = __ldg(p.w3 + (i & 3) * 27 + (i >> 2));
+    for (int i = tid; i < 27 * 4; i += TH) W3[i] = __ldg(p.w3 + (i & 3) * 27 + (i >> 2));
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ct_smem_u32(&s_bar)), "r"((unsigned)nissue));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ct_smem_u32(&s_tmem)),
-                     "r"((unsigned)CT_TMEM_COLS)
+                     "r"(tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -147,17 +149,17 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         const float *t = tgt + m * 32 * (int64_t)C;
         __syncthreads();   // the previous volume is finished with the shared volumes
         // zero the A planes (halo rows must read as zero; the conv stages of the previous volume overwrote them)
-        for (int i = tid; i < 4 * R; i += CT_THREADS) sA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < 4 * R; i += TH) sA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < 32) s_src[tid] = __ldg(src + m * 32 + tid);
         __syncthreads();
         // software pipeline over the four channel octets: the weight image of octet q+1 (cp.async into the other
         // B buffer) and its target values (registers) are fetched while the tensor core works on octet q
-        constexpr int CT_VPT = 3;   // voxels per thread: ceil(11^3 / 512)
+        constexpr int CT_VPT = TH == 512 ? 3 : 1;   // voxels per thread: ceil(11^3 / 512); 6^3 <= 256
         float4 pt0[CT_VPT], pt1[CT_VPT];
         auto fetch_tgt = [&](int q) {
 #pragma unroll
             for (int u = 0; u < CT_VPT; ++u) {
-                const int c = tid + u * CT_THREADS;
+                const int c = tid + u * TH;
                 if (c < C) {
                     pt0[u] = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q));
                     pt1[u] = __ldg(reinterpret_cast<const float4 *>(t + (int64_t)c * 32 + 8 * q + 4));
@@ -167,7 +169,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         auto fetch_b = [&](int q) {
             const float4 *bi = reinterpret_cast<const float4 *>(bimage + (size_t)q * CT_B_FLOATS_Q);
             const uint32_t dst = ct_smem_u32(sB) + (uint32_t)(q & 1) * (CT_B_FLOATS_Q * 4);
-            for (int i = tid; i < CT_B_FLOATS_Q / 4; i += CT_THREADS)
+            for (int i = tid; i < CT_B_FLOATS_Q / 4; i += TH)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(bi + i) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -178,7 +180,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
             const float4 s0 = *reinterpret_cast<const float4 *>(s_src + 8 * q), s1 = *reinterpret_cast<const float4 *>(s_src + 8 * q + 4);
 #pragma unroll
             for (int u = 0; u < CT_VPT; ++u) {
-                const int c = tid + u * CT_THREADS;
+                const int c = tid + u * TH;
                 if (c >= C) continue;
                 const float4 t0 = pt0[u], t1 = pt1[u];
                 const int z = c % G, y = (c / G) % G, x = c / (G * G);
@@ -211,7 +213,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
             if (warp < nissue) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const bool leader = ct_elect_one();
-                for (int tile = warp; tile < ntiles; tile += CT_THREADS / 32) {
+                for (int tile = warp; tile < ntiles; tile += TH / 32) {
                     const uint32_t d = tmem_base + (uint32_t)tile * 32u;   // columns 0..15: Vh Wh + Vl Wh, 16..31: Vh Wl
                     const uint32_t row0 = (uint32_t)(m_lo + tile * 128);
                     const uint64_t a0 = ct_desc(a_base + row0 * 16u, plane, 128u);
@@ -243,7 +245,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         // ---- conv1 accumulators: TMEM -> + bias -> shared [16][Cp] ----
         {
             const int lq = warp & 3;   // a warp reads the TMEM lanes 32 (warp % 4) .. + 31
-            for (int tile = warp >> 2; tile < ntiles; tile += CT_THREADS / 128) {
+            for (int tile = warp >> 2; tile < ntiles; tile += TH / 128) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)tile * 32u;
                 asm volatile(
@@ -273,7 +275,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         {
             constexpr int ZV = 3;
             const int NG = (G + ZV - 1) / ZV, items = G * G * NG;
-            for (int it = tid; it < items; it += CT_THREADS) {
+            for (int it = tid; it < items; it += TH) {
                 const int line = it / NG, zg = it - line * NG;
                 const int x = line / G, y = line - x * G, z0 = zg * ZV;
                 float2 a2[ZV][2];
@@ -325,7 +327,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         }
         __syncthreads();
         // ---- conv3 4 -> 1: thread per voxel ----
-        for (int c = tid; c < C; c += CT_THREADS) {
+        for (int c = tid; c < C; c += TH) {
             const int iz = c % G, iy = (c / G) % G, ix = c / (G * G);
             float a3 = b3;
             for (int dx = -1; dx <= 1; ++dx) {
@@ -355,7 +357,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
         // ---- softmax over the C voxels + weighted candidate sum ----
         {
             float mx = -INFINITY;
-            for (int c = tid; c < C; c += CT_THREADS) mx = fmaxf(mx, LG[c]);
+            for (int c = tid; c < C; c += TH) mx = fmaxf(mx, LG[c]);
 #pragma unroll
             for (int s = 16; s; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
             __syncthreads();
@@ -363,21 +365,21 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
             __syncthreads();
             mx = red[0];
 #pragma unroll
-            for (int w = 1; w < CT_THREADS / 32; ++w) mx = fmaxf(mx, red[w]);
+            for (int w = 1; w < TH / 32; ++w) mx = fmaxf(mx, red[w]);
             float zp = 0.f;
-            for (int c = tid; c < C; c += CT_THREADS) zp += expf(LG[c] - mx);
-            const float Z = ct_block_sum(zp, red, tid);
+            for (int c = tid; c < C; c += TH) zp += expf(LG[c] - mx);
+            const float Z = ct_block_sum<TH>(zp, red, tid);
             const float *cp = cand + m * C * 3;
             float a[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int c = tid; c < C; c += CT_THREADS) {
+            for (int c = tid; c < C; c += TH) {
                 const float w = expf(LG[c] - mx) / Z;
                 a[0] = fmaf(w, __ldg(cp + 3 * c), a[0]);
                 a[1] = fmaf(w, __ldg(cp + 3 * c + 1), a[1]);
                 a[2] = fmaf(w, __ldg(cp + 3 * c + 2), a[2]);
                 a[3] += w;
             }
-            const float sx = ct_block_sum(a[0], red, tid), sy = ct_block_sum(a[1], red, tid),
-                        sz = ct_block_sum(a[2], red, tid), sw = ct_block_sum(a[3], red, tid);
+            const float sx = ct_block_sum<TH>(a[0], red, tid), sy = ct_block_sum<TH>(a[1], red, tid),
+                        sz = ct_block_sum<TH>(a[2], red, tid), sw = ct_block_sum<TH>(a[3], red, tid);
             if (tid == 0) {
                 vcp[m * 3] = sx / sw;
                 vcp[m * 3 + 1] = sy / sw;
@@ -388,7 +390,7 @@ cpg_tc_kernel(const float *__restrict__ src, const float *__restrict__ tgt, cons
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)CT_TMEM_COLS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
                      : "memory");
     }
 }
@@ -407,9 +409,19 @@ int cpg_tc_launch(const float *src_dfe, const float *tgt_dfe, const float *cand,
     DVCP_CHECK_LAUNCH();
     const int R = ct_rows(G);
     const int smem = 4 * R * 16 + (2 * CT_B_FLOATS_Q + 27 * 16 * 4 + 112) * (int)sizeof(float);
-    DVCP_CUDA(cudaFuncSetAttribute(cpg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int64_t grid = M < DVCP_NUM_SMS ? M : DVCP_NUM_SMS;
-    cpg_tc_kernel<<<(unsigned)grid, CT_THREADS, smem, st>>>(src_dfe, tgt_dfe, cand, M, G, R, image, p, vcp, logits);
+    const int Gp = G + 2, m_lo = Gp * Gp + Gp + 1, ntiles = ((G - 1) * m_lo + 1 + 127) / 128;
+    unsigned tmem_cols = 32;
+    while ((int)tmem_cols < ntiles * 32) tmem_cols *= 2;   // allocation: a power of two >= 32
+    if (G <= 6) {
+        // small volumes (6^3 is the reference's own grid): 256-thread CTAs, two per SM (2 x smem <= 227 KB, 2 x TMEM <= 512)
+        DVCP_CUDA(cudaFuncSetAttribute(cpg_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int64_t grid = M < 2 * DVCP_NUM_SMS ? M : 2 * DVCP_NUM_SMS;
+        cpg_tc_kernel<256><<<(unsigned)grid, 256, smem, st>>>(src_dfe, tgt_dfe, cand, M, G, R, tmem_cols, image, p, vcp, logits);
+    } else {
+        DVCP_CUDA(cudaFuncSetAttribute(cpg_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int64_t grid = M < DVCP_NUM_SMS ? M : DVCP_NUM_SMS;
+        cpg_tc_kernel<512><<<(unsigned)grid, 512, smem, st>>>(src_dfe, tgt_dfe, cand, M, G, R, tmem_cols, image, p, vcp, logits);
+    }
     DVCP_CHECK_LAUNCH();
     return 0;
 }
