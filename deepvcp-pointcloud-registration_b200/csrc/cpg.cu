@@ -413,6 +413,8 @@ cpg_fused_kernel(const float *__restrict__ src, const float *__restrict__ tgt, i
 namespace dvcp {
 int cpg_tc_launch(const float *src_dfe, const float *tgt_dfe, const float *cand, int64_t M, int G, dvcp_cpg_params_t p,
                   float *vcp, float *logits, float *image, cudaStream_t st);   // cpg_tc.cu
+int cpg_tcz_launch(const float *src_dfe, const float *tgt_dfe, const float *cand, int64_t M, int G, dvcp_cpg_params_t p,
+                   float *vcp, float *logits, float *image, cudaStream_t st);  // cpg_tc.cu
 }
 extern "C" int64_t dvcp_cpg_tc_image_bytes(void);
 
@@ -434,10 +436,12 @@ extern "C" int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int lay
     if (workspace_bytes < dvcp_cpg_workspace_bytes(M, G)) return DVCP_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int C = G * G * G;
-    if (path < DVCP_CPG_AUTO || path > DVCP_CPG_TC) return DVCP_E_ARG;
+    if (path < DVCP_CPG_AUTO || path > DVCP_CPG_TCZ) return DVCP_E_ARG;
     if (path == DVCP_CPG_FUSED && G > CF_MAXG) return DVCP_E_UNSUPPORTED;
-    if (path == DVCP_CPG_TC && (G > CF_MAXG || G < 2 || layout != 0)) return DVCP_E_UNSUPPORTED;
-    if (path == DVCP_CPG_TC || (path == DVCP_CPG_AUTO && layout == 0 && G >= 2 && G <= CF_MAXG))
+    if ((path == DVCP_CPG_TC || path == DVCP_CPG_TCZ) && (G > CF_MAXG || G < 2 || layout != 0)) return DVCP_E_UNSUPPORTED;
+    if (path == DVCP_CPG_TCZ || (path == DVCP_CPG_AUTO && layout == 0 && G >= 2 && G <= CF_MAXG))
+        return cpg_tcz_launch(src_dfe, tgt_dfe, cand, M, G, p, vcp, logits, (float *)workspace, st);
+    if (path == DVCP_CPG_TC)
         return cpg_tc_launch(src_dfe, tgt_dfe, cand, M, G, p, vcp, logits, (float *)workspace, st);
     if (G <= CF_MAXG && path != DVCP_CPG_LAYERED) {
         const int Cp = (C + 3) & ~3;

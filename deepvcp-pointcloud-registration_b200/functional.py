@@ -467,7 +467,7 @@ def dfe_dense(X, dfe):
     return out
 
 
-CPG_AUTO, CPG_FUSED, CPG_LAYERED, CPG_TC = 0, 1, 2, 3
+CPG_AUTO, CPG_FUSED, CPG_LAYERED, CPG_TC, CPG_TCZ = 0, 1, 2, 3, 4
 
 
 def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False, path=CPG_AUTO):
@@ -483,7 +483,7 @@ def cpg(src_dfe, tgt_dfe, layout, cand, G, params, want_logits=False, path=CPG_A
     logits = torch.empty(M, C, dtype=torch.float32, device=dev) if want_logits else None
     check(lib().dvcp_cpg_path(ptr(_f32c(src_dfe)), ptr(_f32c(tgt_dfe)), layout, ptr(_f32c(cand)), M, G, params,
                               ptr(vcp), ptr(logits), ptr(ws), nbytes, path, stream_ptr(dev)), "dvcp_cpg")
-    tc = path == CPG_TC or (path == CPG_AUTO and layout == 0 and 2 <= G <= 11)
+    tc = path in (CPG_TC, CPG_TCZ) or (path == CPG_AUTO and layout == 0 and 2 <= G <= 11)
     _count(2 if tc else (1 if G <= 11 and path != CPG_LAYERED else 5))   # TC: weight image + kernel; fused: 1; layered: 5
     return vcp, logits
 

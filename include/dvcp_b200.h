@@ -298,6 +298,7 @@ DVCP_API int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, co
 #define DVCP_CPG_FUSED   1
 #define DVCP_CPG_LAYERED 2
 #define DVCP_CPG_TC      3   /* conv1 as an implicit GEMM on tcgen05 (3xTF32, TMEM); layout 0, 2 <= G <= 11 */
+#define DVCP_CPG_TCZ     4   /* same, the three z taps of a column as the N dimension (9 operand shifts instead of 27) */
 DVCP_API int dvcp_cpg_path(const float *src_dfe, const float *tgt_dfe, int layout, const float *cand, int64_t M,
              int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
              int64_t workspace_bytes, int path, dvcp_stream_t stream);

@@ -173,14 +173,16 @@ def test_m64_batch_sampled_pairs_vs_oracle(dv):
 
 @pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("G,path", [(11, "auto"), (11, "fused"), (11, "layered"), (11, "tc"), (15, "auto"), (21, "auto"),
-                                    (7, "layered"), (5, "fused"), (5, "tc"), (6, "tc"), (7, "tc"), (2, "tc"), (3, "tc")])
+                                    (7, "layered"), (5, "fused"), (5, "tc"), (6, "tc"), (7, "tc"), (2, "tc"), (3, "tc"),
+                                    (11, "tcz"), (10, "tcz"), (9, "tcz"), (8, "tcz"), (7, "tcz"), (6, "tcz"), (5, "tcz"),
+                                    (4, "tcz"), (3, "tcz"), (2, "tcz")])
 def test_cpg_large_grids_vs_oracle(dv, F, G, path, layout):
     """cpg.forward (cpg.py:27-60) standalone at the benchmark's 11^3 and the sweep's 15^3 / 21^3: every kernel
     family, the logical [32, C] argument (layout 0) and the DFE's own [C, 32] order (layout 1, the permute of
     deepVCP.py:106 applied inside the kernel) against the oracle's conv3d chain."""
-    if path == "tc" and layout == 1:
+    if path in ("tc", "tcz") and layout == 1:
         pytest.skip("the tensor-core kernel reads the logical [32, C] order only (layout 0)")
-    M, C = (5 if path != "tc" else 301), G * G * G     # tc: two rounds of the persistent kernel + a ragged tail
+    M, C = (5 if path not in ("tc", "tcz") else 301), G * G * G     # tc: two rounds of the persistent kernel + a ragged tail
     g = torch.Generator().manual_seed(100 + G)
     net = dv.cpg()
     sd = {"cpg." + k: v.clone() for k, v in net.state_dict().items()}
@@ -189,7 +191,8 @@ def test_cpg_large_grids_vs_oracle(dv, F, G, path, layout):
     tgt_cf = torch.randn(1, M, C, 32, generator=g)            # [candidate, feature] as the DFE produces it
     cand = (torch.rand(1, M, C, 3, generator=g) * 2 - 1) * 20
     vcp_ref, logits_ref = stages.cpg(sd, src, tgt_cf, cand, G, reshape_quirk=True)
-    pid = {"auto": F.CPG_AUTO, "fused": F.CPG_FUSED, "layered": F.CPG_LAYERED, "tc": F.CPG_TC}[path]
+    pid = {"auto": F.CPG_AUTO, "fused": F.CPG_FUSED, "layered": F.CPG_LAYERED, "tc": F.CPG_TC,
+           "tcz": F.CPG_TCZ}[path]
     if layout == 1:
         flat = tgt_cf.reshape(M, C * 32)
     else:   # the logical row-major order of the [32, C] view the reference hands to cpg

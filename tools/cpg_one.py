@@ -11,7 +11,7 @@ net = dv.cpg().to(dev)
 src = torch.randn(M, 32, generator=g).to(dev)
 tgt = torch.randn(M, 32 * C, generator=g).to(dev)
 cand = torch.randn(M, C, 3, generator=g).to(dev)
-path = {"tc": F_.CPG_TC, "fused": F_.CPG_FUSED}[sys.argv[1] if len(sys.argv) > 1 else "tc"]
+path = {"tc": F_.CPG_TC, "tcz": F_.CPG_TCZ, "fused": F_.CPG_FUSED}[sys.argv[1] if len(sys.argv) > 1 else "tc"]
 for _ in range(3):
     F_.cpg(src, tgt, 0, cand, G, net.params(), path=path)
 torch.cuda.synchronize()
