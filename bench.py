@@ -322,7 +322,11 @@ def run_ours(args):
     all_poses = dv.sharding.all_gather_poses(poses, B * world)
     assert all_poses.shape == (B * world, 12)
     tm = torch.tensor([ms_total, e2e_s * 1e3, sustained[1] if sustained else 0.0], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        every = [torch.zeros_like(tm) for _ in range(world)]
+        dist.all_gather(every, tm)
+        per_rank = [round(float(x[0]) / args.steps, 4) for x in every]   # every rank's own ms per step (value uses the max)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, ms_sus = float(tm[0]), float(tm[1]), float(tm[2])
 
@@ -405,6 +409,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_pose.numel() * 8},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if per_rank is not None:
+            out["per_rank_ms_per_step"] = per_rank
         if sustained:
             out["sustained"] = {"value": round(pairs * sustained[0] / (ms_sus * 1e-3), 3), "unit": "pairs/s",
                                 "steps": sustained[0], "seconds": round(ms_sus * 1e-3, 3)}
