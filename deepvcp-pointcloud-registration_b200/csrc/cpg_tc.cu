@@ -20,6 +20,11 @@
 // conv2 / conv3 / softmax / weighted sum follow in the same CTA on the CUDA cores (they are 12 % of the
 // arithmetic) with the volume in shared memory, as in cpg_fused_kernel (cpg.cu).
 //
+// Two kernels share this file: cpg_tc_kernel (the form above: one tap per MMA pair, DVCP_CPG_TC) and
+// cpg_tcz_kernel (further down: the three z taps of a column as the N dimension, a third of the operand
+// fetches; DVCP_CPG_TCZ, what dvcp_cpg picks). tools/cpg_timing.py prints the per-phase cycle counts of both
+// (library built with -DDVCP_CPG_TIMING).
+//
 // The target embedding is read as flat[c' * 32 + f'] (the LOGICAL [32, C] order, `layout` 0 of dvcp_cpg):
 // 32 contiguous floats per voxel. DeepVCP.match has the embedding kernel write that order directly.
 #include "common.cuh"

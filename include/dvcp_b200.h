@@ -292,7 +292,7 @@ DVCP_API int dvcp_cpg(const float *src_dfe, const float *tgt_dfe, int layout, co
              int G, dvcp_cpg_params_t p, float *vcp, float *logits, void *workspace,
              int64_t workspace_bytes, dvcp_stream_t stream);
 /* Same, with the kernel family chosen by the caller (parity tests compare the families with each other
- * and with the oracle at every grid size): AUTO = what dvcp_cpg picks (TC for layout 0 up to 11^3); FUSED = whole chain in one kernel
+ * and with the oracle at every grid size): AUTO = what dvcp_cpg picks (TCZ for layout 0 up to 11^3); FUSED = whole chain in one kernel
  * with the volume in shared memory (G <= 11); LAYERED = one kernel per layer through the workspace. */
 #define DVCP_CPG_AUTO    0
 #define DVCP_CPG_FUSED   1
