@@ -399,9 +399,11 @@ def run_ours(args):
                        "each step" % (n_rot, n_rot * (d_src.numel() + d_tgt.numel()) * 4 / 1e6),
                        "pipeline_depth": args.depth,
                        "cuda_graphs": bool(args.graphs),
-                       "pipeline": "StreamedRegistration: batches alternate between %d streams, so the sampling of "
-                                   "batch i+1 overlaps the dense stages of batch i; every batch runs the complete "
-                                   "forward + pose solve" % args.depth,
+                       "pipeline": "%s, depth %d: the feature halves (index, sampling, SA layer) of %d batch(es) run on "
+                                   "their own stream(s) beside the match half (key-points ... CPG, pose) of an earlier "
+                                   "batch; sampling mode %d (0 = clusters of 8 CTAs per cloud, 2 = one CTA per cloud); "
+                                   "every batch runs the complete forward + pose solve"
+                                   % (type(pipe).__name__, args.depth, len(pipe.fe_streams), pipe.sampling),
                        "parallelism": "pairs sharded by rank, all-gather of poses only"},
             "latency_ms_per_step_unpipelined": round(latency_ms, 4),
             "roofline": roofline, "kernels": kernels,
@@ -554,7 +556,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, help="batches in flight (1 = one at a time)")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight (1 = one at a time; >= 3: one sampling CTA per cloud, depth - 1 feature halves in flight)")
     ap.add_argument("--no-graphs", dest="graphs", action="store_false",
                     help="eager kernel launches instead of the captured CUDA graphs")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the extra sustained timed pass (0 = skip)")

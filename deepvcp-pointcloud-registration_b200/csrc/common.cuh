@@ -6,6 +6,14 @@
 #include "../../include/dvcp_b200.h"
 
 #define DVCP_NUM_SMS 148
+// The tensor-core kernels that fill the GPU (embedding, CPG) are launched as several CTAs per SM slot instead of one
+// persistent CTA per SM: in a stream of batches some SMs are held for milliseconds by the sampling CTAs of the next
+// batches (one CTA per cloud, the whole register file), and a CTA that waits for such an SM must not hold a fixed
+// share of the work. The hardware hands the queued CTAs to whichever SMs are free (measured at K8, embedding with
+// 2 / 3 / 4 / 6 / 8 / 16 CTAs per slot: 3.50 / 3.40 / 3.35 / 3.30 / 3.28 / 3.33 ms per pipelined step; alone the
+// kernel pays its per-CTA set-up: 0.79 -> 0.83 ms at 8).
+#define DVCP_DFE_WAVES 8
+#define DVCP_CPG_WAVES 4
 
 #define DVCP_CHECK_LAUNCH()                              \
     do {                                                 \

@@ -593,7 +593,7 @@ extern "C" int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, cons
         return DVCP_E_ARG;
     if (index.cap != dvcp_index_capacity(N) || index.cap == 0) return DVCP_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!fps_sequential_mode() && fps_use_cluster(B, N))
+    if (!fps_sequential_mode() && concurrent != 2 && fps_use_cluster(B, N))
         return dvcp_fps_cluster_launch(xyz, index, B, N, npoint, start, out64, out32, concurrent, st);
     // one CTA per cloud: that kernel sorts the cloud itself; it must not rewrite an index others are reading
     dvcp_cloud_index_t none = {nullptr, nullptr, 0};

@@ -92,7 +92,7 @@ def fps_indexed(xyz_cloud: Cloud, device, B, N, npoint, start, index, want64=Fal
     o64 = torch.empty(B, npoint, dtype=torch.int64, device=device) if want64 else None
     o32 = torch.empty(B, npoint, dtype=torch.int32, device=device) if want32 else None
     check(lib().dvcp_fps_indexed(xyz_cloud, B, N, npoint, ptr(start), ptr(o64), ptr(o32), index.c(),
-                                 1 if concurrent else 0, stream_ptr(device)), "dvcp_fps_indexed")
+                                 int(concurrent), stream_ptr(device)), "dvcp_fps_indexed")
     _count(1)
     return o64, o32
 

@@ -10,7 +10,20 @@ first half of batch k+1 therefore runs on its own stream beside the second half 
 
 FE(k) is released when M(k - depth) has finished, i.e. (depth 2) exactly when M(k-1)
 starts, so the sampling coincides with the KNN of the previous batch and is over before
-that batch's persistent embedding / CPG kernels want the whole GPU. Each batch still
+that batch's embedding / CPG kernels want the whole GPU.
+
+depth >= 3 (what bench.py uses) trades latency for throughput: the sampling runs as ONE CTA per
+cloud (dvcp_fps_indexed, concurrent = 2: 4.7 ms instead of 2.3 ms for the 16 clouds of a K8 batch, but
+16 SMs instead of 122, a third of the SM time), and the feature halves of depth - 1 batches are in
+flight at once on their own streams beside the match half of an earlier batch:
+
+    feature stream 0   FE(0)......  FE(2)......  FE(4)......
+    feature stream 1         FE(1)......  FE(3)......
+    match stream                   M(0)  M(1)  M(2)  M(3) ...
+
+The sampling CTAs hold their SMs for milliseconds, which is why the embedding and CPG kernels are
+launched as several CTAs per SM slot (common.cuh, DVCP_DFE_WAVES): whichever SMs are free take the
+work. K8 on one B200: 3.69 -> 3.28 ms per batch. Each batch still
 runs the complete path (DeepVCP.forward + svd_optimization, deepVCP.py:24-110,
 deepVCP_loss.py:57-90) and results come back in submission order; nothing is shared
 between batches except the read-only weights. The reference has no counterpart (batch
@@ -21,21 +34,37 @@ from .deepVCP_loss import pose_from_forward
 from .sharding import pack_poses
 
 
+def _pipeline_shape(depth, fe_streams, sampling):
+    """Defaults of the two pipeline classes: depth <= 2: one feature stream, cluster sampling (mode 0);
+    depth >= 3: depth - 1 feature streams, one sampling CTA per cloud (mode 2)."""
+    if depth < 1:
+        raise ValueError("depth >= 1")
+    if fe_streams is None:
+        fe_streams = max(1, depth - 1)
+    if sampling is None:
+        sampling = 2 if depth >= 3 else 0
+    if sampling not in (0, 1, 2) or fe_streams < 1:
+        raise ValueError("sampling in (0, 1, 2), fe_streams >= 1")
+    return fe_streams, sampling
+
+
 class StreamedRegistration:
-    def __init__(self, model, depth=2):
+    def __init__(self, model, depth=2, fe_streams=None, sampling=None):
+        """depth: batches in flight (1 = one at a time). fe_streams: feature halves in flight at once (default
+        depth - 1). sampling: the `concurrent` mode of dvcp_fps_indexed (default 0 = clusters up to depth 2,
+        2 = one CTA per cloud from depth 3 on)."""
         dev = model.cpg.conv1.weight.device
         if dev.type != "cuda":
             raise RuntimeError("StreamedRegistration needs the model on a CUDA device")
-        if depth < 1:
-            raise ValueError("depth >= 1")
+        n_fe, self.sampling = _pipeline_shape(depth, fe_streams, sampling)
         self.model, self.dev, self.depth = model, dev, depth
         self.fe_stream = torch.cuda.Stream(device=dev)
+        self.fe_streams = [self.fe_stream] + [torch.cuda.Stream(device=dev) for _ in range(n_fe - 1)]
         self.match_stream = torch.cuda.Stream(device=dev)
-        self.streams = [self.fe_stream, self.match_stream]
+        self.streams = self.fe_streams + [self.match_stream]
         self.done = []         # completion event of every batch submitted since the last collect()
         self.pending = []      # (done event, poses) in submission order
         self.t_init = torch.zeros(1, 3)
-        self.small_sampling_ctas = False   # sampling with half-size CTAs (measured: no gain on B200 at K8)
         self.timing = False    # development: completion events carry timestamps
         self.trace = []
 
@@ -54,12 +83,12 @@ class StreamedRegistration:
             # strictly one batch at a time: both halves on the match stream
             fs = self.match_stream
         else:
-            fs = self.fe_stream
+            fs = self.fe_streams[k % len(self.fe_streams)]
         fs.wait_stream(cur)                                   # inputs produced on the caller's stream
         with torch.cuda.stream(fs):
             if self.depth > 1 and k >= self.depth:
                 fs.wait_event(self.done[k - self.depth])      # run ahead by at most `depth` batches
-            fe = self.model.extract_features(to(src), to(tgt), starts, concurrent=self.small_sampling_ctas)
+            fe = self.model.extract_features(to(src), to(tgt), starts, concurrent=self.sampling)
             Ri, Rt, tt = to(R_init), to(R_true), to(t_true)
             ev_fe = torch.cuda.Event(enable_timing=self.timing)
             ev_fe.record(fs)
@@ -107,20 +136,22 @@ class GraphedRegistration:
     k's match half exactly as in StreamedRegistration; results are identical to it (same kernels, same order).
     The reference has no counterpart (train.py:105 calls the eager model once per pair)."""
 
-    def __init__(self, model, B, C_in, N, depth=2):
+    def __init__(self, model, B, C_in, N, depth=2, fe_streams=None, sampling=None):
+        """depth / fe_streams / sampling: as for StreamedRegistration."""
         dev = model.cpg.conv1.weight.device
         if dev.type != "cuda":
             raise RuntimeError("GraphedRegistration needs the model on a CUDA device")
         from . import functional as F_
         self.model, self.dev, self.depth = model, dev, max(1, depth)
+        self.n_fe, self.sampling = _pipeline_shape(self.depth, fe_streams, sampling)
         self.B, self.C_in, self.N = B, C_in, N
         import os
-        self.small_sampling_ctas = os.environ.get("DVCP_FPS_SMALL") == "1"   # development: 8-warp sampling CTAs
         self.ahead_index = os.environ.get("DVCP_AHEAD_INDEX", "1") == "1"    # spatial index built one batch ahead
         self.fe_stream = torch.cuda.Stream(device=dev)
+        self.fe_streams = [self.fe_stream] + [torch.cuda.Stream(device=dev) for _ in range(self.n_fe - 1)]
         self.match_stream = torch.cuda.Stream(device=dev) if self.depth > 1 else self.fe_stream
         self.copy_stream = torch.cuda.Stream(device=dev)   # input copies run ahead of the (in-order) feature stream
-        self.streams = [self.fe_stream, self.match_stream]
+        self.streams = self.fe_streams + [self.match_stream]
         self.slots = []
         self.pending = []
         self.launches_per_batch = 0
@@ -146,7 +177,7 @@ class GraphedRegistration:
 
     def _run_fe(self, s, prepared=None):
         return self.model.extract_features(s["src"], s["tgt"], (s["st"][0], s["st"][1], s["st"][2]),
-                                           concurrent=self.small_sampling_ctas, prepared=prepared)
+                                           concurrent=self.sampling, prepared=prepared)
 
     def _run_match(self, s, fe):
         kp, vcp = self.model.match(fe, s["Ri"])
@@ -186,7 +217,7 @@ class GraphedRegistration:
         FPS start index tensors [B]). Poses are copied into host_out (pinned [B,12] float64) if given."""
         k = len(self.pending)
         s = self.slots[k % len(self.slots)]
-        fs, ms, cs = self.fe_stream, self.match_stream, self.copy_stream
+        fs, ms, cs = self.fe_streams[k % len(self.fe_streams)], self.match_stream, self.copy_stream
         cur = torch.cuda.current_stream(self.dev)
         cs.wait_stream(cur)
         # The inputs go into the slot's static buffers on their OWN stream: queued behind the previous batch's

@@ -101,8 +101,11 @@ DVCP_API int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, con
 /* Same as dvcp_fps for float32 clouds whose spatial index is ALREADY built (dvcp_build_index on
  * the same stream or ordered before this call): the index is consumed, not rewritten, so other
  * kernels may read it concurrently (DeepVCP.forward runs the SA layer beside the sampling).
- * concurrent != 0: the sampling will share the GPU with other work (a stream of batches): smaller
- * CTAs that leave most of every SM free, at the price of a longer kernel. Same results. */
+ * concurrent: how the sampling shares the GPU with other work (a stream of batches); same results in every mode.
+ *   0  few large clouds are spread over clusters of 8 CTAs each (shortest kernel: 2.3 ms for 16 clouds of 16384);
+ *   1  the same with half-size CTAs;
+ *   2  ONE CTA per cloud (4.7 ms for any number of clouds up to the SM count, but a third of the SM time of mode 0):
+ *      for throughput, with the feature halves of several batches in flight (GraphedRegistration, depth >= 3). */
 DVCP_API int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
                      int32_t *out32, dvcp_cloud_index_t index, int concurrent, dvcp_stream_t stream);
 

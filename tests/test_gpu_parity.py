@@ -715,14 +715,16 @@ def test_overlapped_sa_equals_sequential_path(dv, F, synthetic):
     assert torch.equal(feat2[:1], L["src_fe_feat"]) and torch.equal(feat2[1:], L["tgt_fe_feat"])
 
 
-def test_streamed_registration_equals_one_batch_at_a_time(dv, synthetic):
-    """Throughput mode (batches alternating between streams) returns, in order, exactly the poses
-    of the same batches registered one after the other."""
+@pytest.mark.parametrize("depth", [2, 3, 4])
+def test_streamed_registration_equals_one_batch_at_a_time(dv, synthetic, depth):
+    """Throughput mode (batches alternating between streams; from depth 3 on several feature halves in flight
+    and one sampling CTA per cloud) returns, in order, exactly the poses of the same batches registered one
+    after the other."""
     N = 4096
     torch.manual_seed(9)
     model = dv.DeepVCP(use_normal=False, npoint=N, r=1.2, s=0.4).to(DEV).eval()
     batches = []
-    for i in range(5):
+    for i in range(7):
         src, tgt, R, t = synthetic.make_batch("kitti", [2 * i, 2 * i + 1], N)
         starts = (torch.tensor([i, i + 1]), torch.tensor([i + 2, i + 3]), torch.tensor([i + 4, i + 5]))
         batches.append((src, tgt, R, t.view(2, 3, 1), starts))
@@ -731,7 +733,8 @@ def test_streamed_registration_equals_one_batch_at_a_time(dv, synthetic):
         kp, vcp = model(src.to(DEV), tgt.to(DEV), R.to(DEV), torch.zeros(1, 3), starts=starts)
         R2, t2 = dv.pose_from_forward(kp, vcp, R.to(DEV), t.to(DEV))
         ref.append(dv.sharding.pack_poses(R2, t2).cpu())
-    pipe = dv.StreamedRegistration(model, depth=2)
+    pipe = dv.StreamedRegistration(model, depth=depth)
+    assert pipe.sampling == (2 if depth >= 3 else 0) and len(pipe.fe_streams) == max(1, depth - 1)
     hosts = [torch.empty(2, 12, dtype=torch.float64).pin_memory() for _ in batches]
     for (src, tgt, R, t, starts), h in zip(batches, hosts):
         pipe.submit(src, tgt, R, R, t, starts=starts, host_out=h)
@@ -747,7 +750,7 @@ def test_graphed_registration_equals_streamed(dv, synthetic):
     torch.manual_seed(5)
     model = dv.DeepVCP(use_normal=False, npoint=N, r=1.2000000000000002, s=0.4).to(DEV).eval()
     batches = []
-    for k in range(5):
+    for k in range(9):
         src, tgt, R, t = synthetic.make_batch("kitti", [2 * k, 2 * k + 1], N)
         starts = (torch.tensor([k, k + 1]), torch.tensor([k + 2, k + 3]), torch.tensor([k + 4, k + 5]))
         batches.append((src, tgt, R, t.view(B, 3, 1), starts))
@@ -755,7 +758,7 @@ def test_graphed_registration_equals_streamed(dv, synthetic):
     for src, tgt, R, t, starts in batches:
         eager.submit(src.to(DEV), tgt.to(DEV), R.to(DEV), R.to(DEV), t.to(DEV), starts=starts)
     ref = [p.cpu() for p in eager.collect()]
-    for depth in (2, 1):
+    for depth in (3, 4, 2, 1):   # 3, 4: one sampling CTA per cloud, 2 / 3 feature halves in flight
         gr = dv.GraphedRegistration(model, B, 3, N, depth=depth)
         assert gr.launches_per_batch >= 10
         host = [torch.empty(B, 12, dtype=torch.float64).pin_memory() for _ in batches]
