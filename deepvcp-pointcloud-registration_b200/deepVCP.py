@@ -234,8 +234,14 @@ class DeepVCP(nn.Module):
         return self.match_finish(st, keep_stages=keep_stages)
 
     def match_search(self, fe, R_init, keep_stages=False, topk_override=None, t_init=None):
-        """match() up to and including the KNN (many small CTAs: they share the GPU with the sampling of the next
-        batch); match_finish() continues with the persistent tensor-core kernels."""
+        """match() up to and including the KNN; match_finish() continues with the tensor-core kernels."""
+        return self.match_knn(self.match_select(fe, R_init, keep_stages=keep_stages, topk_override=topk_override,
+                                                t_init=t_init), keep_stages=keep_stages)
+
+    def match_select(self, fe, R_init, keep_stages=False, topk_override=None, t_init=None):
+        """The small kernels at the head of match(): key-point selection, key-point stage, candidate lattice
+        (deepVCP.py:33-67,86-91,101). A handful of short launches that leave the GPU idle: the depth >= 3 pipeline
+        runs them at the end of the FEATURE half, beside the dense kernels of an earlier batch."""
         src, tgt, index, fps2, feat2, starts = fe["src"], fe["tgt"], fe["index"], fe["fps2"], fe["feat2"], fe["starts"]
         B, N, dev = fe["B"], fe["N"], fe["dev"]
         ilo = fe.get("index_lo", B)   # target clouds are batch items ilo..ilo+B-1 of the index
@@ -271,6 +277,19 @@ class DeepVCP(nn.Module):
             cand = F_.candidates(centres, self.r, self.s, G)                 # [B,K,C,3]
             mark("keypoint_candidates")
             C = G * G * G
+            # point-major float4 copy of the target xyz for the tensor-core embedding: one 16-byte load per gathered neighbour
+            tgt4 = F_.pack_xyz4(cloud_cm(tgt), dev, B, N) if self.dfe_tensor_cores else None
+        return dict(fe=fe, tfeat=tfeat, sfps=sfps, tfps=tfps, sfeat=sfeat, scores=scores, topk=topk, keypts=keypts,
+                    picked=picked, cat=cat, src_dfe=src_dfe, centres=centres, cand=cand, G=G, C=C, dfe=dfe, tgt4=tgt4)
+
+    def match_knn(self, st, keep_stages=False):
+        """The K nearest target points of every candidate (get_cat_feat_tgt.py:45,52) on the state of match_select()."""
+        fe = st["fe"]
+        tgt, index, B, N, dev = fe["tgt"], fe["index"], fe["B"], fe["N"], fe["dev"]
+        ilo = fe.get("index_lo", B)   # target clouds are batch items ilo..ilo+B-1 of the index
+        K, ns, cand, C, G = self.K_topk, self.nsample, st["cand"], st["C"], st["G"]
+        mark = lambda name: self._mark(name, dev)
+        with torch.no_grad():
             if index is not None and self.knn_pools and N >= self.knn_pools_min_n:
                 # one CTA per key-point: the target points around its candidate lattice are pooled in shared memory
                 kd, ki64, ki32 = F_.knn_groups(index, ilo, dev, B, N, cand.view(B, K * C, 3), ns, group=C, zline=G,
@@ -287,9 +306,9 @@ class DeepVCP(nn.Module):
                 kd, ki64, ki32 = F_.knn(cloud_cm(tgt), dev, B, N, cand.view(B, K * C, 3), ns, want64=keep_stages,
                                         want32=True)
             mark("knn")
-        return dict(fe=fe, tfeat=tfeat, sfps=sfps, tfps=tfps, sfeat=sfeat, scores=scores, topk=topk, keypts=keypts,
-                    picked=picked, cat=cat, src_dfe=src_dfe, centres=centres, cand=cand, kd=kd, ki64=ki64, ki32=ki32,
-                    G=G, C=C, dfe=dfe)
+        st = dict(st)
+        st.update(kd=kd, ki64=ki64, ki32=ki32)
+        return st
 
     def match_finish(self, st, keep_stages=False):
         """Embedding, CPG (deepVCP.py:93-110) on the state match_search() returned."""
@@ -305,8 +324,7 @@ class DeepVCP(nn.Module):
             fm = False   # tgt_dfe held feature-major per key-point ([B,K,32,C])?
             if self.dfe_tensor_cores:
                 b_hi, b_lo = self.DFE.tc_operand()
-                # point-major float4 copy of the target xyz: one 16-byte load per gathered neighbour
-                tgt4 = F_.pack_xyz4(cloud_cm(tgt), dev, B, N)
+                tgt4 = st["tgt4"]
                 # Reference mode: cpg.py:34 re-reads the LOGICAL [32, C] order of the permuted tensor (Q4); the
                 # embedding kernel writes exactly that order, so CPG finds a voxel's 32 values contiguous
                 # (layout 0) and its tensor-core kernel applies. Intended mode wants [C, 32] as it is: also layout 0.

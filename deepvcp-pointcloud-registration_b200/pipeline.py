@@ -147,6 +147,7 @@ class GraphedRegistration:
         self.B, self.C_in, self.N = B, C_in, N
         import os
         self.ahead_index = os.environ.get("DVCP_AHEAD_INDEX", "1") == "1"    # spatial index built one batch ahead
+        self.select_early = self.depth >= 3 and os.environ.get("DVCP_SELECT_EARLY", "1") == "1"
         self.fe_stream = torch.cuda.Stream(device=dev)
         self.fe_streams = [self.fe_stream] + [torch.cuda.Stream(device=dev) for _ in range(self.n_fe - 1)]
         self.match_stream = torch.cuda.Stream(device=dev) if self.depth > 1 else self.fe_stream
@@ -176,11 +177,17 @@ class GraphedRegistration:
         return self.model.prepare_index(s["src"], s["tgt"])
 
     def _run_fe(self, s, prepared=None):
-        return self.model.extract_features(s["src"], s["tgt"], (s["st"][0], s["st"][1], s["st"][2]),
-                                           concurrent=self.sampling, prepared=prepared)
+        fe = self.model.extract_features(s["src"], s["tgt"], (s["st"][0], s["st"][1], s["st"][2]),
+                                         concurrent=self.sampling, prepared=prepared)
+        # depth >= 3: the short launches at the head of the match half (key-point selection, key-point stage, candidate
+        # lattice) leave the GPU almost idle; at the end of the feature half they run beside an earlier batch's dense kernels
+        return self.model.match_select(fe, s["Ri"]) if self.select_early else fe
 
     def _run_match(self, s, fe):
-        kp, vcp = self.model.match(fe, s["Ri"])
+        if self.select_early:
+            kp, vcp = self.model.match_finish(self.model.match_knn(fe))
+        else:
+            kp, vcp = self.model.match(fe, s["Ri"])
         R2, t2 = pose_from_forward(kp, vcp, s["Rt"], s["tt"], quirks=self.model.quirks)
         return pack_poses(R2, t2)
 
