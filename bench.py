@@ -275,6 +275,21 @@ def run_ours(args):
             stage_ms[name] = stage_ms.get(name, 0.0) + e0.elapsed_time(e1)
     model.profile = False
     latency_ms = sum(lat_ms) / len(lat_ms)
+    # the sampling kernel the depth >= 3 pipeline uses (one CTA per cloud), timed alone on the same clouds
+    fps_mode2_ms = None
+    prep = model.prepare_index(d_src, d_tgt)
+    if prep is not None:
+        lib_mod = importlib.import_module(PKG + "._lib")
+        st2 = torch.cat([starts[0], starts[2]])
+        run2 = lambda: F_.fps_indexed(lib_mod.cloud_cm(prep["both"]), dev, 2 * B, N, N, st2, prep["index"], concurrent=2)
+        run2()
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run2()
+        b.record()
+        torch.cuda.synchronize(dev)
+        fps_mode2_ms = a.elapsed_time(b)
 
     # ---- timed region: K steps through the streamed API (batch i+1's sampling overlaps batch i's dense
     #      stages; --depth 1 = strictly one batch at a time), device time, clocks sampled ----
@@ -351,7 +366,10 @@ def run_ours(args):
             kernels["fps"].update({"picks_per_s": round(picks / (kernels["fps"]["ms"] * 1e-3), 1),
                                    "ns_per_pick_per_cloud": round(kernels["fps"]["ms"] * 1e6 / N, 2),
                                    "clouds": 2 * B, "picks_per_cloud": N,
-                                   "note": "stage = index build + sampling (SA layer beside it on another stream)"})
+                                   "note": "stage = index build + sampling by clusters of 8 CTAs per cloud, the latency "
+                                           "form (SA layer beside it on another stream); the depth >= 3 pipeline "
+                                           "samples with ONE CTA per cloud: ms_one_cta_per_cloud, on 2B SMs",
+                                   "ms_one_cta_per_cloud": None if fps_mode2_ms is None else round(fps_mode2_ms, 4)})
         # The roofline object is for the KNN kernel: it is the kernel BASELINE.json's metric names and the
         # longest HBM-type kernel. The longest stage overall is the sampling ("fps", latency-bound: a chain of
         # dependent selections), which has no meaningful bandwidth roofline.
