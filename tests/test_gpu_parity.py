@@ -111,6 +111,32 @@ def test_fps_duplicates_and_padding_in_indexed_kernel(dv):
         assert torch.equal(out.cpu(), ref)
 
 
+def test_fps_one_cta_per_cloud_at_full_size(dv, F, synthetic):
+    """dvcp_fps_indexed, concurrent = 2: the one-CTA-per-cloud kernel the depth >= 3 pipeline samples with. At 16384
+    points it runs the WIDE rounds (two exposed keys per bucket, 64 candidates per step): random, KITTI-shaped,
+    dense-lattice (heavy ties), duplicated and padded clouds, npoint < N -- against the oracle and the cluster kernel."""
+    lib = importlib.import_module(PKG + "._lib")
+    g = torch.Generator().manual_seed(4)
+    kitti, _, _, _ = synthetic.make_batch("kitti", [3], 16384)
+    base = torch.rand(1, 9000, 3, generator=g) * 10
+    clouds = [
+        (torch.rand(1, 16384, 3, generator=g) * 4 - 2, 16384, 5000),
+        (kitti[:, :3].permute(0, 2, 1).contiguous(), 16384, 77),
+        (lattice_cloud(16384, 11, extent=2.0), 16384, 8192),                       # thousands of points per distance value
+        (torch.cat([base, base[:, :5000]], dim=1), 14000, 13999),                  # 14000 points (padded index), 9000 distinct
+        (torch.rand(1, 16384, 3, generator=g) * 30, 700, 0),                       # npoint < N
+    ]
+    for xyz, npoint, st in clouds:
+        n = xyz.shape[1]
+        start = torch.tensor([st])
+        ref = stages.farthest_point_sample(xyz, npoint, start)
+        cm = xyz.permute(0, 2, 1).contiguous().to(DEV)                             # [1, 3, n] channel-major
+        index = F.build_index(lib.cloud_cm(cm), cm.device, 1, n)
+        for mode in (2, 0):
+            _, out = F.fps_indexed(lib.cloud_cm(cm), cm.device, 1, n, npoint, start, index, concurrent=mode)
+            assert torch.equal(out.cpu().long(), ref), "mode %d, n %d, npoint %d" % (mode, n, npoint)
+
+
 def test_fps_many_clouds_one_cta_each(dv):
     """More clouds than clusters fit: the library falls back to one CTA per cloud (batched rounds)."""
     g = torch.Generator().manual_seed(77)
