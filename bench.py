@@ -164,11 +164,12 @@ def extra_config(torch, dv, dev, kind, B, N, G, use_normal, steps, depth, graphs
     d_src, d_tgt, d_R, d_t = src.to(dev), tgt.to(dev), R.to(dev), t.view(B, 3, 1).to(dev)
     n_rot = max(2, int(160e6 // (d_src.numel() * 8)) + 1)
     rot = [(d_src.clone(), d_tgt.clone()) for _ in range(min(n_rot, 64))]
+    depth = depth or dv.pipeline.auto_depth(N)
     pipe = (dv.GraphedRegistration(model, B, src.shape[1], N, depth=depth) if graphs
             else dv.StreamedRegistration(model, depth=depth))
     time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, 3 * depth + 2)      # warm-up: pipeline + allocator pools
     ms, _ = time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, steps)
-    return {"pairs_per_gpu": B, "n_points": N, "grid": "%d^3" % G, "steps": steps,
+    return {"pairs_per_gpu": B, "n_points": N, "grid": "%d^3" % G, "steps": steps, "pipeline_depth": depth,
             "ms_per_step": round(ms / steps, 4), "pairs_per_s": round(B * steps / (ms * 1e-3), 1)}
 
 
@@ -294,6 +295,8 @@ def run_ours(args):
     # ---- timed region: K steps through the streamed API (batch i+1's sampling overlaps batch i's dense
     #      stages; --depth 1 = strictly one batch at a time), device time, clocks sampled ----
     # both halves of the step captured once into CUDA graphs and replayed (--no-graphs: eager launches)
+    depth_arg = args.depth   # 0 = automatic per workload
+    args.depth = args.depth or dv.pipeline.auto_depth(N)
     pipe = (dv.GraphedRegistration(model, B, 3, N, depth=args.depth) if args.graphs
             else dv.StreamedRegistration(model, depth=args.depth))
     # Between timed iterations nothing may stay L2-resident: every step reads its clouds from a different
@@ -437,8 +440,8 @@ def run_ours(args):
         if world == 1 and not args.no_extra:
             # the other BASELINE.json configurations in the same run (configs[1] and one rank's share of configs[3])
             out["extra_configs"] = {
-                "M64": extra_config(torch, dv, dev, "modelnet", 64, 1024, 5, True, 20, args.depth, args.graphs),
-                "K256_per_gpu_32": extra_config(torch, dv, dev, "kitti", 32, 16384, 11, False, 5, args.depth, args.graphs),
+                "M64": extra_config(torch, dv, dev, "modelnet", 64, 1024, 5, True, 20, depth_arg, args.graphs),
+                "K256_per_gpu_32": extra_config(torch, dv, dev, "kitti", 32, 16384, 11, False, 5, depth_arg, args.graphs),
             }
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
@@ -574,7 +577,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, help="batches in flight (1 = one at a time; >= 3: one sampling CTA per cloud, depth - 1 feature halves in flight)")
+    ap.add_argument("--depth", type=int, default=0, help="batches in flight (0 = pipeline.auto_depth(N): 3 for large clouds, 2 for small ones; 1 = one at a time; >= 3: one sampling CTA per cloud, depth - 1 feature halves in flight)")
     ap.add_argument("--no-graphs", dest="graphs", action="store_false",
                     help="eager kernel launches instead of the captured CUDA graphs")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the extra sustained timed pass (0 = skip)")

@@ -924,7 +924,7 @@ int cpg_tcz_launch(const float *src_dfe, const float *tgt_dfe, const float *cand
     while ((int)tmem_cols < TG * 96) tmem_cols *= 2;   // allocation: a power of two >= 32
     if (small) {
         DVCP_CUDA(cudaFuncSetAttribute(cpg_tcz_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int64_t grid = M < 2 * DVCP_NUM_SMS * DVCP_CPG_WAVES ? M : 2 * DVCP_NUM_SMS * DVCP_CPG_WAVES;
+        int64_t grid = M < 2 * DVCP_NUM_SMS ? M : 2 * DVCP_NUM_SMS;   // small grids go with small clouds: persistent
         cpg_tcz_kernel<256><<<(unsigned)grid, 256, smem, st>>>(src_dfe, tgt_dfe, cand, M, G, Rg, TG, tmem_cols, image, p, vcp, logits);
     } else {
         DVCP_CUDA(cudaFuncSetAttribute(cpg_tcz_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

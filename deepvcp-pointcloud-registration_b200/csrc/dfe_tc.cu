@@ -558,7 +558,9 @@ extern "C" int dvcp_dfe_tgt_tc(const float *cand, dvcp_cloud_t tgt_xyz, const fl
     if (((uintptr_t)knn_idx | (uintptr_t)knn_dist) & 15) return DVCP_E_UNSUPPORTED;   // bulk copies: 16-byte aligned sources
     DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     DVCP_CUDA(cudaFuncSetAttribute(dfe_tgt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    int64_t grid = (int64_t)DVCP_NUM_SMS * DVCP_DFE_WAVES;   // CTAs of >= one run of tiles, several per SM slot (common.cuh)
+    // several CTAs per SM slot (common.cuh) when the clouds are large enough for one-CTA-per-cloud sampling kernels to
+    // hold SMs for milliseconds beside this kernel; small clouds (N <= 2048: 0.1 ms samplings): one persistent CTA per SM
+    int64_t grid = (int64_t)DVCP_NUM_SMS * (N > 2048 ? DVCP_DFE_WAVES : 1);
     const int64_t nruns = (ntiles + TC_RUN - 1) / TC_RUN;
     if (grid > nruns) grid = nruns;
     // one cloud stride for the whole batch: tgt_xyz is addressed with b = candidate / Q

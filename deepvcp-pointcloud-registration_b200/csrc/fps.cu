@@ -100,6 +100,9 @@ __device__ __forceinline__ float warp_max_f(float v) {
 // Bucket j (32 consecutive points of the Hilbert order) belongs to warp j % WARPS,
 // slot j / WARPS: spatial neighbours are spread over the warps, so the few
 // buckets a round revisits are processed in parallel instead of by one warp.
+#ifdef DVCP_FPS_TIMING
+__device__ long long g_fb_stat[8];
+#endif
 template <int WARPS, int BPW, bool BATCHED, bool WIDE = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int64_t cs, int N,
@@ -354,6 +357,12 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
         }
         __syncthreads();
         int produced = 0;
+#ifdef DVCP_FPS_TIMING
+        long long t_last__ = clock64();
+#define FB_TICK(slot) do { if (b == 0 && tid == 0) { const long long now__ = clock64(); g_fb_stat[slot] += now__ - t_last__; t_last__ = now__; } } while (0)
+#else
+#define FB_TICK(slot)
+#endif
         while (true) {
             // ---- update: the A <= 64 centroids accepted in the previous step ----
             const int A = (int)s_nacc;
@@ -382,6 +391,9 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
                         const float d = sq3_nofma(__fsub_rn(x, c.x), __fsub_rn(y, c.y), __fsub_rn(z, c.z));
                         dk = d < dk ? d : dk;
                     } while (Fk);
+                    // the box test lets a centroid in that lowers nothing in about every other case: the bucket's
+                    // largest keys are then what they were
+                    if (!__any_sync(0xffffffffu, dk < dist[k])) continue;
                     dist[k] = dk;
                     const unsigned hi0 = __float_as_uint(dk);
                     const unsigned lo0 = ((0xffffu - ((idp[k >> 1] >> (16 * (k & 1))) & 0xffffu)) << 16) | (unsigned)pp;
@@ -402,6 +414,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
             }
             produced += A;
             if (produced >= npoint) break;
+            FB_TICK(4);
             // ---- S = largest third-best key over all buckets ----
             {
                 unsigned hi = lane < BPW ? tval : 0u, lo = lane < BPW ? tlo : 0u;
@@ -451,6 +464,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
                 }
                 break;
             }
+            FB_TICK(5);
             // ---- rank the candidates (number of larger keys; keys are distinct): the WCAP largest go to s_top in
             //      descending order with their coordinates, the next one is the threshold T. P adjacent lanes share a key ----
             {
@@ -483,8 +497,12 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
                 }
             }
             __syncthreads();
+            FB_TICK(6);
             const int m = n < WCAP ? n : WCAP;
             const unsigned long long T = n > WCAP ? s_T : S;
+#ifdef DVCP_FPS_TIMING
+            if (b == 0 && tid == 0) { g_fb_stat[0] += 1; g_fb_stat[1] += n; g_fb_stat[2] += A; }
+#endif
             // ---- pair tests: item (row r, part p) covers the earlier candidates 8p .. 8p+7 of candidate r ----
             for (int it = tid; it < WCAP * 8; it += THREADS) {
                 const int r = it & (WCAP - 1), part = it / WCAP;
@@ -508,6 +526,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
                 }
             }
             __syncthreads();
+            FB_TICK(7);
             if (warp == 0) {
                 // lane l resolves rows l and l + 32 (row r = word r / 32, bit r % 32 of the masks)
                 unsigned Kq[2][2], Lq[2][2];
@@ -581,6 +600,7 @@ fps_bucketed_kernel(const float *__restrict__ base, int64_t bs, int64_t ps, int6
                 }
             }
             __syncthreads();
+            FB_TICK(3);
         }
     } else {
         // ---- batched rounds (exact): several centroids per block-wide step ----
@@ -790,10 +810,10 @@ static int launch_bucketed(const dvcp_cloud_t &c, int B, int N, int npoint, cons
                            int64_t *o64, int32_t *o32, dvcp_cloud_index_t index, cudaStream_t st, bool consume) {
     if (fps_sequential_mode()) return launch_bucketed_impl<WARPS, BPW, false>(c, B, N, npoint, start, o64, o32, index, st, consume);
     if constexpr (WARPS == 16 && BPW == 32) {   // 16384 points, 512 buckets: two exposed keys per bucket, 64 candidates per step
-        static const bool narrow = [] { const char *e = getenv("DVCP_FPS_NARROW"); return e && e[0] == '1'; }();   // development: A / B
-        if (!narrow) return launch_bucketed_impl<WARPS, BPW, true, true>(c, B, N, npoint, start, o64, o32, index, st, consume);
+        return launch_bucketed_impl<WARPS, BPW, true, true>(c, B, N, npoint, start, o64, o32, index, st, consume);
     }
-    return launch_bucketed_impl<WARPS, BPW, true>(c, B, N, npoint, start, o64, o32, index, st, consume);
+    else
+        return launch_bucketed_impl<WARPS, BPW, true>(c, B, N, npoint, start, o64, o32, index, st, consume);
 }
 
 static int dispatch_bucketed(const dvcp_cloud_t &xyz, int B, int N, int npoint, const int64_t *start,
@@ -899,3 +919,12 @@ extern "C" int dvcp_fps_plain(dvcp_cloud_t xyz, int B, int N, int npoint, const 
     DVCP_CHECK_LAUNCH();
     return 0;
 }
+
+#ifdef DVCP_FPS_TIMING
+extern "C" __attribute__((visibility("default"))) int dvcp_debug_fps_bucketed_stat(long long *host8, int reset) {
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int rc = (int)cudaMemcpyFromSymbol(host8, dvcp::g_fb_stat, 8 * sizeof(long long));
+    if (reset) rc |= (int)cudaMemcpyToSymbol(dvcp::g_fb_stat, z, 8 * sizeof(long long));
+    return rc;
+}
+#endif
