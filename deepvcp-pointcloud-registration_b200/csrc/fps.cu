@@ -11,7 +11,11 @@
 //    members. A round only revisits buckets whose box lower bound -- evaluated
 //    with the same rounded arithmetic, hence never above any member's rounded
 //    distance -- is below the bucket's current maximum. Everything lives in
-//    shared memory / registers of ONE CTA per cloud; one __syncthreads per round.
+//    shared memory / registers of ONE CTA per cloud. The batched rounds accept
+//    many exact picks per block-wide step (one exposed key per bucket and 32
+//    candidates per step; at 16384 points the WIDE rounds: two exposed keys, 64
+//    candidates). With `consume` the cloud's index is read instead of rebuilt: the
+//    form dvcp_fps_indexed (concurrent = 2) uses for the throughput pipeline.
 //  * fps_generic_kernel   (float32/float64, any N <= 57344): plain O(N * npoint).
 #include <cstdlib>
 
