@@ -26,7 +26,8 @@
 // adds the two column halves in registers and takes the max over its 32 lanes with a transposing butterfly
 // (16 shuffles per 16 channels).
 //
-// Roles in a CTA (18 warps, one persistent CTA per SM, 3 operand stages + 3 TMEM accumulators of 64 columns):
+// Roles in a CTA (18 warps, one CTA per SM at a time -- 8 CTAs per SM slot for large clouds, see the launcher --,
+// 3 operand stages + 3 TMEM accumulators of 64 columns):
 //   warps 0-3   epilogue: warp w owns TMEM lanes 32w..32w+31 = candidate w of the tile: tcgen05.ld of
 //               16 + 16 columns at a time, add, max over the lanes, one coalesced 128-byte store;
 //   warps 4-15  producers, 3 groups of 4 (group g builds tiles g, g+3, ... into stage g): gather the
@@ -202,7 +203,8 @@ dfe_tgt_tc_kernel(const float *__restrict__ cand, Cloud txyz, const float *__res
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * TC_K; i += blockDim.x) {
         const int n = i / TC_K, k = i - n * TC_K;
-        const float w = Bhi[tc_off(n, k) / 4] + Blo[tc_off(n, k) / 4];
+        const float w = reinterpret_cast<const float *>(sB)[tc_off(n, k) / 4] +
+                        reinterpret_cast<const float *>(sB + TC_BW_BYTES)[tc_off(n, k) / 4];   // the copies made above
         *reinterpret_cast<__nv_bfloat16 *>(sW16 + tc_l16_off(n, k)) = __float2bfloat16_rn(w);
     }
     if (threadIdx.x == 0) {
