@@ -132,6 +132,27 @@ def make_inputs(dv, rank, B):
     return dv.synthetic.make_batch(w["kind"], ids, w["n_points"])
 
 
+def sm_time_accounting(kernels, B, fps_one_cta_ms, depth, sms=148):
+    """Why the pipelined step takes what it takes: the GPU is saturated, so the period is the sum of the
+    kernels' SM time over the SM count. The dense kernels fill all SMs for their event-timed duration; the sampling
+    holds one SM per cloud (2B clouds) at depth >= 3, about half of 122 SMs as clusters of 8 CTAs otherwise."""
+    try:
+        dense = {k: kernels[k]["ms"] * sms for k in ("knn", "dfe", "cpg") if k in kernels}
+        small = sum(kernels[k]["ms"] for k in ("sa_layer", "weighting_topk", "keypoint_candidates") if k in kernels) * sms
+        if depth >= 3 and fps_one_cta_ms:
+            samp = fps_one_cta_ms * 2 * B
+        else:
+            samp = kernels["fps"]["ms"] * 61
+        total = sum(dense.values()) + small + samp
+        out = {k + "_sm_ms": round(v, 1) for k, v in dense.items()}
+        out.update({"sampling_sm_ms": round(samp, 1), "small_kernels_sm_ms": round(small, 1), "sum_sm_ms": round(total, 1),
+                    "sum_over_sm_count_ms": round(total / sms, 3),
+                    "note": "event-timed duration alone x SMs held; compare sum_over_sm_count_ms with ms_per_step"})
+        return out
+    except Exception as e:   # accounting only: never fail the bench line
+        return {"error": repr(e)}
+
+
 def time_streamed(torch, pipe, dev, rot, d_R, d_t, starts, steps, barrier=None):
     """K steps through the streamed API, CUDA events on the current stream around them. Returns ms."""
     cur = torch.cuda.current_stream(dev)
@@ -427,6 +448,7 @@ def run_ours(args):
                                    % (type(pipe).__name__, args.depth, len(pipe.fe_streams), pipe.sampling),
                        "parallelism": "pairs sharded by rank, all-gather of poses only"},
             "latency_ms_per_step_unpipelined": round(latency_ms, 4),
+            "sm_time_accounting": sm_time_accounting(kernels, B, fps_mode2_ms, args.depth),
             "roofline": roofline, "kernels": kernels,
             "e2e": {"value": round(pairs / (e2e_ms * 1e-3 / args.steps), 3), "unit": "pairs/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_pose.numel() * 8},
