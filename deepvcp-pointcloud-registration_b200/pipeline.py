@@ -13,8 +13,8 @@ starts, so the sampling coincides with the KNN of the previous batch and is over
 that batch's embedding / CPG kernels want the whole GPU.
 
 depth >= 3 (what bench.py uses) trades latency for throughput: the sampling runs as ONE CTA per
-cloud (dvcp_fps_indexed, concurrent = 2: 4.7 ms instead of 2.3 ms for the 16 clouds of a K8 batch, but
-16 SMs instead of 122, a third of the SM time), and the feature halves of depth - 1 batches are in
+cloud (dvcp_fps_indexed, concurrent = 2: 3.8 ms instead of 2.3 ms for the 16 clouds of a K8 batch, but
+16 SMs instead of 122, under half the SM time), and the feature halves of depth - 1 batches are in
 flight at once on their own streams beside the match half of an earlier batch:
 
     feature stream 0   FE(0)......  FE(2)......  FE(4)......
@@ -23,7 +23,8 @@ flight at once on their own streams beside the match half of an earlier batch:
 
 The sampling CTAs hold their SMs for milliseconds, which is why the embedding and CPG kernels are
 launched as several CTAs per SM slot (common.cuh, DVCP_DFE_WAVES): whichever SMs are free take the
-work. K8 on one B200: 3.69 -> 3.28 ms per batch. Each batch still
+work; the short launches at the head of the match half (DeepVCP.match_select) run at the end of the
+feature half. K8 on one B200: 3.69 -> 3.10 ms per batch. Each batch still
 runs the complete path (DeepVCP.forward + svd_optimization, deepVCP.py:24-110,
 deepVCP_loss.py:57-90) and results come back in submission order; nothing is shared
 between batches except the read-only weights. The reference has no counterpart (batch

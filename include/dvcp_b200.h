@@ -104,7 +104,7 @@ DVCP_API int dvcp_fps(dvcp_cloud_t xyz, int dtype, int B, int N, int npoint, con
  * concurrent: how the sampling shares the GPU with other work (a stream of batches); same results in every mode.
  *   0  few large clouds are spread over clusters of 8 CTAs each (shortest kernel: 2.3 ms for 16 clouds of 16384);
  *   1  the same with half-size CTAs;
- *   2  ONE CTA per cloud (4.7 ms for any number of clouds up to the SM count, but a third of the SM time of mode 0):
+ *   2  ONE CTA per cloud (3.8 ms for any number of clouds up to the SM count, but under half the SM time of mode 0):
  *      for throughput, with the feature halves of several batches in flight (GraphedRegistration, depth >= 3). */
 DVCP_API int dvcp_fps_indexed(dvcp_cloud_t xyz, int B, int N, int npoint, const int64_t *start, int64_t *out64,
                      int32_t *out32, dvcp_cloud_index_t index, int concurrent, dvcp_stream_t stream);
