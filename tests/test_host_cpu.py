@@ -197,3 +197,24 @@ def test_modelnet_loader_host_logic(pkg, tmp_path):
         mn.ingest([a], device="cpu")
     with pytest.raises(RuntimeError):
         pkg.KITTIDataset.voxel_grid_filter(torch.zeros(8, 5), 0.1)
+
+
+def test_pipeline_shape_defaults_and_errors(pkg):
+    """Host logic of the throughput pipeline (pipeline.py): depth -> feature streams / sampling mode, the automatic
+    depth per cloud size, argument errors, and no CPU fallback."""
+    pipeline = importlib.import_module(PKG + ".pipeline")
+    assert pipeline._pipeline_shape(1, None, None) == (1, 0)      # one batch at a time: clusters
+    assert pipeline._pipeline_shape(2, None, None) == (1, 0)      # FE(k+1) beside M(k): clusters
+    assert pipeline._pipeline_shape(3, None, None) == (2, 2)      # two feature halves in flight, one CTA per cloud
+    assert pipeline._pipeline_shape(4, None, None) == (3, 2)
+    assert pipeline._pipeline_shape(3, 1, 0) == (1, 0)            # explicit values win
+    for bad in ((0, None, None), (3, 0, None), (3, None, 3)):
+        with pytest.raises(ValueError):
+            pipeline._pipeline_shape(*bad)
+    assert pipeline.auto_depth(1024) == 2 and pipeline.auto_depth(2048) == 2      # short samplings: plain overlap
+    assert pipeline.auto_depth(4096) == 3 and pipeline.auto_depth(16384) == 3     # long samplings: depth 3
+    dv = importlib.import_module(PKG)
+    model = dv.DeepVCP(use_normal=False, npoint=1024, r=0.8, s=0.4).eval()         # parameters on the CPU
+    for make in (lambda: dv.StreamedRegistration(model, depth=3), lambda: dv.GraphedRegistration(model, 2, 3, 1024)):
+        with pytest.raises(RuntimeError):
+            make()
